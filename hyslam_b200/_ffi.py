@@ -1,0 +1,140 @@
+"""ctypes binding of libhyorb.so (include/hyorb.h).  No torch types cross the boundary: numpy arrays for the
+``_host`` entry points, raw device addresses (ints) for the ``_device`` ones.
+
+The library is built in-tree (hyslam_b200/lib/libhyorb.so) by ``build()`` / ``__graft_entry__.build()``.
+There is no CPU fallback: a missing library or a missing CUDA device raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhyorb.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+OK, EINVAL, ECAPACITY, EUNSUPPORTED, ENOMEM, ECUDA = 0, -1, -2, -3, -4, -5
+MAX_LEVELS = 16
+GRID_COLS, GRID_ROWS = 64, 48
+RULE_LANDMARK, RULE_BOW, RULE_MONOINIT = 0, 1, 2
+DBG_PYRAMID, DBG_BLURRED, DBG_CANDIDATES, DBG_LEVEL_COUNT = 0, 1, 2, 3
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+WQ_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("r", "<f4"), ("size_lo", "<f4"), ("size_hi", "<f4"),
+                     ("ur", "<f4"), ("ur_radius", "<f4")])
+assert KP_DTYPE.itemsize == 28 and WQ_DTYPE.itemsize == 28
+
+
+class ExtractorParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32), ("cell_px", C.c_int32),
+                ("ini_th", C.c_int32), ("min_th", C.c_int32), ("flags", C.c_uint32)]
+
+
+class StereoParams(C.Structure):
+    _fields_ = [("mbf", C.c_float), ("fx", C.c_float), ("n_rows", C.c_int32), ("th_high", C.c_float),
+                ("th_low", C.c_float), ("size_ref", C.c_float)]
+
+
+class Bounds(C.Structure):
+    _fields_ = [("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
+
+
+class HyorbError(RuntimeError):
+    def __init__(self, rc, msg):
+        super().__init__(f"hyorb rc={rc}: {msg}")
+        self.rc = rc
+
+
+# every symbol include/hyorb.h declares (tests/test_abi.py checks the library exports exactly these)
+SYMBOLS = [
+    "hyorb_extractor_create", "hyorb_extractor_destroy", "hyorb_extractor_get_levels", "hyorb_extractor_get_scales",
+    "hyorb_extract_host", "hyorb_extract_batch_host", "hyorb_extract_batch_device", "hyorb_extractor_sync",
+    "hyorb_extractor_level_size", "hyorb_extractor_debug_read", "hyorb_extractor_launch_count",
+    "hyorb_matcher_create", "hyorb_matcher_destroy", "hyorb_matcher_sync", "hyorb_matcher_launch_count",
+    "hyorb_stereo_match_host", "hyorb_stereo_match_batch_device", "hyorb_match_csr_host",
+    "hyorb_match_bruteforce_device", "hyorb_grid_build_host", "hyorb_match_window_host",
+    "hyorb_rotation_consistency_host", "hyorb_last_error", "hyorb_version", "hyorb_device_count",
+]
+
+
+def build(force=False, verbose=False):
+    """Compile libhyorb.so for sm_100a with nvcc (cross-compiles without a GPU).  Idempotent."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    srcs += [os.path.join(_HERE, "..", "include", f) for f in ("hyorb.h", "hyorb_brief_pattern.inc")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise RuntimeError("building libhyorb.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the library (never builds implicitly on a GPU box: the .so ships with the tree)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.hyorb_last_error.restype = C.c_char_p
+        L.hyorb_version.restype = C.c_char_p
+        L.hyorb_extractor_debug_read.restype = C.c_long
+        L.hyorb_extractor_launch_count.restype = C.c_long
+        L.hyorb_matcher_launch_count.restype = C.c_long
+        L.hyorb_extractor_debug_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        L.hyorb_extract_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.hyorb_extract_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t,
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.hyorb_extract_batch_device.argtypes = L.hyorb_extract_batch_host.argtypes
+        L.hyorb_extractor_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hyorb_extractor_destroy.argtypes = [C.c_void_p]
+        L.hyorb_extractor_sync.argtypes = [C.c_void_p]
+        L.hyorb_extractor_get_levels.argtypes = [C.c_void_p]
+        L.hyorb_extractor_launch_count.argtypes = [C.c_void_p]
+        L.hyorb_extractor_get_scales.argtypes = [C.c_void_p] * 6
+        L.hyorb_extractor_level_size.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.hyorb_matcher_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.hyorb_matcher_destroy.argtypes = [C.c_void_p]
+        L.hyorb_matcher_sync.argtypes = [C.c_void_p]
+        L.hyorb_matcher_launch_count.argtypes = [C.c_void_p]
+        L.hyorb_stereo_match_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hyorb_stereo_match_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hyorb_match_csr_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hyorb_match_bruteforce_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hyorb_grid_build_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hyorb_match_window_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hyorb_rotation_consistency_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise HyorbError(rc, lib().hyorb_last_error().decode())
+    return rc
+
+
+def ptr(a):
+    """address of a numpy array (or pass through None / int device pointers)"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    return a.ctypes.data
+
+
+def device_count():
+    return lib().hyorb_device_count()

@@ -1,0 +1,598 @@
+// api.cu -- the C ABI of libhyorb (include/hyorb.h): handles, workspaces, staging, status plumbing.
+// Host side of the drop-in: what ORBExtractor / Stereomatcher / FeatureMatcher objects own in the reference
+// (per-object pyramid + scratch, src/features/ORBExtractor.h:102) lives in a handle here; nothing is global.
+#include <string.h>
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace hyorb {
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return HYORB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) -> %s", bytes, cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? HYORB_ENOMEM : HYORB_ECUDA; }
+        cap = bytes;
+        return HYORB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+static int status_to_rc(int st)
+{
+    if (st == 0) return HYORB_OK;
+    if (st & (ST_CAND_OVERFLOW | ST_SEL_OVERFLOW | ST_OUT_OVERFLOW)) {
+        set_error("device buffer overflow (status 0x%x): %s%s%s", st, (st & ST_CAND_OVERFLOW) ? "FAST candidate list " : "",
+                  (st & ST_SEL_OVERFLOW) ? "quadtree leaf list " : "", (st & ST_OUT_OVERFLOW) ? "output capacity" : "");
+        return HYORB_ECAPACITY;
+    }
+    if (st & (ST_QT_LIMIT | ST_QT_MISMATCH)) { set_error("quadtree kernel limit / consistency check failed (status 0x%x)", st); return HYORB_EUNSUPPORTED; }
+    if (st & ST_BAD_INDEX) { set_error("candidate index or rotation bin out of range"); return HYORB_EINVAL; }
+    if (st & ST_ROW_RANGE) { set_error("stereo: keypoint row band outside [0, n_rows) (the reference writes out of bounds here)"); return HYORB_EINVAL; }
+    set_error("device status 0x%x", st);
+    return HYORB_ECUDA;
+}
+
+}  // namespace hyorb
+
+using namespace hyorb;
+
+struct hyorb_extractor {
+    hyorb_extractor_params params;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    float scale[HYORB_MAX_LEVELS], inv[HYORB_MAX_LEVELS], sigma2[HYORB_MAX_LEVELS], inv_sigma2[HYORB_MAX_LEVELS];
+    int quota[HYORB_MAX_LEVELS];
+    HostPlan plan;
+    bool have_plan = false;
+    DevBuf d_plan, d_resize, d_lut;
+    int Bcap = 0;
+    DevBuf d_pyr, d_blur, d_cand, d_qcode, d_qnode, d_qleaf, d_sel, d_candCount, d_selCount, d_status;
+    DevBuf d_in, d_kps, d_desc, d_counts;       // staging of the _host entry points
+    long launches = 0;
+    // last call (for debug_read)
+    int last_B = 0;
+    Level0 last_l0{nullptr, 0, 0};
+};
+
+static int ex_ensure_plan(hyorb_extractor *h, int w, int hgt)
+{
+    if (h->have_plan && h->plan.dev.width == w && h->plan.dev.height == hgt) return HYORB_OK;
+    HostPlan np;
+    HY_TRY(build_plan(h->params, w, hgt, &np));
+    HY_TRY(h->d_plan.ensure(sizeof(PlanDev)));
+    HY_TRY(h->d_resize.ensure(sizeof(ResizeTab) * std::max<size_t>(np.resize.size(), 1)));
+    HY_TRY(h->d_lut.ensure(sizeof(uint32_t) * std::max<size_t>(np.lut.size(), 1)));
+    // the tables must not be overwritten while earlier launches may still read them
+    HY_CUDA(cudaStreamSynchronize(h->stream));
+    h->plan = np;
+    HY_CUDA(cudaMemcpyAsync(h->d_plan.p, &h->plan.dev, sizeof(PlanDev), cudaMemcpyHostToDevice, h->stream));
+    if (!np.resize.empty()) HY_CUDA(cudaMemcpyAsync(h->d_resize.p, h->plan.resize.data(), sizeof(ResizeTab) * np.resize.size(), cudaMemcpyHostToDevice, h->stream));
+    HY_CUDA(cudaMemcpyAsync(h->d_lut.p, h->plan.lut.data(), sizeof(uint32_t) * np.lut.size(), cudaMemcpyHostToDevice, h->stream));
+    HY_CUDA(cudaStreamSynchronize(h->stream));
+    h->have_plan = true;
+    h->Bcap = 0;
+    return HYORB_OK;
+}
+
+static int ex_ensure_workspace(hyorb_extractor *h, int B)
+{
+    if (B <= h->Bcap) return HYORB_OK;
+    HY_CUDA(cudaStreamSynchronize(h->stream));
+    const PlanDev &P = h->plan.dev;
+    HY_TRY(h->d_pyr.ensure((size_t)P.pyrStride * B + 256));
+    HY_TRY(h->d_blur.ensure((size_t)P.pyrStride * B + 256));
+    HY_TRY(h->d_cand.ensure(sizeof(uint32_t) * (size_t)P.candStride * B));
+    HY_TRY(h->d_qcode.ensure(sizeof(uint32_t) * (size_t)P.candStride * B));
+    HY_TRY(h->d_qnode.ensure(sizeof(uint16_t) * (size_t)P.candStride * B));
+    HY_TRY(h->d_qleaf.ensure(sizeof(uint2) * (size_t)P.selStride * B));
+    HY_TRY(h->d_sel.ensure(sizeof(uint32_t) * (size_t)P.selStride * B));
+    HY_TRY(h->d_candCount.ensure(sizeof(int) * HYORB_MAX_LEVELS * (size_t)B));
+    HY_TRY(h->d_selCount.ensure(sizeof(int) * HYORB_MAX_LEVELS * (size_t)B));
+    if (!h->d_status.p) {
+        HY_TRY(h->d_status.ensure(sizeof(int)));
+        HY_CUDA(cudaMemsetAsync(h->d_status.p, 0, sizeof(int), h->stream));
+    }
+    h->Bcap = B;
+    return HYORB_OK;
+}
+
+static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_keypoint *d_kps, uint8_t *d_desc, int capacity, int32_t *d_counts)
+{
+    HY_CUDA(cudaSetDevice(h->device));
+    HY_TRY(ex_ensure_plan(h, w, hgt));
+    HY_TRY(ex_ensure_workspace(h, B));
+    const PlanDev &P = h->plan.dev;
+    const PlanDev *dp = h->d_plan.as<PlanDev>();
+    cudaStream_t st = h->stream;
+    HY_CUDA(cudaMemsetAsync(h->d_candCount.p, 0, sizeof(int) * HYORB_MAX_LEVELS * (size_t)B, st));
+    HY_TRY(launch_pyramid(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_resize.as<ResizeTab>(), B, st, &h->launches));
+    HY_TRY(launch_fast(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_cand.as<uint32_t>(), h->d_candCount.as<int>(), h->d_status.as<int>(), B, st, &h->launches));
+    HY_TRY(launch_quadtree(P, dp, h->d_cand.as<uint32_t>(), h->d_candCount.as<int>(), h->d_lut.as<uint32_t>(), h->d_qcode.as<uint32_t>(),
+                           h->d_qnode.as<uint16_t>(), h->d_qleaf.as<uint2>(), h->d_sel.as<uint32_t>(), h->d_selCount.as<int>(),
+                           h->d_status.as<int>(), B, st, &h->launches));
+    HY_TRY(launch_blur(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_blur.as<uint8_t>(), B, st, &h->launches));
+    HY_TRY(launch_describe(P, dp, h->d_blur.as<uint8_t>(), h->d_sel.as<uint32_t>(), h->d_selCount.as<int>(), d_kps, d_desc, capacity, d_counts,
+                           h->d_status.as<int>(), B, st, &h->launches));
+    h->last_B = B; h->last_l0 = l0;
+    return HYORB_OK;
+}
+
+static int ex_sync(hyorb_extractor *h)
+{
+    int st = 0;
+    if (h->d_status.p) {
+        HY_CUDA(cudaMemcpyAsync(&st, h->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        HY_CUDA(cudaStreamSynchronize(h->stream));
+        if (st) HY_CUDA(cudaMemsetAsync(h->d_status.p, 0, sizeof(int), h->stream));
+    } else {
+        HY_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return status_to_rc(st);
+}
+
+extern "C" {
+
+HYORB_API const char *hyorb_last_error(void) { return hyorb::last_error(); }
+HYORB_API const char *hyorb_version(void) { return "hyorb-b200 0.1 (sm_100a)"; }
+HYORB_API int hyorb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+HYORB_API int hyorb_extractor_create(const hyorb_extractor_params *params, int device, void *cuda_stream, hyorb_extractor **out)
+{
+    if (!params || !out) { set_error("null argument"); return HYORB_EINVAL; }
+    *out = nullptr;
+    if (params->flags != 0) { set_error("flags must be 0"); return HYORB_EINVAL; }
+    if (params->nfeatures < 1) { set_error("nfeatures must be >= 1"); return HYORB_EINVAL; }
+    hyorb_extractor *h = new (std::nothrow) hyorb_extractor();
+    if (!h) return HYORB_ENOMEM;
+    h->params = *params;
+    int rc = scale_tables(*params, h->scale, h->inv, h->sigma2, h->inv_sigma2, h->quota);
+    if (rc) { delete h; return rc; }
+    if (hyorb_device_count() <= device || device < 0) { set_error("CUDA device %d not available (no CPU fallback exists)", device); delete h; return HYORB_ECUDA; }
+    h->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) {
+        if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
+        else { e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking); h->own_stream = true; }
+    }
+    if (e != cudaSuccess) { set_error("CUDA init: %s", cudaGetErrorString(e)); delete h; return HYORB_ECUDA; }
+    *out = h;
+    return HYORB_OK;
+}
+
+HYORB_API int hyorb_extractor_destroy(hyorb_extractor *h)
+{
+    if (!h) return HYORB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->d_plan, &h->d_resize, &h->d_lut, &h->d_pyr, &h->d_blur, &h->d_cand, &h->d_qcode, &h->d_qnode, &h->d_qleaf, &h->d_sel,
+                      &h->d_candCount, &h->d_selCount, &h->d_status, &h->d_in, &h->d_kps, &h->d_desc, &h->d_counts};
+    for (DevBuf *b : bufs) b->release();
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return HYORB_OK;
+}
+
+HYORB_API int hyorb_extractor_get_levels(const hyorb_extractor *h) { return h ? h->params.nlevels : HYORB_EINVAL; }
+
+HYORB_API int hyorb_extractor_get_scales(const hyorb_extractor *h, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2, int32_t *quota)
+{
+    if (!h) { set_error("null handle"); return HYORB_EINVAL; }
+    for (int i = 0; i < h->params.nlevels; i++) {
+        if (scale) scale[i] = h->scale[i];
+        if (inv_scale) inv_scale[i] = h->inv[i];
+        if (sigma2) sigma2[i] = h->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->inv_sigma2[i];
+        if (quota) quota[i] = h->quota[i];
+    }
+    return HYORB_OK;
+}
+
+HYORB_API int hyorb_extract_batch_device(hyorb_extractor *h, const uint8_t *d_images, int n_images, int width, int height, int stride,
+                                         size_t image_stride, hyorb_keypoint *d_kps, uint8_t *d_desc, int capacity, int32_t *d_counts)
+{
+    if (!h || !d_images || !d_kps || !d_desc || !d_counts) { set_error("null argument"); return HYORB_EINVAL; }
+    if (n_images < 1 || width < 1 || height < 1 || stride < width || capacity < 1) { set_error("bad shape"); return HYORB_EINVAL; }
+    if (n_images > 65535) { set_error("at most 65535 images per batch"); return HYORB_EUNSUPPORTED; }
+    Level0 l0{d_images, stride, (unsigned long long)image_stride};
+    return ex_run(h, l0, n_images, width, height, d_kps, d_desc, capacity, d_counts);
+}
+
+HYORB_API int hyorb_extractor_sync(hyorb_extractor *h)
+{
+    if (!h) { set_error("null handle"); return HYORB_EINVAL; }
+    HY_CUDA(cudaSetDevice(h->device));
+    return ex_sync(h);
+}
+
+HYORB_API int hyorb_extract_batch_host(hyorb_extractor *h, const uint8_t *images, int n_images, int width, int height, int stride,
+                                       size_t image_stride, hyorb_keypoint *kps, uint8_t *desc, int capacity, int32_t *counts)
+{
+    if (!h || !images || !kps || !desc || !counts) { set_error("null argument"); return HYORB_EINVAL; }
+    if (n_images < 1 || width < 1 || height < 1 || stride < width || capacity < 1) { set_error("bad shape"); return HYORB_EINVAL; }
+    if (n_images > 65535) { set_error("at most 65535 images per batch"); return HYORB_EUNSUPPORTED; }
+    HY_CUDA(cudaSetDevice(h->device));
+    HY_TRY(ex_ensure_plan(h, width, height));
+    const PlanDev &P = h->plan.dev;
+    const int pitch = P.lv[0].pitch;
+    const size_t dstride = ((size_t)pitch * height + 255) & ~(size_t)255;
+    HY_TRY(h->d_in.ensure(dstride * n_images + 256));
+    HY_TRY(h->d_kps.ensure(sizeof(hyorb_keypoint) * (size_t)capacity * n_images));
+    HY_TRY(h->d_desc.ensure((size_t)HYORB_DESC_BYTES * capacity * n_images));
+    HY_TRY(h->d_counts.ensure(sizeof(int32_t) * n_images));
+    if ((size_t)stride * height == image_stride && n_images > 1) {
+        // images are back to back: one 2D copy over all rows of the batch is not possible with a padded destination stride,
+        // so fall through to per-image copies unless the destination is equally dense
+    }
+    for (int i = 0; i < n_images; i++)
+        HY_CUDA(cudaMemcpy2DAsync(h->d_in.as<uint8_t>() + dstride * i, pitch, images + image_stride * i, stride, width, height,
+                                  cudaMemcpyHostToDevice, h->stream));
+    Level0 l0{h->d_in.as<uint8_t>(), pitch, (unsigned long long)dstride};
+    HY_TRY(ex_run(h, l0, n_images, width, height, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), capacity, h->d_counts.as<int32_t>()));
+    HY_CUDA(cudaMemcpyAsync(counts, h->d_counts.p, sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, h->stream));
+    HY_CUDA(cudaMemcpyAsync(kps, h->d_kps.p, sizeof(hyorb_keypoint) * (size_t)capacity * n_images, cudaMemcpyDeviceToHost, h->stream));
+    HY_CUDA(cudaMemcpyAsync(desc, h->d_desc.p, (size_t)HYORB_DESC_BYTES * capacity * n_images, cudaMemcpyDeviceToHost, h->stream));
+    return ex_sync(h);
+}
+
+HYORB_API int hyorb_extract_host(hyorb_extractor *h, const uint8_t *gray, int width, int height, int stride, hyorb_keypoint *kps,
+                                 uint8_t *desc, int capacity, int *n)
+{
+    if (!h || !n) { set_error("null argument"); return HYORB_EINVAL; }
+    *n = 0;
+    if (!gray || width <= 0 || height <= 0) return HYORB_OK;     // ORBExtractor.cpp:499-500: empty image -> silent return
+    if (!kps || !desc || capacity < 1 || stride < width) { set_error("bad argument"); return HYORB_EINVAL; }
+    HY_CUDA(cudaSetDevice(h->device));
+    HY_TRY(ex_ensure_plan(h, width, height));
+    const PlanDev &P = h->plan.dev;
+    const int pitch = P.lv[0].pitch;
+    HY_TRY(h->d_in.ensure((size_t)pitch * height + 512));
+    HY_TRY(h->d_kps.ensure(sizeof(hyorb_keypoint) * (size_t)capacity));
+    HY_TRY(h->d_desc.ensure((size_t)HYORB_DESC_BYTES * capacity));
+    HY_TRY(h->d_counts.ensure(sizeof(int32_t)));
+    HY_CUDA(cudaMemcpy2DAsync(h->d_in.p, pitch, gray, stride, width, height, cudaMemcpyHostToDevice, h->stream));
+    Level0 l0{h->d_in.as<uint8_t>(), pitch, (unsigned long long)pitch * height};
+    HY_TRY(ex_run(h, l0, 1, width, height, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), capacity, h->d_counts.as<int32_t>()));
+    int32_t cnt = 0;
+    HY_CUDA(cudaMemcpyAsync(&cnt, h->d_counts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    HY_TRY(ex_sync(h));
+    if (cnt > 0) {
+        HY_CUDA(cudaMemcpyAsync(kps, h->d_kps.p, sizeof(hyorb_keypoint) * (size_t)cnt, cudaMemcpyDeviceToHost, h->stream));
+        HY_CUDA(cudaMemcpyAsync(desc, h->d_desc.p, (size_t)HYORB_DESC_BYTES * cnt, cudaMemcpyDeviceToHost, h->stream));
+        HY_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    *n = cnt;
+    return HYORB_OK;
+}
+
+HYORB_API int hyorb_extractor_level_size(hyorb_extractor *h, int width, int height, int level, int *lw, int *lh)
+{
+    if (!h || level < 0 || level >= h->params.nlevels) { set_error("bad argument"); return HYORB_EINVAL; }
+    const int w = (int)lrintf((float)width * h->inv[level]), hh = (int)lrintf((float)height * h->inv[level]);   // ORBExtractor.cpp:569
+    if (lw) *lw = w;
+    if (lh) *lh = hh;
+    return HYORB_OK;
+}
+
+HYORB_API long hyorb_extractor_launch_count(const hyorb_extractor *h) { return h ? h->launches : 0; }
+
+HYORB_API long hyorb_extractor_debug_read(hyorb_extractor *h, int image_index, int what, int level, void *dst, size_t dst_bytes)
+{
+    if (!h || !dst || !h->have_plan || image_index < 0 || image_index >= h->last_B || level < 0 || level >= h->plan.dev.nlevels) {
+        set_error("debug_read: bad argument or no previous extract call");
+        return HYORB_EINVAL;
+    }
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("debug_read: CUDA error"); return HYORB_ECUDA; }
+    const PlanDev &P = h->plan.dev;
+    const LevelDev &L = P.lv[level];
+    switch (what) {
+    case HYORB_DBG_PYRAMID:
+    case HYORB_DBG_BLURRED: {
+        const size_t need = (size_t)L.w * L.h;
+        if (dst_bytes < need) { set_error("debug_read: need %zu bytes", need); return HYORB_ECAPACITY; }
+        const uint8_t *src; int pitch;
+        if (what == HYORB_DBG_BLURRED) { src = h->d_blur.as<uint8_t>() + (size_t)P.pyrStride * image_index + L.off; pitch = L.pitch; }
+        else if (level == 0) { src = h->last_l0.base + (size_t)h->last_l0.stride * image_index; pitch = h->last_l0.pitch; }
+        else { src = h->d_pyr.as<uint8_t>() + (size_t)P.pyrStride * image_index + L.off; pitch = L.pitch; }
+        if (cudaMemcpy2D(dst, L.w, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("debug_read: copy failed"); return HYORB_ECUDA; }
+        return (long)need;
+    }
+    case HYORB_DBG_CANDIDATES: {
+        int cnt = 0;
+        if (cudaMemcpy(&cnt, h->d_candCount.as<int>() + image_index * HYORB_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return HYORB_ECUDA;
+        if (cnt > L.candCap) cnt = L.candCap;
+        const size_t need = sizeof(int32_t) * 3 * (size_t)cnt;
+        if (dst_bytes < need) { set_error("debug_read: need %zu bytes", need); return HYORB_ECAPACITY; }
+        std::vector<uint32_t> c(cnt);
+        if (cnt && cudaMemcpy(c.data(), h->d_cand.as<uint32_t>() + (size_t)P.candStride * image_index + L.candOff, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return HYORB_ECUDA;
+        std::sort(c.begin(), c.end(), [&](uint32_t a, uint32_t b) {
+            return cand_order_key(cand_x(a), cand_y(a), L.wCell, L.hCell, L.nCols) < cand_order_key(cand_x(b), cand_y(b), L.wCell, L.hCell, L.nCols);
+        });
+        int32_t *o = (int32_t *)dst;
+        for (int i = 0; i < cnt; i++) { o[3 * i] = cand_x(c[i]); o[3 * i + 1] = cand_y(c[i]); o[3 * i + 2] = cand_resp(c[i]); }
+        return (long)need;
+    }
+    case HYORB_DBG_LEVEL_COUNT: {
+        if (dst_bytes < sizeof(int32_t)) return HYORB_ECAPACITY;
+        if (cudaMemcpy(dst, h->d_selCount.as<int>() + image_index * HYORB_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return HYORB_ECUDA;
+        return (long)sizeof(int32_t);
+    }
+    default: set_error("debug_read: unknown selector %d", what); return HYORB_EINVAL;
+    }
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// matcher handle
+// =====================================================================================================
+struct hyorb_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long launches = 0;
+    DevBuf d_status, d_a, d_b, d_c, d_d, d_e, d_f, d_g, d_h, d_i, d_j, d_k, d_l;   // generic staging slots
+    DevBuf d_pkey, d_psecond, d_rowtab, d_bestd, d_cellof, d_cellcnt;
+};
+
+static int m_prepare(hyorb_matcher *m)
+{
+    if (!m) { set_error("null matcher handle"); return HYORB_EINVAL; }
+    HY_CUDA(cudaSetDevice(m->device));
+    if (!m->d_status.p) {
+        HY_TRY(m->d_status.ensure(sizeof(int)));
+        HY_CUDA(cudaMemsetAsync(m->d_status.p, 0, sizeof(int), m->stream));
+    }
+    return HYORB_OK;
+}
+static int m_sync(hyorb_matcher *m)
+{
+    int st = 0;
+    HY_CUDA(cudaMemcpyAsync(&st, m->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaStreamSynchronize(m->stream));
+    if (st) HY_CUDA(cudaMemsetAsync(m->d_status.p, 0, sizeof(int), m->stream));
+    return status_to_rc(st);
+}
+static int m_upload(hyorb_matcher *m, DevBuf &buf, const void *src, size_t bytes)
+{
+    HY_TRY(buf.ensure(std::max<size_t>(bytes, 16)));
+    if (bytes) HY_CUDA(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, m->stream));
+    return HYORB_OK;
+}
+static int bf_splits(int nq, int nt)
+{
+    // enough CTAs to fill 148 SMs a few times over, without slicing the target list below one smem tile
+    const int qblocks = (nq + 127) / 128;
+    int s = (148 * 8 + qblocks - 1) / qblocks;
+    const int maxs = std::max(1, nt / 128);
+    return std::max(1, std::min(s, std::min(maxs, 64)));
+}
+
+extern "C" {
+
+HYORB_API int hyorb_matcher_create(int device, void *cuda_stream, hyorb_matcher **out)
+{
+    if (!out) { set_error("null argument"); return HYORB_EINVAL; }
+    *out = nullptr;
+    if (device < 0 || hyorb_device_count() <= device) { set_error("CUDA device %d not available (no CPU fallback exists)", device); return HYORB_ECUDA; }
+    hyorb_matcher *m = new (std::nothrow) hyorb_matcher();
+    if (!m) return HYORB_ENOMEM;
+    m->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) {
+        if (cuda_stream) m->stream = (cudaStream_t)cuda_stream;
+        else { e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking); m->own_stream = true; }
+    }
+    if (e != cudaSuccess) { set_error("CUDA init: %s", cudaGetErrorString(e)); delete m; return HYORB_ECUDA; }
+    *out = m;
+    return HYORB_OK;
+}
+
+HYORB_API int hyorb_matcher_destroy(hyorb_matcher *m)
+{
+    if (!m) return HYORB_OK;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    DevBuf *bufs[] = {&m->d_status, &m->d_a, &m->d_b, &m->d_c, &m->d_d, &m->d_e, &m->d_f, &m->d_g, &m->d_h, &m->d_i, &m->d_j, &m->d_k, &m->d_l,
+                      &m->d_pkey, &m->d_psecond, &m->d_rowtab, &m->d_bestd, &m->d_cellof, &m->d_cellcnt};
+    for (DevBuf *b : bufs) b->release();
+    if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return HYORB_OK;
+}
+
+HYORB_API int hyorb_matcher_sync(hyorb_matcher *m) { HY_TRY(m_prepare(m)); return m_sync(m); }
+HYORB_API long hyorb_matcher_launch_count(const hyorb_matcher *m) { return m ? m->launches : 0; }
+
+HYORB_API int hyorb_match_bruteforce_device(hyorb_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int rule, float thr,
+                                            float ratio, int32_t *d_best_idx, uint16_t *d_best, uint16_t *d_second, uint8_t *d_accepted)
+{
+    HY_TRY(m_prepare(m));
+    if (nq < 0 || nt < 0 || rule < 0 || rule > 2) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (nq == 0) return HYORB_OK;
+    const int ns = bf_splits(nq, nt);
+    HY_TRY(m->d_pkey.ensure(sizeof(uint32_t) * (size_t)ns * nq));
+    HY_TRY(m->d_psecond.ensure(sizeof(uint16_t) * (size_t)ns * nq));
+    return launch_match_bruteforce(d_q, nq, d_t, nt, rule, thr, ratio, d_best_idx, d_best, d_second, d_accepted, m->d_pkey.as<uint32_t>(),
+                                   m->d_psecond.as<uint16_t>(), ns, m->stream, &m->launches);
+}
+
+HYORB_API int hyorb_match_csr_host(hyorb_matcher *m, const uint8_t *q_desc, int nq, const uint8_t *t_desc, int nt, const int32_t *cand_off,
+                                   const int32_t *cand_idx, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best,
+                                   uint16_t *second, uint8_t *accepted)
+{
+    HY_TRY(m_prepare(m));
+    if (nq < 0 || nt < 0 || rule < 0 || rule > 2 || (cand_off == nullptr) != (cand_idx == nullptr)) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (nq == 0) return HYORB_OK;
+    if (!q_desc || (nt > 0 && !t_desc) || !best_idx || !best || !second || !accepted) { set_error("null argument"); return HYORB_EINVAL; }
+    HY_TRY(m_upload(m, m->d_a, q_desc, (size_t)nq * 32));
+    HY_TRY(m_upload(m, m->d_b, t_desc, (size_t)nt * 32));
+    HY_TRY(m->d_c.ensure(sizeof(int32_t) * (size_t)nq));
+    HY_TRY(m->d_d.ensure(sizeof(uint16_t) * (size_t)nq));
+    HY_TRY(m->d_e.ensure(sizeof(uint16_t) * (size_t)nq));
+    HY_TRY(m->d_f.ensure((size_t)nq));
+    if (cand_off) {
+        const int total = cand_off[nq];
+        if (cand_off[0] != 0 || total < 0) { set_error("cand_off must start at 0 and be non-decreasing"); return HYORB_EINVAL; }
+        for (int i = 0; i < nq; i++) {
+            if (cand_off[i + 1] < cand_off[i]) { set_error("cand_off must be non-decreasing"); return HYORB_EINVAL; }
+            if (cand_off[i + 1] - cand_off[i] >= (1 << 22)) { set_error("candidate list too long"); return HYORB_EUNSUPPORTED; }
+        }
+        HY_TRY(m_upload(m, m->d_g, cand_off, sizeof(int32_t) * ((size_t)nq + 1)));
+        HY_TRY(m_upload(m, m->d_h, cand_idx, sizeof(int32_t) * (size_t)total));
+        HY_TRY(launch_match_csr(m->d_a.as<uint8_t>(), nq, m->d_b.as<uint8_t>(), nt, m->d_g.as<int32_t>(), m->d_h.as<int32_t>(), rule, thr, ratio,
+                                m->d_c.as<int32_t>(), m->d_d.as<uint16_t>(), m->d_e.as<uint16_t>(), m->d_f.as<uint8_t>(), m->d_status.as<int>(),
+                                m->stream, &m->launches));
+    } else {
+        HY_TRY(hyorb_match_bruteforce_device(m, m->d_a.as<uint8_t>(), nq, m->d_b.as<uint8_t>(), nt, rule, thr, ratio, m->d_c.as<int32_t>(),
+                                             m->d_d.as<uint16_t>(), m->d_e.as<uint16_t>(), m->d_f.as<uint8_t>()));
+    }
+    HY_CUDA(cudaMemcpyAsync(best_idx, m->d_c.p, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(best, m->d_d.p, sizeof(uint16_t) * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(second, m->d_e.p, sizeof(uint16_t) * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(accepted, m->d_f.p, (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    return m_sync(m);
+}
+
+HYORB_API int hyorb_grid_build_host(hyorb_matcher *m, const hyorb_keypoint *kps, int n, const hyorb_bounds *b, int32_t *cell_off, int32_t *cell_idx)
+{
+    HY_TRY(m_prepare(m));
+    if (n < 0 || !b || !cell_off || (n > 0 && (!kps || !cell_idx))) { set_error("bad argument"); return HYORB_EINVAL; }
+    constexpr int NC = HYORB_GRID_COLS * HYORB_GRID_ROWS;
+    HY_TRY(m_upload(m, m->d_a, kps, sizeof(hyorb_keypoint) * (size_t)n));
+    HY_TRY(m->d_i.ensure(sizeof(int32_t) * (NC + 1)));
+    HY_TRY(m->d_j.ensure(sizeof(int32_t) * std::max(n, 1)));
+    HY_TRY(m->d_cellof.ensure(sizeof(int32_t) * std::max(n, 1)));
+    HY_TRY(m->d_cellcnt.ensure(sizeof(int32_t) * NC));
+    HY_TRY(launch_grid_build(m->d_a.as<hyorb_keypoint>(), n, *b, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(), m->d_cellof.as<int32_t>(),
+                             m->d_cellcnt.as<int32_t>(), m->stream, &m->launches));
+    HY_CUDA(cudaMemcpyAsync(cell_off, m->d_i.p, sizeof(int32_t) * (NC + 1), cudaMemcpyDeviceToHost, m->stream));
+    HY_TRY(m_sync(m));
+    const int total = cell_off[NC];
+    if (total > 0) {
+        HY_CUDA(cudaMemcpyAsync(cell_idx, m->d_j.p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, m->stream));
+        HY_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    return HYORB_OK;
+}
+
+HYORB_API int hyorb_match_window_host(hyorb_matcher *m, const hyorb_keypoint *t_kps, const uint8_t *t_desc, const float *t_uR,
+                                      const uint8_t *t_matched, int nt, const hyorb_bounds *b, const hyorb_window_query *queries,
+                                      const uint8_t *q_desc, int nq, float thr, float ratio, int32_t *best_idx, uint16_t *best,
+                                      uint16_t *second, uint8_t *accepted)
+{
+    HY_TRY(m_prepare(m));
+    if (nq < 0 || nt < 0 || !b) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (nq == 0) return HYORB_OK;
+    if (!queries || !q_desc || !best_idx || !best || !second || !accepted || (nt > 0 && (!t_kps || !t_desc))) { set_error("null argument"); return HYORB_EINVAL; }
+    for (int i = 0; i < nq; i++)
+        if (queries[i].ur_radius >= 0 && !t_uR) { set_error("stereo consistency requested but t_uR is NULL"); return HYORB_EINVAL; }
+    constexpr int NC = HYORB_GRID_COLS * HYORB_GRID_ROWS;
+    HY_TRY(m_upload(m, m->d_a, t_kps, sizeof(hyorb_keypoint) * (size_t)nt));
+    HY_TRY(m_upload(m, m->d_b, t_desc, (size_t)nt * 32));
+    if (t_uR) HY_TRY(m_upload(m, m->d_k, t_uR, sizeof(float) * (size_t)nt));
+    if (t_matched) HY_TRY(m_upload(m, m->d_l, t_matched, (size_t)nt));
+    HY_TRY(m_upload(m, m->d_g, queries, sizeof(hyorb_window_query) * (size_t)nq));
+    HY_TRY(m_upload(m, m->d_h, q_desc, (size_t)nq * 32));
+    HY_TRY(m->d_i.ensure(sizeof(int32_t) * (NC + 1)));
+    HY_TRY(m->d_j.ensure(sizeof(int32_t) * std::max(nt, 1)));
+    HY_TRY(m->d_cellof.ensure(sizeof(int32_t) * std::max(nt, 1)));
+    HY_TRY(m->d_cellcnt.ensure(sizeof(int32_t) * NC));
+    HY_TRY(m->d_c.ensure(sizeof(int32_t) * (size_t)nq));
+    HY_TRY(m->d_d.ensure(sizeof(uint16_t) * (size_t)nq));
+    HY_TRY(m->d_e.ensure(sizeof(uint16_t) * (size_t)nq));
+    HY_TRY(m->d_f.ensure((size_t)nq));
+    HY_TRY(launch_grid_build(m->d_a.as<hyorb_keypoint>(), nt, *b, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(), m->d_cellof.as<int32_t>(),
+                             m->d_cellcnt.as<int32_t>(), m->stream, &m->launches));
+    HY_TRY(launch_match_window(m->d_a.as<hyorb_keypoint>(), m->d_b.as<uint8_t>(), t_uR ? m->d_k.as<float>() : nullptr,
+                               t_matched ? m->d_l.as<uint8_t>() : nullptr, nt, *b, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(),
+                               m->d_g.as<hyorb_window_query>(), m->d_h.as<uint8_t>(), nq, thr, ratio, m->d_c.as<int32_t>(), m->d_d.as<uint16_t>(),
+                               m->d_e.as<uint16_t>(), m->d_f.as<uint8_t>(), m->stream, &m->launches));
+    HY_CUDA(cudaMemcpyAsync(best_idx, m->d_c.p, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(best, m->d_d.p, sizeof(uint16_t) * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(second, m->d_e.p, sizeof(uint16_t) * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(accepted, m->d_f.p, (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    return m_sync(m);
+}
+
+HYORB_API int hyorb_rotation_consistency_host(hyorb_matcher *m, const float *angle_prev, const float *angle_curr, int n, uint8_t *keep)
+{
+    HY_TRY(m_prepare(m));
+    if (n < 0) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (n == 0) return HYORB_OK;
+    if (!angle_prev || !angle_curr || !keep) { set_error("null argument"); return HYORB_EINVAL; }
+    HY_TRY(m_upload(m, m->d_a, angle_prev, sizeof(float) * (size_t)n));
+    HY_TRY(m_upload(m, m->d_b, angle_curr, sizeof(float) * (size_t)n));
+    HY_TRY(m->d_f.ensure((size_t)n));
+    HY_TRY(launch_rotation(m->d_a.as<float>(), m->d_b.as<float>(), n, m->d_f.as<uint8_t>(), m->d_status.as<int>(), m->stream, &m->launches));
+    HY_CUDA(cudaMemcpyAsync(keep, m->d_f.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    return m_sync(m);
+}
+
+HYORB_API int hyorb_stereo_match_batch_device(hyorb_matcher *m, const hyorb_stereo_params *sp, int n_pairs, const hyorb_keypoint *d_kps,
+                                              const uint8_t *d_desc, const int32_t *d_counts, int capacity, float *d_uR, float *d_depth,
+                                              int32_t *d_best_r, int32_t *d_best_dist)
+{
+    HY_TRY(m_prepare(m));
+    if (!sp || n_pairs < 0 || capacity < 1 || !d_kps || !d_desc || !d_counts || !d_uR || !d_depth) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (n_pairs == 0) return HYORB_OK;
+    const int tabCap = capacity * 20;
+    HY_TRY(m->d_rowtab.ensure(sizeof(int32_t) * (size_t)tabCap * n_pairs));
+    if (!d_best_dist) {
+        HY_TRY(m->d_bestd.ensure(sizeof(int32_t) * (size_t)capacity * n_pairs));
+        d_best_dist = m->d_bestd.as<int32_t>();
+    }
+    return launch_stereo(*sp, n_pairs, d_kps, d_desc, d_counts, capacity, m->d_rowtab.as<int32_t>(), tabCap, d_uR, d_depth, d_best_r, d_best_dist,
+                         m->d_status.as<int>(), m->stream, &m->launches);
+}
+
+HYORB_API int hyorb_stereo_match_host(hyorb_matcher *m, const hyorb_stereo_params *sp, const hyorb_keypoint *kps_l, const uint8_t *desc_l, int n_l,
+                                      const hyorb_keypoint *kps_r, const uint8_t *desc_r, int n_r, float *uR, float *depth, int32_t *best_r,
+                                      int32_t *best_dist)
+{
+    HY_TRY(m_prepare(m));
+    if (!sp || n_l < 0 || n_r < 0) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (n_l == 0) return HYORB_OK;
+    if (!kps_l || !desc_l || !uR || !depth || (n_r > 0 && (!kps_r || !desc_r))) { set_error("null argument"); return HYORB_EINVAL; }
+    const int cap = std::max(std::max(n_l, n_r), 1);
+    // lay the pair out the way hyorb_extract_batch_device does: image 0 = left, image 1 = right, stride = cap
+    HY_TRY(m->d_a.ensure(sizeof(hyorb_keypoint) * (size_t)cap * 2));
+    HY_TRY(m->d_b.ensure((size_t)32 * cap * 2));
+    HY_TRY(m->d_c.ensure(sizeof(int32_t) * 2));
+    HY_TRY(m->d_d.ensure(sizeof(float) * (size_t)cap));
+    HY_TRY(m->d_e.ensure(sizeof(float) * (size_t)cap));
+    HY_TRY(m->d_g.ensure(sizeof(int32_t) * (size_t)cap));
+    HY_TRY(m->d_h.ensure(sizeof(int32_t) * (size_t)cap));
+    const int32_t cnt[2] = {n_l, n_r};
+    HY_CUDA(cudaMemcpyAsync(m->d_a.p, kps_l, sizeof(hyorb_keypoint) * (size_t)n_l, cudaMemcpyHostToDevice, m->stream));
+    HY_CUDA(cudaMemcpyAsync(m->d_b.p, desc_l, (size_t)32 * n_l, cudaMemcpyHostToDevice, m->stream));
+    if (n_r) {
+        HY_CUDA(cudaMemcpyAsync(m->d_a.as<hyorb_keypoint>() + cap, kps_r, sizeof(hyorb_keypoint) * (size_t)n_r, cudaMemcpyHostToDevice, m->stream));
+        HY_CUDA(cudaMemcpyAsync(m->d_b.as<uint8_t>() + (size_t)32 * cap, desc_r, (size_t)32 * n_r, cudaMemcpyHostToDevice, m->stream));
+    }
+    HY_CUDA(cudaMemcpyAsync(m->d_c.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, m->stream));
+    HY_CUDA(cudaStreamSynchronize(m->stream));     // cnt is a stack array
+    HY_TRY(hyorb_stereo_match_batch_device(m, sp, 1, m->d_a.as<hyorb_keypoint>(), m->d_b.as<uint8_t>(), m->d_c.as<int32_t>(), cap,
+                                           m->d_d.as<float>(), m->d_e.as<float>(), m->d_g.as<int32_t>(), m->d_h.as<int32_t>()));
+    HY_CUDA(cudaMemcpyAsync(uR, m->d_d.p, sizeof(float) * (size_t)n_l, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(depth, m->d_e.p, sizeof(float) * (size_t)n_l, cudaMemcpyDeviceToHost, m->stream));
+    if (best_r) HY_CUDA(cudaMemcpyAsync(best_r, m->d_g.p, sizeof(int32_t) * (size_t)n_l, cudaMemcpyDeviceToHost, m->stream));
+    if (best_dist) HY_CUDA(cudaMemcpyAsync(best_dist, m->d_h.p, sizeof(int32_t) * (size_t)n_l, cudaMemcpyDeviceToHost, m->stream));
+    return m_sync(m);
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+// common.cuh -- shared declarations of libhyorb (host + device).  B200 / sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <vector>
+
+#include "../../include/hyorb.h"
+
+namespace hyorb {
+
+// ---- error plumbing (thread-local message behind hyorb_last_error) ----
+void set_error(const char *fmt, ...);
+#define HY_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            hyorb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return HYORB_ECUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+#define HY_TRY(expr)          \
+    do {                      \
+        int _rc = (expr);     \
+        if (_rc) return _rc;  \
+    } while (0)
+
+// ---- algorithm constants (reference file:line in comments) ----
+constexpr int EDGE_THRESHOLD = 19;   // ORBExtractor.cpp:74
+constexpr int PATCH_SIZE = 31;       // ORBExtractor.cpp:73
+constexpr int HALF_PATCH = 15;       // ORBFinder.cpp:14
+constexpr int FAST_T = 20;           // ORBFinder.h:92 + setter bug ORBFinder.cpp:58-60
+constexpr int LATTICE_MIN = 16;      // minBorderX = EDGE_THRESHOLD-3 (ORBExtractor.cpp:417)
+constexpr int DET_MIN = 19;          // first pixel FAST can report: lattice min + 3
+
+// FAST tile geometry: a CTA scores a 64x32 region (one 4-pixel group x one row per work item, two items per
+// thread) and emits the 62x30 interior, so the 3x3 NMS never leaves the CTA.
+constexpr int FT_SW = 64, FT_SH = 32;          // score region
+constexpr int FT_OW = FT_SW - 2, FT_OH = FT_SH - 2;   // emitted interior
+constexpr int FT_PW = FT_SW + 6, FT_PH = FT_SH + 6;   // pixel region (ring radius 3)
+constexpr int FT_PITCH = 72;                           // bytes, 18 words
+constexpr int FT_THREADS = 256;
+
+constexpr int QT_DMAX = 13;          // quadtree path bits per axis
+constexpr int QT_THREADS = 512;
+constexpr int QT_MAX_ROOTS = 64;
+
+constexpr int MAX_DIM = 4095 + 2 * LATTICE_MIN;  // candidates are packed x:12 | y:12 | response:8 in lattice coordinates
+
+// device-visible per-level constants of one (width, height) plan
+struct LevelDev {
+    int w, h, pitch;          // pitch of the level inside the pyramid block (level 0 may live in the caller's buffer)
+    unsigned long long off;   // byte offset of the level inside one image's pyramid block
+    int maxBX, maxBY;         // w-16, h-16  (ORBExtractor.cpp:419-420)
+    int nCols, nRows, wCell, hCell;   // cell lattice (:425-428)
+    int tilesX, tilesY, tileBase;     // FAST tiles of this level; tileBase = first tile id inside one image
+    int quota;                // mnFeaturesPerLevel[l]
+    int nIni; float hX;       // quadtree roots (:183-185)
+    int candCap; unsigned candOff;    // candidate slots of this level inside one image's candidate block (uint32 units)
+    int selCap; unsigned selOff;      // selected-keypoint slots (uint32 units)
+    int lutX, lutY;           // offsets into the quadtree path LUT (uint32 units): col code by lattice x, row code by lattice y
+    int rsX, rsY;             // offsets into the resize tables (entries), level >= 1
+    int area2x;               // cv::resize's exact-2x INTER_AREA shortcut applies between level-1 and this level
+    float scale;              // mvScaleFactor[l]
+    float kpSize;             // (float)(int)(PATCH_SIZE*scale)  (:478)
+    int qtMaxN;               // power of two >= 4*quota: node arrays of the quadtree kernel
+};
+
+struct PlanDev {
+    int nlevels, width, height;
+    int tilesPerImage;
+    unsigned long long pyrStride;   // bytes per image pyramid block
+    unsigned candStride;            // uint32 per image
+    unsigned selStride;             // uint32 per image
+    int selTotalCap;                // sum of selCap over levels (upper bound on keypoints per image)
+    int blurTileBase[HYORB_MAX_LEVELS + 1];   // first blur tile of each level inside one image (blur.cu)
+    LevelDev lv[HYORB_MAX_LEVELS];
+};
+
+struct ResizeTab { int ofs; short c0, c1; };   // source index + Q11 coefficients of one destination row/column
+
+// where level 0 lives for the current batch
+struct Level0 {
+    const uint8_t *base; int pitch; unsigned long long stride;
+};
+
+__host__ __device__ inline uint32_t pack_cand(int x, int y, int resp) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)resp << 24); }
+__host__ __device__ inline int cand_x(uint32_t c) { return (int)(c & 0xFFFu); }
+__host__ __device__ inline int cand_y(uint32_t c) { return (int)((c >> 12) & 0xFFFu); }
+__host__ __device__ inline int cand_resp(uint32_t c) { return (int)(c >> 24); }
+
+// order in which the reference generates candidates: cell row-major, then row-major inside the cell's ROI
+// (ORBExtractor.cpp:430-470).  Lattice coordinates in, unique key out.
+__host__ __device__ inline uint32_t cand_order_key(int x, int y, int wCell, int hCell, int nCols)
+{
+    const int cj = (x - 3) / wCell, ci = (y - 3) / hCell;
+    return ((uint32_t)(ci * nCols + cj) << 14) | ((uint32_t)(y - ci * hCell) << 7) | (uint32_t)(x - cj * wCell);
+}
+
+// ---- host-side plan (tables.cu) ----
+struct HostPlan {
+    PlanDev dev;
+    std::vector<ResizeTab> resize;      // all levels, x tables then y tables
+    std::vector<uint32_t> lut;          // quadtree path LUTs
+};
+int scale_tables(const hyorb_extractor_params &p, float *scale, float *inv, float *sigma2, float *inv_sigma2, int *quota);
+int build_plan(const hyorb_extractor_params &p, int width, int height, HostPlan *out);
+void blur_tiles(PlanDev *hp);
+const char *last_error();
+
+// ---- kernel launchers (each returns a HYORB status; all enqueue on `st`) ----
+int launch_pyramid(const PlanDev &hp, const PlanDev *dp, Level0 l0, uint8_t *pyr, const ResizeTab *tabs, int B, cudaStream_t st, long *launches);
+int launch_fast(const PlanDev &hp, const PlanDev *dp, Level0 l0, const uint8_t *pyr, uint32_t *cand, int *candCount, int *status, int B, cudaStream_t st, long *launches);
+int launch_quadtree(const PlanDev &hp, const PlanDev *dp, const uint32_t *cand, const int *candCount, const uint32_t *lut,
+                    uint32_t *qcode, uint16_t *qnode, uint2 *qleaf, uint32_t *sel, int *selCount, int *status, int B, cudaStream_t st, long *launches);
+int launch_blur(const PlanDev &hp, const PlanDev *dp, Level0 l0, const uint8_t *pyr, uint8_t *blur, int B, cudaStream_t st, long *launches);
+int launch_describe(const PlanDev &hp, const PlanDev *dp, const uint8_t *blur, const uint32_t *sel, const int *selCount,
+                    hyorb_keypoint *kps, uint8_t *desc, int capacity, int *counts, int *status, int B, cudaStream_t st, long *launches);
+
+// matching / stereo (match.cu, stereo.cu)
+int launch_match_bruteforce(const uint8_t *q, int nq, const uint8_t *t, int nt, int rule, float thr, float ratio,
+                            int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted,
+                            uint32_t *pkey, uint16_t *psecond, int nsplit, cudaStream_t st, long *launches);
+int launch_match_csr(const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *off, const int32_t *idx, int rule, float thr,
+                     float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, int *status, cudaStream_t st, long *launches);
+int launch_grid_build(const hyorb_keypoint *kps, int n, hyorb_bounds b, int32_t *cell_off, int32_t *cell_idx, int32_t *cell_of, int32_t *cell_cnt,
+                      cudaStream_t st, long *launches);
+int launch_match_window(const hyorb_keypoint *kps, const uint8_t *tdesc, const float *t_uR, const uint8_t *t_matched, int nt, hyorb_bounds b,
+                        const int32_t *cell_off, const int32_t *cell_idx, const hyorb_window_query *q, const uint8_t *qdesc, int nq,
+                        float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, cudaStream_t st, long *launches);
+int launch_rotation(const float *a_prev, const float *a_curr, int n, uint8_t *keep, int *status, cudaStream_t st, long *launches);
+int launch_stereo(const hyorb_stereo_params &sp, int n_pairs, const hyorb_keypoint *kps, const uint8_t *desc, const int32_t *counts, int capacity,
+                  int32_t *rowtab, int tabCap, float *uR, float *depth, int32_t *best_r, int32_t *best_d, int *status, cudaStream_t st, long *launches);
+
+// device-side status word bits (OR-ed by kernels, read back at sync)
+enum { ST_CAND_OVERFLOW = 1, ST_SEL_OVERFLOW = 2, ST_OUT_OVERFLOW = 4, ST_QT_LIMIT = 8, ST_BAD_INDEX = 16, ST_ROW_RANGE = 32, ST_QT_MISMATCH = 64 };
+
+// acceptance rules shared by the matching kernels (MatchCriteria.cpp:214-246, 601-635, 486-523);
+// best/second are Hamming distances as floats, FLT_MAX when absent.
+__host__ __device__ inline bool accept_rule(int rule, float best, float second, float thr, float ratio)
+{
+#ifdef __CUDA_ARCH__
+    const float rs = __fmul_rn(ratio, second);
+#else
+    const float rs = ratio * second;
+#endif
+    switch (rule) {
+    case HYORB_RULE_LANDMARK: return (best <= thr) && !(best > rs);
+    case HYORB_RULE_BOW: return (best < thr) && (best < rs);
+    case HYORB_RULE_MONOINIT: return (best <= thr) && (best < rs);
+    default: return false;
+    }
+}
+
+}  // namespace hyorb

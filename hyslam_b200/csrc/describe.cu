@@ -1,0 +1,135 @@
+// describe.cu -- K5: orientation + rotated BRIEF + final keypoint packaging.
+// Replaces ORBFinder::compute (src/features/low_level/ORBFinder.cpp:70-78): intensityCentroidAngle (:16-43) and
+// computeOrbDescriptor (:89-129), both evaluated on the BLURRED level (ORBExtractor.cpp:536-541), and
+// the tail of ORBExtractor::operator() (:546-561): pt *= scale[level], levels concatenated 0..L-1.
+// One warp per keypoint: lanes 0..30 are the 31 columns of the intensity-centroid disc (integer moments, exact in
+// any order), then lane i evaluates the 8 tests of descriptor byte i.  Floating point follows the reference's
+// x86-64 baseline build: every fp32 operation individually rounded (no FMA contraction), cos/sin in double then
+// narrowed, cvRound = round-half-even.
+#include <float.h>
+#include "common.cuh"
+
+namespace hyorb {
+
+__device__ const int8_t d_brief_pattern[1024] = {
+#include "../../include/hyorb_brief_pattern.inc"
+};
+
+constexpr int DS_WARPS = 8;
+
+// cv::fastAtan2 (OpenCV core/mathfuncs_core, scalar atan_f32), called at ORBFinder.cpp:42
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    const float k = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * k, p3 = -0.3258083974640975f * k;
+    const float p5 = 0.1555786518463281f * k, p7 = -0.04432655554792128f * k;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(DS_WARPS * 32)
+k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, const uint32_t *__restrict__ sel_all,
+           const int *__restrict__ selCount, hyorb_keypoint *__restrict__ kps, uint8_t *__restrict__ desc, int capacity,
+           int *__restrict__ counts, int *__restrict__ status)
+{
+    // umax of ORBFinder::orientationSetup (ORBFinder.cpp:131-149), asserted against the oracle in tests
+    const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int k = blockIdx.x * DS_WARPS + warp;
+    const int nl = plan->nlevels;
+    // locate output slot k: levels are concatenated in order (ORBExtractor.cpp:523-555)
+    int acc = 0, l = -1, j = 0, total = 0;
+    for (int i = 0; i < nl; i++) {
+        int c = selCount[b * HYORB_MAX_LEVELS + i];
+        if (c > plan->lv[i].selCap) c = plan->lv[i].selCap;
+        if (l < 0 && k < acc + c) { l = i; j = k - acc; }
+        acc += c;
+    }
+    total = acc;
+    if (k == 0 && lane == 0) {
+        if (total > capacity) { atomicOr(status, ST_OUT_OVERFLOW); counts[b] = capacity; }
+        else counts[b] = total;
+    }
+    if (l < 0 || k >= capacity) return;
+    const LevelDev &L = plan->lv[l];
+    const uint32_t c = sel_all[(size_t)b * plan->selStride + L.selOff + j];
+    const int px = cand_x(c) + LATTICE_MIN, py = cand_y(c) + LATTICE_MIN;     // :484-485
+    const int pitch = L.pitch;
+    const uint8_t *center = blur + (size_t)b * plan->pyrStride + L.off + (size_t)py * pitch + px;
+
+    // ---- intensity centroid (ORBFinder.cpp:16-43)
+    int m10 = 0, m01 = 0;
+    const int u = lane - HALF_PATCH;
+    if (lane < 31) {
+        const int au = u < 0 ? -u : u;
+#pragma unroll
+        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {
+            const int av = v < 0 ? -v : v;
+            if (au <= umax[av]) {
+                const int val = center[v * pitch + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- rotated BRIEF (ORBFinder.cpp:89-129)
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    const float rad = __fmul_rn(angle, factorPI);
+    const float a = (float)cos((double)rad), bb = (float)sin((double)rad);
+    const int8_t *pat = d_brief_pattern + lane * 32;
+    int val = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const float x0 = (float)pat[4 * t], y0 = (float)pat[4 * t + 1], x1 = (float)pat[4 * t + 2], y1 = (float)pat[4 * t + 3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, bb), __fmul_rn(y0, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bb)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bb), __fmul_rn(y1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, bb)));
+        const int t0 = center[r0 * pitch + c0], t1 = center[r1 * pitch + c1];
+        val |= (t0 < t1) << t;
+    }
+    const size_t o = (size_t)b * capacity + k;
+    desc[o * HYORB_DESC_BYTES + lane] = (uint8_t)val;
+    if (lane == 0) {
+        hyorb_keypoint kp;
+        kp.x = (float)px; kp.y = (float)py;
+        if (l != 0) { kp.x = __fmul_rn(kp.x, L.scale); kp.y = __fmul_rn(kp.y, L.scale); }   // ORBExtractor.cpp:546-552
+        kp.size = L.kpSize; kp.angle = angle; kp.response = (float)cand_resp(c);
+        kp.octave = l; kp.class_id = -1;
+        kps[o] = kp;
+    }
+}
+
+int launch_describe(const PlanDev &hp, const PlanDev *dp, const uint8_t *blur, const uint32_t *sel, const int *selCount,
+                    hyorb_keypoint *kps, uint8_t *desc, int capacity, int *counts, int *status, int B, cudaStream_t st, long *launches)
+{
+    int slots = hp.selTotalCap < capacity ? hp.selTotalCap : capacity;
+    if (slots < 1) slots = 1;
+    dim3 grd((slots + DS_WARPS - 1) / DS_WARPS, B);
+    k_describe<<<grd, DS_WARPS * 32, 0, st>>>(dp, blur, sel, selCount, kps, desc, capacity, counts, status);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+}  // namespace hyorb

@@ -1,0 +1,352 @@
+// match.cu -- K6: binary-descriptor matching.  Replaces the inner loops of HYSLAM::FeatureMatcher / MatchCriteria:
+//   * ORBDistance::distance (src/features/low_level/DescriptorDistance.cpp:9-25): 256-bit Hamming distance, here
+//     uint4 loads, XOR and __popc;
+//   * BestScoreCriterionCore (src/features/MatchCriteria.cpp:248-280): best / second-best scan with strict `<`
+//     (first candidate wins ties, the second best may equal the best);
+//   * the acceptance rules of BestScoreCriterion (:214-246), BestMatchBoWCriterion (:601-635), MonoInitBestScore (:486-523);
+//   * Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInAreaNEW (src/core/Frame.cc:137-153, 459-469, 416-457);
+//   * PreviouslyMatchedCriterion (:124-144), FeatureSizeCriterion (:350-360), StereoConsistencyCriterion (:149-177);
+//   * RotationConsistency + ComputeThreeMaxima (:684-767).
+// INT-pipe bound (XOR/POPC), HBM traffic negligible; no tensor cores (bit work, not a contraction).
+//
+// Order semantics without a sequential scan: (best, first index) = min over candidates of the packed key
+// (distance << 22 | position); second = 2nd order statistic of the distances with multiplicity.  Both merge
+// associatively, so lanes / CTAs scan slices and combine with warp shuffles.
+#include <float.h>
+#include "common.cuh"
+
+namespace hyorb {
+
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+constexpr int POS_BITS = 22;
+constexpr uint32_t POS_MASK = (1u << POS_BITS) - 1;
+constexpr int DIST_NONE = 1023;    // > 256: "no candidate" (the reference's FLT_MAX)
+
+__device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1)
+{
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// running (best key, second distance) update with one more candidate
+__device__ __forceinline__ void scan_update(uint32_t &bkey, int &second, int d, uint32_t pos)
+{
+    const uint32_t key = ((uint32_t)d << POS_BITS) | pos;
+    if (key < bkey) { second = min(second, (int)(bkey >> POS_BITS)); bkey = key; }
+    else second = min(second, d);
+}
+// merge two partial scans
+__device__ __forceinline__ void scan_merge(uint32_t &bkey, int &second, uint32_t okey, int osecond)
+{
+    const uint32_t lo = min(bkey, okey), hi = max(bkey, okey);
+    second = min(min(second, osecond), (int)(hi >> POS_BITS));
+    bkey = lo;
+}
+__device__ __forceinline__ void warp_merge(uint32_t &bkey, int &second)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t ok = __shfl_xor_sync(0xffffffffu, bkey, o);
+        const int os = __shfl_xor_sync(0xffffffffu, second, o);
+        scan_merge(bkey, second, ok, os);
+    }
+}
+
+__device__ __forceinline__ void write_result(int q, uint32_t bkey, int second, int best_target, int rule, float thr, float ratio,
+                                             int32_t *best_idx, uint16_t *best, uint16_t *sec, uint8_t *accepted)
+{
+    const int bd = (int)(bkey >> POS_BITS);
+    const bool has = bd < DIST_NONE;
+    const float fb = has ? (float)bd : FLT_MAX, fs = second < DIST_NONE ? (float)second : FLT_MAX;
+    best_idx[q] = has ? best_target : -1;
+    best[q] = has ? (uint16_t)bd : (uint16_t)65535;
+    sec[q] = second < DIST_NONE ? (uint16_t)second : (uint16_t)65535;
+    accepted[q] = (uint8_t)(has && accept_rule(rule, fb, fs, thr, ratio));
+}
+
+// ---------------- brute force: every target in index order (C4: 8000 x 8000)
+constexpr int BF_THREADS = 128, BF_TILE = 128;
+
+__global__ void __launch_bounds__(BF_THREADS)
+k_bf_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, int chunk,
+             uint32_t *__restrict__ pkey, uint16_t *__restrict__ psecond)
+{
+    __shared__ uint4 s_t[BF_TILE * 2];
+    const int qi = blockIdx.x * BF_THREADS + threadIdx.x;
+    const int t0 = blockIdx.y * chunk, t1 = min(t0 + chunk, nt);
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (qi < nq) { a0 = q[2 * qi]; a1 = q[2 * qi + 1]; }
+    uint32_t bkey = KEY_NONE; int second = DIST_NONE;
+    for (int base = t0; base < t1; base += BF_TILE) {
+        const int cnt = min(BF_TILE, t1 - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * cnt; i += BF_THREADS) s_t[i] = t[2 * (size_t)base + i];
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < cnt; j++) {
+            const int d = hamming256(a0, a1, s_t[2 * j], s_t[2 * j + 1]);
+            scan_update(bkey, second, d, (uint32_t)(base + j));
+        }
+    }
+    if (qi < nq) {
+        pkey[(size_t)blockIdx.y * nq + qi] = bkey;
+        psecond[(size_t)blockIdx.y * nq + qi] = (uint16_t)second;
+    }
+}
+
+__global__ void k_bf_finalize(const uint32_t *__restrict__ pkey, const uint16_t *__restrict__ psecond, int nsplit, int nq,
+                              int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *sec, uint8_t *accepted)
+{
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    uint32_t bkey = KEY_NONE; int second = DIST_NONE;
+    for (int s = 0; s < nsplit; s++) scan_merge(bkey, second, pkey[(size_t)s * nq + qi], (int)psecond[(size_t)s * nq + qi]);
+    write_result(qi, bkey, second, (int)(bkey & POS_MASK), rule, thr, ratio, best_idx, best, sec, accepted);
+}
+
+// ---------------- candidate lists (CSR): one warp per query, lanes stride over the list
+__global__ void __launch_bounds__(256)
+k_match_csr(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, const int32_t *__restrict__ off,
+            const int32_t *__restrict__ idx, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *sec,
+            uint8_t *accepted, int *status)
+{
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const uint4 a0 = q[2 * qi], a1 = q[2 * qi + 1];
+    const int lo = off[qi], hi = off[qi + 1];
+    uint32_t bkey = KEY_NONE; int second = DIST_NONE;
+    for (int c = lo + lane; c < hi; c += 32) {
+        const int ti = idx[c];
+        if (ti < 0 || ti >= nt) { atomicOr(status, ST_BAD_INDEX); continue; }
+        const int d = hamming256(a0, a1, t[2 * (size_t)ti], t[2 * (size_t)ti + 1]);
+        scan_update(bkey, second, d, (uint32_t)(c - lo) & POS_MASK);
+    }
+    warp_merge(bkey, second);
+    if (lane == 0) {
+        const int bt = bkey != KEY_NONE ? idx[lo + (int)(bkey & POS_MASK)] : -1;
+        write_result(qi, bkey, second, bt, rule, thr, ratio, best_idx, best, sec, accepted);
+    }
+}
+
+// ---------------- Frame grid (Frame.cc:137-153, 459-469)
+__global__ void k_grid_cells(const hyorb_keypoint *__restrict__ kps, int n, hyorb_bounds b, int32_t *__restrict__ cell_of,
+                             int32_t *__restrict__ cell_cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float invW = __fdiv_rn((float)HYORB_GRID_COLS, __fsub_rn(b.max_x, b.min_x));   // Frame.cc:65-66
+    const float invH = __fdiv_rn((float)HYORB_GRID_ROWS, __fsub_rn(b.max_y, b.min_y));
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, b.min_x), invW));            // PosInGrid uses round()
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, b.min_y), invH));
+    int c = -1;
+    if (px >= 0 && px < HYORB_GRID_COLS && py >= 0 && py < HYORB_GRID_ROWS) { c = px * HYORB_GRID_ROWS + py; atomicAdd(&cell_cnt[c], 1); }
+    cell_of[i] = c;
+}
+
+// single CTA: exclusive scan of the 3072 cell counts, then a stable fill (ascending keypoint index inside a cell,
+// i.e. the reference's push_back order) -- warps take turns so no atomics are needed.
+__global__ void __launch_bounds__(1024)
+k_grid_fill(const int32_t *__restrict__ cell_of, int n, const int32_t *__restrict__ cell_cnt, int32_t *__restrict__ cell_off,
+            int32_t *__restrict__ cell_idx)
+{
+    constexpr int NC = HYORB_GRID_COLS * HYORB_GRID_ROWS;
+    __shared__ int s_off[NC + 1];
+    __shared__ int s_fill[NC];
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x;
+    // 3 cells per thread
+    int v[3], sum = 0;
+    for (int k = 0; k < 3; k++) { const int c = tid * 3 + k; v[k] = c < NC ? cell_cnt[c] : 0; sum += v[k]; }
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int t = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += t;
+        __syncthreads();
+    }
+    int base = s_part[tid] - sum;
+    for (int k = 0; k < 3; k++) { const int c = tid * 3 + k; if (c < NC) { s_off[c] = base; s_fill[c] = 0; cell_off[c] = base; } base += v[k]; }
+    if (tid == 1023) { s_off[NC] = s_part[1023]; cell_off[NC] = s_part[1023]; }
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int chunk = 0; chunk < n; chunk += 1024) {
+        const int i = chunk + tid;
+        const int c = i < n ? cell_of[i] : -1;
+        for (int w = 0; w < 32; w++) {
+            if (warp == w) {
+                const unsigned peers = __match_any_sync(0xffffffffu, c);
+                if (c >= 0) {
+                    const int rank = __popc(peers & ((1u << lane) - 1));
+                    const int first = s_fill[c];
+                    __syncwarp();
+                    if (rank == 0) s_fill[c] = first + __popc(peers);
+                    cell_idx[s_off[c] + first + rank] = i;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------- windowed matching (one warp per landmark query)
+__global__ void __launch_bounds__(256)
+k_match_window(const hyorb_keypoint *__restrict__ kps, const uint4 *__restrict__ tdesc, const float *__restrict__ t_uR,
+               const uint8_t *__restrict__ t_matched, int nt, hyorb_bounds b, const int32_t *__restrict__ cell_off,
+               const int32_t *__restrict__ cell_idx, const hyorb_window_query *__restrict__ qs, const uint4 *__restrict__ qdesc, int nq,
+               float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *sec, uint8_t *accepted)
+{
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const hyorb_window_query Q = qs[qi];
+    const uint4 a0 = qdesc[2 * qi], a1 = qdesc[2 * qi + 1];
+    // Frame::GetFeaturesInAreaNEW (Frame.cc:416-457)
+    const float invW = __fdiv_rn((float)HYORB_GRID_COLS, __fsub_rn(b.max_x, b.min_x));
+    const float invH = __fdiv_rn((float)HYORB_GRID_ROWS, __fsub_rn(b.max_y, b.min_y));
+    int x0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(Q.u, b.min_x), Q.r), invW));
+    int x1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(Q.u, b.min_x), Q.r), invW));
+    int y0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(Q.v, b.min_y), Q.r), invH));
+    int y1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(Q.v, b.min_y), Q.r), invH));
+    x0 = max(x0, 0); x1 = min(x1, HYORB_GRID_COLS - 1); y0 = max(y0, 0); y1 = min(y1, HYORB_GRID_ROWS - 1);
+    uint32_t bkey = KEY_NONE; int second = DIST_NONE;
+    int bestT = -1;
+    uint32_t pos0 = 0;
+    if (x0 < HYORB_GRID_COLS && x1 >= 0 && y0 < HYORB_GRID_ROWS && y1 >= 0) {
+        for (int ix = x0; ix <= x1; ix++)
+            for (int iy = y0; iy <= y1; iy++) {
+                const int c = ix * HYORB_GRID_ROWS + iy;
+                const int lo = cell_off[c], hi = cell_off[c + 1];
+                for (int j = lo + lane; j < hi; j += 32) {
+                    const int k = cell_idx[j];
+                    const hyorb_keypoint kp = kps[k];
+                    const float dx = __fsub_rn(kp.x, Q.u), dy = __fsub_rn(kp.y, Q.v);
+                    if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
+                    if (t_matched && t_matched[k]) continue;                          // PreviouslyMatchedCriterion
+                    if (!(kp.size > Q.size_lo && kp.size < Q.size_hi)) continue;      // FeatureSizeCriterion
+                    if (Q.ur_radius >= 0) {                                           // StereoConsistencyCriterion
+                        const float ur = t_uR[k];
+                        if (!(fabsf(__fsub_rn(Q.ur, ur)) < Q.ur_radius && ur > 0)) continue;
+                    }
+                    const int d = hamming256(a0, a1, tdesc[2 * (size_t)k], tdesc[2 * (size_t)k + 1]);
+                    const uint32_t pos = (pos0 + (uint32_t)(j - lo)) & POS_MASK;
+                    const uint32_t key = ((uint32_t)d << POS_BITS) | pos;
+                    if (key < bkey) bestT = k;
+                    scan_update(bkey, second, d, pos);
+                }
+                pos0 += (uint32_t)(hi - lo);
+            }
+    }
+    // merge lanes, carrying the target index of the winner
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t ok = __shfl_xor_sync(0xffffffffu, bkey, o);
+        const int os = __shfl_xor_sync(0xffffffffu, second, o);
+        const int ot = __shfl_xor_sync(0xffffffffu, bestT, o);
+        if (ok < bkey) bestT = ot;
+        scan_merge(bkey, second, ok, os);
+    }
+    if (lane == 0) write_result(qi, bkey, second, bestT, HYORB_RULE_LANDMARK, thr, ratio, best_idx, best, sec, accepted);
+}
+
+// ---------------- rotation histogram (single CTA)
+__global__ void __launch_bounds__(256)
+k_rotation(const float *__restrict__ a_prev, const float *__restrict__ a_curr, int n, uint8_t *__restrict__ keep, int *status)
+{
+    constexpr int HL = 30;
+    __shared__ int hist[HL];
+    __shared__ int ind[3];
+    if (threadIdx.x < HL) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const float factor = 1.0f / HL;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float rot = __fsub_rn(a_prev[i], a_curr[i]);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == HL) bin = 0;
+        if (bin < 0 || bin >= HL) { atomicOr(status, ST_BAD_INDEX); continue; }   // the reference asserts
+        atomicAdd(&hist[bin], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // ComputeThreeMaxima (:727-767)
+        int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < HL; i++) {
+            const int s = hist[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+            else if (s > max3) { max3 = s; i3 = i; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3 = -1; }
+        ind[0] = i1; ind[1] = i2; ind[2] = i3;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float rot = __fsub_rn(a_prev[i], a_curr[i]);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == HL) bin = 0;
+        keep[i] = (uint8_t)(bin == ind[0] || bin == ind[1] || bin == ind[2]);
+    }
+}
+
+// ---------------- launchers
+int launch_match_bruteforce(const uint8_t *q, int nq, const uint8_t *t, int nt, int rule, float thr, float ratio,
+                            int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted,
+                            uint32_t *pkey, uint16_t *psecond, int nsplit, cudaStream_t st, long *launches)
+{
+    if (nq <= 0) return HYORB_OK;
+    if (nt >= (1 << POS_BITS)) { set_error("more than %d targets", (1 << POS_BITS) - 1); return HYORB_EUNSUPPORTED; }
+    const int chunk = nt > 0 ? (nt + nsplit - 1) / nsplit : 1;
+    dim3 grd((nq + BF_THREADS - 1) / BF_THREADS, nsplit);
+    k_bf_partial<<<grd, BF_THREADS, 0, st>>>((const uint4 *)q, nq, (const uint4 *)t, nt, chunk, pkey, psecond);
+    k_bf_finalize<<<(nq + 255) / 256, 256, 0, st>>>(pkey, psecond, nsplit, nq, rule, thr, ratio, best_idx, best, second, accepted);
+    *launches += 2;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+int launch_match_csr(const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *off, const int32_t *idx, int rule, float thr,
+                     float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, int *status, cudaStream_t st, long *launches)
+{
+    if (nq <= 0) return HYORB_OK;
+    k_match_csr<<<(nq + 7) / 8, 256, 0, st>>>((const uint4 *)q, nq, (const uint4 *)t, nt, off, idx, rule, thr, ratio, best_idx, best, second, accepted, status);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+int launch_grid_build(const hyorb_keypoint *kps, int n, hyorb_bounds b, int32_t *cell_off, int32_t *cell_idx, int32_t *cell_of, int32_t *cell_cnt,
+                      cudaStream_t st, long *launches)
+{
+    HY_CUDA(cudaMemsetAsync(cell_cnt, 0, sizeof(int32_t) * HYORB_GRID_COLS * HYORB_GRID_ROWS, st));
+    if (n > 0) { k_grid_cells<<<(n + 255) / 256, 256, 0, st>>>(kps, n, b, cell_of, cell_cnt); ++*launches; }
+    k_grid_fill<<<1, 1024, 0, st>>>(cell_of, n, cell_cnt, cell_off, cell_idx);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+int launch_match_window(const hyorb_keypoint *kps, const uint8_t *tdesc, const float *t_uR, const uint8_t *t_matched, int nt, hyorb_bounds b,
+                        const int32_t *cell_off, const int32_t *cell_idx, const hyorb_window_query *q, const uint8_t *qdesc, int nq,
+                        float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, cudaStream_t st, long *launches)
+{
+    if (nq <= 0) return HYORB_OK;
+    k_match_window<<<(nq + 7) / 8, 256, 0, st>>>(kps, (const uint4 *)tdesc, t_uR, t_matched, nt, b, cell_off, cell_idx, q, (const uint4 *)qdesc, nq,
+                                                 thr, ratio, best_idx, best, second, accepted);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+int launch_rotation(const float *a_prev, const float *a_curr, int n, uint8_t *keep, int *status, cudaStream_t st, long *launches)
+{
+    if (n <= 0) return HYORB_OK;
+    k_rotation<<<1, 256, 0, st>>>(a_prev, a_curr, n, keep, status);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+}  // namespace hyorb

@@ -1,0 +1,125 @@
+"""Host-side mirrors of HYSLAM::Stereomatcher (src/features/Stereomatcher.h:25-51) and of the Hamming scans of
+HYSLAM::FeatureMatcher / MatchCriteria (src/features/FeatureMatcher.h:105-176) over the C ABI."""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi as F
+from .settings import FeatureExtractorSettings, FeatureMatcherSettings
+
+
+class _Handle:
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        F.check(F.lib().hyorb_matcher_create(int(device), stream, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            F.lib().hyorb_matcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def sync(self):
+        F.check(F.lib().hyorb_matcher_sync(self._h))
+
+    def launch_count(self):
+        return int(F.lib().hyorb_matcher_launch_count(self._h))
+
+
+class Stereomatcher(_Handle):
+    """``Stereomatcher(views, camera, settings)`` -> ``computeStereoMatches()`` -> ``getData()`` as in
+    ImageProcessing::ProcessStereoImage (src/main/ImageProcessing.cpp:100-103).  ``views`` is the tuple
+    (kps_left, desc_left, kps_right, desc_right) the reference packs into a FeatureViews."""
+
+    def __init__(self, views, camera, settings=None, extractor_settings=None, device=0, stream=None):
+        super().__init__(device, stream)
+        self.kl, self.dl, self.kr, self.dr = views
+        ms = settings or FeatureMatcherSettings()
+        es = extractor_settings or FeatureExtractorSettings()
+        self.params = F.StereoParams(float(camera.mbf), float(camera.fx), int(camera.mnMaxY), float(ms.TH_HIGH), float(ms.TH_LOW),
+                                     float(es.size_ref))
+        self.mvuRight = self.mvDepth = self.best_r = self.best_dist = None
+
+    def computeStereoMatches(self):
+        kl, kr = np.ascontiguousarray(self.kl, F.KP_DTYPE), np.ascontiguousarray(self.kr, F.KP_DTYPE)
+        dl, dr = np.ascontiguousarray(self.dl, np.uint8), np.ascontiguousarray(self.dr, np.uint8)
+        nl = len(kl)
+        self.mvuRight = np.full(nl, -1, np.float32)
+        self.mvDepth = np.full(nl, -1, np.float32)
+        self.best_r = np.full(nl, -1, np.int32)
+        self.best_dist = np.full(nl, -1, np.int32)
+        F.check(F.lib().hyorb_stereo_match_host(self._h, C.byref(self.params), F.ptr(kl), F.ptr(dl), nl, F.ptr(kr), F.ptr(dr), len(kr),
+                                                F.ptr(self.mvuRight), F.ptr(self.mvDepth), F.ptr(self.best_r), F.ptr(self.best_dist)))
+
+    def getData(self):
+        return self.mvuRight, self.mvDepth
+
+    def match_batch_device(self, n_pairs, d_kps, d_desc, d_counts, capacity, d_uR, d_depth, d_best_r=None, d_best_dist=None):
+        F.check(F.lib().hyorb_stereo_match_batch_device(self._h, C.byref(self.params), n_pairs, d_kps, d_desc, d_counts, capacity,
+                                                        d_uR, d_depth, d_best_r, d_best_dist))
+
+
+class FeatureMatcher(_Handle):
+    """The data-parallel inner loops of HYSLAM::FeatureMatcher: candidate enumeration (grid window / explicit CSR
+    lists), Hamming scan, best / second-best, acceptance rule, rotation histogram.  Landmark projection and map
+    bookkeeping stay with the caller."""
+
+    def __init__(self, settings=None, device=0, stream=None):
+        super().__init__(device, stream)
+        self.settings = settings or FeatureMatcherSettings()
+
+    def _outs(self, nq):
+        return (np.full(nq, -1, np.int32), np.full(nq, 65535, np.uint16), np.full(nq, 65535, np.uint16), np.zeros(nq, np.uint8))
+
+    def match(self, q_desc, t_desc, cand_off=None, cand_idx=None, rule=F.RULE_BOW, thr=None, ratio=None):
+        """Best / second-best scan of every query over its candidate list (BoW-node lists of
+        FeatureMatcher::_SearchByBoW_, FeatureMatcher.cc:281-345) or, with no lists, over all targets in index order."""
+        q = np.ascontiguousarray(q_desc, np.uint8); t = np.ascontiguousarray(t_desc, np.uint8)
+        nq, nt = len(q), len(t)
+        thr = float(self.settings.TH_LOW if thr is None else thr)
+        ratio = float(self.settings.nnratio if ratio is None else ratio)
+        if cand_off is not None:
+            cand_off = np.ascontiguousarray(cand_off, np.int32); cand_idx = np.ascontiguousarray(cand_idx, np.int32)
+            if len(cand_idx) == 0:
+                cand_idx = np.zeros(1, np.int32)
+        bi, b, s, acc = self._outs(nq)
+        F.check(F.lib().hyorb_match_csr_host(self._h, F.ptr(q), nq, F.ptr(t), nt, F.ptr(cand_off), F.ptr(cand_idx), int(rule), thr, ratio,
+                                             F.ptr(bi), F.ptr(b), F.ptr(s), F.ptr(acc)))
+        return bi, b, s, acc
+
+    def SearchForTriangulation(self, desc1, desc2, cand_off=None, cand_idx=None, ratio=None):
+        """FeatureMatcher::SearchForTriangulation's scan (FeatureMatcher.cc:373-402): BestMatchBoWCriterion(TH_LOW, ratio)."""
+        return self.match(desc1, desc2, cand_off, cand_idx, F.RULE_BOW, self.settings.TH_LOW, ratio)
+
+    def grid_build(self, kps, bounds):
+        kps = np.ascontiguousarray(kps, F.KP_DTYPE)
+        off = np.zeros(F.GRID_COLS * F.GRID_ROWS + 1, np.int32); idx = np.zeros(max(len(kps), 1), np.int32)
+        b = F.Bounds(*[float(v) for v in bounds])
+        F.check(F.lib().hyorb_grid_build_host(self._h, F.ptr(kps), len(kps), C.byref(b), F.ptr(off), F.ptr(idx)))
+        return off, idx[: off[-1]].copy()
+
+    def SearchByProjection(self, t_kps, t_desc, bounds, queries, q_desc, t_uR=None, t_matched=None, thr=None, ratio=None):
+        """Per-landmark window search of FeatureMatcher::_SearchByProjection_ (FeatureMatcher.cc:57-121)."""
+        t_kps = np.ascontiguousarray(t_kps, F.KP_DTYPE); t_desc = np.ascontiguousarray(t_desc, np.uint8)
+        queries = np.ascontiguousarray(queries, F.WQ_DTYPE); q_desc = np.ascontiguousarray(q_desc, np.uint8)
+        t_uR = None if t_uR is None else np.ascontiguousarray(t_uR, np.float32)
+        t_matched = None if t_matched is None else np.ascontiguousarray(t_matched, np.uint8)
+        thr = float(self.settings.TH_HIGH if thr is None else thr)
+        ratio = float(self.settings.nnratio if ratio is None else ratio)
+        nq = len(queries)
+        b = F.Bounds(*[float(v) for v in bounds])
+        bi, bb, s, acc = self._outs(nq)
+        F.check(F.lib().hyorb_match_window_host(self._h, F.ptr(t_kps), F.ptr(t_desc), F.ptr(t_uR), F.ptr(t_matched), len(t_kps), C.byref(b),
+                                                F.ptr(queries), F.ptr(q_desc), nq, thr, ratio, F.ptr(bi), F.ptr(bb), F.ptr(s), F.ptr(acc)))
+        return bi, bb, s, acc
+
+    def RotationConsistency(self, angle_prev, angle_curr):
+        a = np.ascontiguousarray(angle_prev, np.float32); c = np.ascontiguousarray(angle_curr, np.float32)
+        keep = np.zeros(len(a), np.uint8)
+        F.check(F.lib().hyorb_rotation_consistency_host(self._h, F.ptr(a), F.ptr(c), len(a), F.ptr(keep)))
+        return keep
+
+    def match_bruteforce_device(self, d_q, nq, d_t, nt, rule, thr, ratio, d_best_idx, d_best, d_second, d_accepted):
+        F.check(F.lib().hyorb_match_bruteforce_device(self._h, d_q, nq, d_t, nt, int(rule), float(thr), float(ratio),
+                                                      d_best_idx, d_best, d_second, d_accepted))

@@ -1,0 +1,214 @@
+/*
+ * hyorb.h -- C ABI of libhyorb: a B200-native (sm_100a) ORB front end that is a drop-in for the
+ * ORB extraction / stereo association / descriptor matching path of bmhopkinson/hyslam.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the hySLAM tree).
+ * Rules of the boundary:
+ *   - plain pointers and sizes only; no C++ / OpenCV / torch types cross it;
+ *   - every function returns an int status (HYORB_OK == 0, negative == error); nothing throws;
+ *     hyorb_last_error() returns a thread-local message for the last failing call on this thread;
+ *   - a handle is single-threaded; distinct handles are independent (own CUDA stream + workspace);
+ *     there is no global mutable state (the reference mutates a shared factory);
+ *   - capacity overflow is reported (HYORB_ECAPACITY), never truncated silently;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with HYORB_ECUDA.
+ *   - "_host" entry points take host memory and stage H2D/D2H themselves (synchronous);
+ *     "_device" entry points take device pointers, enqueue on the handle's stream and do not sync.
+ */
+#ifndef HYORB_H
+#define HYORB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define HYORB_API
+#else
+#define HYORB_API __attribute__((visibility("default")))
+#endif
+
+enum {
+    HYORB_OK = 0,
+    HYORB_EINVAL = -1,       /* bad argument */
+    HYORB_ECAPACITY = -2,    /* an output or internal buffer was too small (nothing is truncated silently) */
+    HYORB_EUNSUPPORTED = -3, /* shape / parameter outside what the kernels implement (see DESIGN.md limits) */
+    HYORB_ENOMEM = -4,       /* host or device allocation failed */
+    HYORB_ECUDA = -5         /* CUDA runtime error, or no CUDA device */
+};
+
+#define HYORB_MAX_LEVELS 16
+#define HYORB_DESC_BYTES 32
+#define HYORB_GRID_COLS 64 /* FRAME_GRID_COLS, src/core/Frame.h:70 */
+#define HYORB_GRID_ROWS 48 /* FRAME_GRID_ROWS, src/core/Frame.h:69 */
+
+/* Same memory layout as cv::KeyPoint (28 bytes): a std::vector<cv::KeyPoint>::data() can be passed. */
+typedef struct hyorb_keypoint {
+    float x, y;      /* pt, in level-0 pixel coordinates (ORBExtractor.cpp:546-552) */
+    float size;      /* (float)(int)(31 * scale[octave])  (ORBExtractor.cpp:478)   */
+    float angle;     /* degrees, cv::fastAtan2 of the intensity centroid (ORBFinder.cpp:16-43) */
+    float response;  /* FAST score */
+    int32_t octave;
+    int32_t class_id; /* always -1 */
+} hyorb_keypoint;
+
+/* Mirrors HYSLAM::FeatureExtractorSettings (src/core/FeatureExtractorSettings.h:19-33) as parsed by
+ * ORBFactory::LoadSettings (src/features/ORBFactory.cpp:55-71). */
+typedef struct hyorb_extractor_params {
+    int32_t nfeatures;   /* N_Features */
+    float scale_factor;  /* scale_factor (float in the reference) */
+    int32_t nlevels;     /* N_Levels, 1..HYORB_MAX_LEVELS */
+    int32_t cell_px;     /* N_Cells: really the FAST cell edge in px (ORBExtractor.cpp:409) */
+    int32_t ini_th;      /* threshold_init -- accepted and ignored: the reference's FAST threshold is stuck */
+    int32_t min_th;      /* threshold_min  -- at 20 (ORBFinder.cpp:58-60, ORBFinder.h:92)                   */
+    uint32_t flags;      /* reserved, must be 0 (== reproduce the reference exactly) */
+} hyorb_extractor_params;
+
+typedef struct hyorb_extractor hyorb_extractor;
+
+/* ----- ORB extraction: replaces HYSLAM::ORBExtractor (src/features/ORBExtractor.h:63-116) ----- */
+
+/* ORBExtractor::ORBExtractor (ORBExtractor.cpp:76-119).  `device` is a CUDA ordinal.
+ * `cuda_stream` is a cudaStream_t to enqueue on, or NULL to let the handle create its own. */
+HYORB_API int hyorb_extractor_create(const hyorb_extractor_params *params, int device, void *cuda_stream,
+                                     hyorb_extractor **out);
+HYORB_API int hyorb_extractor_destroy(hyorb_extractor *h);
+
+/* FeatureExtractor::GetLevels / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (src/features/FeatureExtractor.h:29-35).  Each array: nlevels floats
+ * (NULL to skip).  quota: per-level feature quota mnFeaturesPerLevel (ORBExtractor.cpp:104-117). */
+HYORB_API int hyorb_extractor_get_levels(const hyorb_extractor *h);
+HYORB_API int hyorb_extractor_get_scales(const hyorb_extractor *h, float *scale, float *inv_scale,
+                                         float *sigma2, float *inv_sigma2, int32_t *quota);
+
+/* ORBExtractor::operator()(image, mask, keypoints, descriptors) (ORBExtractor.cpp:496-562) on ONE
+ * 8-bit gray HOST image (`stride` bytes per row).  The mask is ignored by the reference and has no
+ * parameter here.  Writes *n keypoints (levels concatenated 0..L-1, reference order) and n*32
+ * descriptor bytes.  An empty image (NULL / w<=0 / h<=0) returns HYORB_OK with *n = 0 (:499-500). */
+HYORB_API int hyorb_extract_host(hyorb_extractor *h, const uint8_t *gray, int width, int height, int stride,
+                                 hyorb_keypoint *kps, uint8_t *desc, int capacity, int *n);
+
+/* Throughput form of the same operator over n_images same-sized images (the offline / batched path:
+ * one launch sequence covers every level of every image).  Image i starts at images + i*image_stride.
+ * Outputs: kps[i*capacity + k], desc[(i*capacity + k)*32], counts[i]. */
+HYORB_API int hyorb_extract_batch_host(hyorb_extractor *h, const uint8_t *images, int n_images, int width, int height,
+                                       int stride, size_t image_stride, hyorb_keypoint *kps, uint8_t *desc,
+                                       int capacity, int32_t *counts);
+/* Same with DEVICE pointers for images and outputs; asynchronous on the handle's stream.  Errors that are
+ * only known on the device (capacity overflow) are reported by hyorb_extractor_sync(). */
+HYORB_API int hyorb_extract_batch_device(hyorb_extractor *h, const uint8_t *d_images, int n_images, int width,
+                                         int height, int stride, size_t image_stride, hyorb_keypoint *d_kps,
+                                         uint8_t *d_desc, int capacity, int32_t *d_counts);
+/* cudaStreamSynchronize + deferred device-side status of the launches since the last sync. */
+HYORB_API int hyorb_extractor_sync(hyorb_extractor *h);
+
+/* Stage outputs of the LAST extract call, for stage-by-stage parity tests (host destination buffers).
+ * what: */
+enum {
+    HYORB_DBG_PYRAMID = 0,    /* level bytes, tightly packed w*h (ORBExtractor::mvImagePyramid without borders) */
+    HYORB_DBG_BLURRED = 1,    /* GaussianBlur'ed level (ORBExtractor.cpp:536-537), w*h bytes */
+    HYORB_DBG_CANDIDATES = 2, /* per-cell FAST output before distribution: int32 triples (x, y, response), lattice
+                                 coordinates (pixel - 16), in the reference's order (cell row-major, row-major inside) */
+    HYORB_DBG_LEVEL_COUNT = 3 /* one int32: keypoints kept on this level after DistributeOctTree */
+};
+HYORB_API int hyorb_extractor_level_size(hyorb_extractor *h, int width, int height, int level, int *lw, int *lh);
+/* returns the number of bytes written (>= 0) or a negative status */
+HYORB_API long hyorb_extractor_debug_read(hyorb_extractor *h, int image_index, int what, int level, void *dst,
+                                          size_t dst_bytes);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+HYORB_API long hyorb_extractor_launch_count(const hyorb_extractor *h);
+
+/* ----- Stereo association: replaces HYSLAM::Stereomatcher (src/features/Stereomatcher.h:25-51) ----- */
+
+/* Camera + settings actually read by Stereomatcher::computeStereoMatches (Stereomatcher.cpp:36-156). */
+typedef struct hyorb_stereo_params {
+    float mbf;       /* Camera::mbf (stereo baseline * fx) */
+    float fx;        /* Camera::fx() */
+    int32_t n_rows;  /* (int)camera.mnMaxY */
+    float th_high;   /* FeatureMatcherSettings::TH_HIGH, default 100 (FeatureMatcher.h:98-103) */
+    float th_low;    /* FeatureMatcherSettings::TH_LOW,  default 50 */
+    float size_ref;  /* FeatureExtractorSettings::size_ref = 31 (FeatureExtractorSettings.h:27) */
+} hyorb_stereo_params;
+
+typedef struct hyorb_matcher hyorb_matcher; /* workspace + stream for the stereo / matching entry points */
+HYORB_API int hyorb_matcher_create(int device, void *cuda_stream, hyorb_matcher **out);
+HYORB_API int hyorb_matcher_destroy(hyorb_matcher *m);
+HYORB_API int hyorb_matcher_sync(hyorb_matcher *m);
+HYORB_API long hyorb_matcher_launch_count(const hyorb_matcher *m);
+
+/* Stereomatcher::computeStereoMatches + getData(uR, depth): uR[i], depth[i] for every left keypoint,
+ * -1 where unmatched.  best_r / best_dist (optional, may be NULL): matched right index / Hamming distance. */
+HYORB_API int hyorb_stereo_match_host(hyorb_matcher *m, const hyorb_stereo_params *sp,
+                                      const hyorb_keypoint *kps_l, const uint8_t *desc_l, int n_l,
+                                      const hyorb_keypoint *kps_r, const uint8_t *desc_r, int n_r,
+                                      float *uR, float *depth, int32_t *best_r, int32_t *best_dist);
+/* Batched device form over n_pairs stereo pairs laid out as hyorb_extract_batch_device leaves them:
+ * image 2p = left, 2p+1 = right of pair p; kps/desc/counts strided by `capacity`.  Outputs are
+ * [n_pairs][capacity]. */
+HYORB_API int hyorb_stereo_match_batch_device(hyorb_matcher *m, const hyorb_stereo_params *sp, int n_pairs,
+                                              const hyorb_keypoint *d_kps, const uint8_t *d_desc,
+                                              const int32_t *d_counts, int capacity, float *d_uR, float *d_depth,
+                                              int32_t *d_best_r, int32_t *d_best_dist);
+
+/* ----- Descriptor matching: the inner loops of HYSLAM::FeatureMatcher + MatchCriteria ----- */
+
+/* Acceptance rule applied to (best, second) after the scan of BestScoreCriterionCore
+ * (src/features/MatchCriteria.cpp:248-280): */
+enum {
+    HYORB_RULE_LANDMARK = 0, /* BestScoreCriterion::apply   (:214-246): best <= thr && !(best > ratio*second) */
+    HYORB_RULE_BOW = 1,      /* BestMatchBoWCriterion::apply (:601-635): best <  thr &&   best < ratio*second */
+    HYORB_RULE_MONOINIT = 2  /* MonoInitBestScore::apply    (:486-523): best <= thr &&   best < second*ratio */
+};
+
+/* ORBDistance::distance (src/features/low_level/DescriptorDistance.cpp:9-25) scanned over candidate lists.
+ * cand_off[nq+1] / cand_idx: CSR lists of target indices per query (a DBoW2 node's feature list,
+ * FeatureMatcher.cc:281-345); both NULL = every target in index order (C4: brute force).
+ * Outputs per query: best_idx (-1 if no candidate), best / second Hamming distance (65535 = none,
+ * i.e. the reference's FLT_MAX), accepted (0/1). */
+HYORB_API int hyorb_match_csr_host(hyorb_matcher *m, const uint8_t *q_desc, int nq, const uint8_t *t_desc, int nt,
+                                   const int32_t *cand_off, const int32_t *cand_idx, int rule, float thr, float ratio,
+                                   int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted);
+/* Device-pointer brute force (cand lists NULL), asynchronous. */
+HYORB_API int hyorb_match_bruteforce_device(hyorb_matcher *m, const uint8_t *d_q_desc, int nq, const uint8_t *d_t_desc,
+                                            int nt, int rule, float thr, float ratio, int32_t *d_best_idx,
+                                            uint16_t *d_best, uint16_t *d_second, uint8_t *d_accepted);
+
+typedef struct hyorb_bounds { float min_x, max_x, min_y, max_y; } hyorb_bounds; /* Frame::mnMinX.. (Frame.cc:62-66) */
+
+/* Frame::AssignFeaturesToGrid + PosInGrid (src/core/Frame.cc:137-153, 459-469): 64 x 48 grid, round().
+ * cell_off[64*48+1], cell_idx[n]: CSR, cell id = ix*48 + iy, insertion order inside a cell. */
+HYORB_API int hyorb_grid_build_host(hyorb_matcher *m, const hyorb_keypoint *kps, int n, const hyorb_bounds *b,
+                                    int32_t *cell_off, int32_t *cell_idx);
+
+/* One query per landmark of FeatureMatcher::_SearchByProjection_ (FeatureMatcher.cc:57-121). */
+typedef struct hyorb_window_query {
+    float u, v, r;          /* projected position and search radius (FeatureMatcher.cc:88-92) */
+    float size_lo, size_hi; /* FeatureSizeCriterion bounds: keep size_lo < kp.size < size_hi (MatchCriteria.cpp:350-360) */
+    float ur, ur_radius;    /* StereoConsistencyCriterion (:149-177); ur_radius < 0 = mono camera, skip */
+} hyorb_window_query;
+
+/* Frame::GetFeaturesInAreaNEW (Frame.cc:416-457) -> PreviouslyMatchedCriterion (MatchCriteria.cpp:124-144)
+ * -> FeatureSizeCriterion -> StereoConsistencyCriterion -> BestScoreCriterion, for nq queries against one
+ * frame's keypoints.  t_uR / t_matched may be NULL.  Builds the grid internally. */
+HYORB_API int hyorb_match_window_host(hyorb_matcher *m, const hyorb_keypoint *t_kps, const uint8_t *t_desc,
+                                      const float *t_uR, const uint8_t *t_matched, int nt, const hyorb_bounds *b,
+                                      const hyorb_window_query *queries, const uint8_t *q_desc, int nq, float thr,
+                                      float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
+                                      uint8_t *accepted);
+
+/* RotationConsistency + ComputeThreeMaxima (MatchCriteria.cpp:684-767): keep[i] = 1 if match i (angles of the
+ * two matched keypoints, pairs in ascending current-index order) falls in one of the 3 dominant rotation bins. */
+HYORB_API int hyorb_rotation_consistency_host(hyorb_matcher *m, const float *angle_prev, const float *angle_curr,
+                                              int n, uint8_t *keep);
+
+/* ----- misc ----- */
+HYORB_API const char *hyorb_last_error(void);
+HYORB_API const char *hyorb_version(void);
+HYORB_API int hyorb_device_count(void); /* 0 when no CUDA device / driver */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYORB_H */

@@ -1,0 +1,150 @@
+"""GPU parity of the extraction path (pyramid, FAST + cell-local NMS, quadtree distribution, blur, orientation,
+rBRIEF) through the C ABI against the CPU oracle and the committed golden fixtures.  Bit-exact, exact ORDER."""
+import os
+
+import numpy as np
+import pytest
+
+import hyslam_b200 as hb
+from hyslam_b200 import _ffi as F, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _settings(nfeatures=1000, scale=1.2, nlevels=8, cell=30):
+    return hb.FeatureExtractorSettings(nFeatures=nfeatures, fScaleFactor=scale, nLevels=nlevels, N_CELLS=cell)
+
+
+def _oparams(s):
+    return O.default_params(s.nFeatures, s.fScaleFactor, s.nLevels, s.N_CELLS)
+
+
+def _bits(a):
+    return a.view(np.uint32) if a.dtype.kind == "f" else a
+
+
+def assert_kps_equal(k, gk, what=""):
+    assert len(k) == len(gk), f"{what}: {len(k)} keypoints vs {len(gk)} expected"
+    for f in gk.dtype.names:
+        bad = np.nonzero(_bits(np.ascontiguousarray(k[f])) != _bits(np.ascontiguousarray(gk[f])))[0]
+        assert len(bad) == 0, f"{what}: field {f} differs at {bad[:8]} ({len(bad)} of {len(k)}): got {k[f][bad[:4]]} want {gk[f][bad[:4]]}"
+
+
+CASES = [
+    ("noise", 240, 320, 3, 500),
+    ("blocks", 280, 376, 5, 700),
+    ("noise", 480, 752, 0, 1000),      # C1
+    ("blocks", 480, 752, 1, 1000),     # C1, sparse corners: empty cells, quadtree early exits
+    ("noise", 376, 1241, 2, 2000),     # C2
+    ("blocks", 376, 1241, 4, 2000),
+]
+
+
+@pytest.mark.parametrize("kind,h,w,seed,nf", CASES)
+def test_extract_stages_match_oracle(kind, h, w, seed, nf):
+    img = (synth.noise_image if kind == "noise" else synth.blocks_image)(h, w, seed)
+    s = _settings(nf)
+    ok, od, info = O.extract(img, _oparams(s), debug=True)
+    ex = hb.ORBExtractor(s)
+    k, d = ex(img, None)
+    errs = []
+    for l in range(s.nLevels):
+        if not np.array_equal(ex.debug_level(w, h, l, F.DBG_PYRAMID), info["pyramid"][l]):
+            errs.append(f"pyramid level {l}")
+    for l in range(s.nLevels):
+        cx, cy, cr = info["cand"][l]
+        want = np.stack([cx, cy, cr], 1).astype(np.int32)
+        got = ex.debug_candidates(w, h, l)
+        if got.shape != want.shape or not np.array_equal(got, want):
+            errs.append(f"FAST candidates level {l}: got {len(got)} want {len(want)}")
+    for l in range(s.nLevels):
+        if ex.debug_level_count(l) != info["level_count"][l]:
+            errs.append(f"quadtree count level {l}: got {ex.debug_level_count(l)} want {info['level_count'][l]}")
+    for l in range(s.nLevels):
+        if info["level_count"][l] and not np.array_equal(ex.debug_level(w, h, l, F.DBG_BLURRED), info["blurred"][l]):
+            errs.append(f"blur level {l}")
+    assert not errs, errs
+    assert_kps_equal(k, ok, "keypoints")
+    assert np.array_equal(d, od), f"descriptors differ in {np.count_nonzero((d != od).any(1))} rows"
+    ex.close()
+
+
+@pytest.mark.parametrize("name", ["ext_noise_320x240", "ext_blocks_376x280", "ext_blocks_640x360", "ext_c1_noise_752x480"])
+def test_extract_matches_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    fn = synth.noise_image if str(g["kind"]) == "noise" else synth.blocks_image
+    img = fn(int(g["h"]), int(g["w"]), int(g["seed"]))
+    s = _settings(int(g["nfeatures"]), float(g["scale_factor"]), int(g["nlevels"]), int(g["cell_px"]))
+    ex = hb.ORBExtractor(s)
+    k, d = ex(img, None)
+    assert [ex.debug_level_count(l) for l in range(s.nLevels)] == g["level_count"].tolist()
+    assert_kps_equal(k, g["kps"], name)
+    assert np.array_equal(d, g["desc"])
+
+
+def test_c3_full_size_matches_oracle():
+    """C3: 3840x2160, 8000 features (oracle takes a few seconds)."""
+    img = synth.blocks_image(2160, 3840, 11)
+    img[400:1400, 600:2600] = synth.noise_image(1000, 2000, 12)      # a dense region on a sparse canvas
+    s = _settings(8000)
+    ok, od = O.extract(img, _oparams(s), cap=40000)
+    ex = hb.ORBExtractor(s)
+    k, d = ex(img, None, capacity=40000)
+    assert_kps_equal(k, ok, "C3")
+    assert np.array_equal(d, od)
+
+
+def test_batch_equals_single_and_is_deterministic():
+    imgs = np.stack([synth.noise_image(376, 1241, 20 + i) if i % 2 == 0 else synth.blocks_image(376, 1241, 20 + i) for i in range(6)])
+    s = _settings(2000)
+    ex = hb.ORBExtractor(s)
+    kps, desc, counts = ex.extract_batch(imgs)
+    kps2, desc2, counts2 = ex.extract_batch(imgs)
+    assert np.array_equal(counts, counts2)
+    for i in range(len(imgs)):
+        k1, d1 = ex(imgs[i], None)
+        n = counts[i]
+        assert n == len(k1)
+        assert_kps_equal(kps[i, :n], k1, f"image {i}")
+        assert np.array_equal(desc[i, :n], d1)
+        assert np.array_equal(kps[i, :n], kps2[i, :n]) and np.array_equal(desc[i, :n], desc2[i, :n])
+    ok, od = O.extract(imgs[3], _oparams(s))
+    assert_kps_equal(kps[3, :counts[3]], ok, "batch image 3 vs oracle")
+    assert np.array_equal(desc[3, :counts[3]], od)
+
+
+def test_strided_input_and_other_params():
+    big = synth.noise_image(300, 500, 9)
+    view = big[10:250, 17:417]                        # non-contiguous rows, odd offset
+    s = _settings(600, scale=1.3, nlevels=5, cell=24)
+    ok, od = O.extract(np.ascontiguousarray(view), _oparams(s))
+    ex = hb.ORBExtractor(s)
+    k, d = ex(view, None)
+    assert_kps_equal(k, ok, "strided")
+    assert np.array_equal(d, od)
+    assert np.array_equal(ex.GetScaleFactors(), O.scale_tables(_oparams(s))[0])
+    assert ex.features_per_level().tolist() == O.scale_tables(_oparams(s))[4].tolist()
+
+
+def test_flat_image_gives_no_keypoints_and_empty_image_returns_silently():
+    ex = hb.ORBExtractor(_settings(500))
+    k, d = ex(np.full((240, 320), 77, np.uint8), None)
+    assert len(k) == 0 and d.shape == (0, 32)
+    k, d = ex(np.zeros((0, 0), np.uint8), None)
+    assert len(k) == 0
+
+
+def test_error_behaviour():
+    ex = hb.ORBExtractor(_settings(1000))
+    img = synth.noise_image(480, 752, 0)
+    with pytest.raises(hb.HyorbError) as e:
+        ex(img, None, capacity=100)                   # output capacity overflow is reported, not truncated
+    assert e.value.rc == F.ECAPACITY
+    k, _ = ex(img, None)                              # the handle stays usable
+    assert len(k) > 900
+    with pytest.raises(hb.HyorbError) as e:
+        ex(synth.noise_image(100, 120, 1), None)      # level 7 smaller than one FAST cell: the reference divides by zero
+    assert e.value.rc == F.EUNSUPPORTED
+    with pytest.raises(ValueError):
+        ex(img.astype(np.float32), None)
