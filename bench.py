@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- ORB stereo front end throughput on B200 (BASELINE.json metric: ORB frames/s, extract + match).
+
+Workload (config.workload): C2 -- KITTI-shaped 1241x376 stereo pairs, 2000 features per image, 8 levels, scale 1.2,
+extract(left) + extract(right) + ComputeStereoMatches.  One "frame" = one stereo pair.  One "step" = one batch of
+`--pairs` pairs through hyorb_process_stereo_batch_* (ImageProcessing::ProcessStereoImage, ImageProcessing.cpp:69-116).
+
+  value : frames/s with the batch already resident in HBM (device pointers in, device pointers out), CUDA events on
+          the launching stream, max over ranks.
+  e2e   : the same through the host-buffer C-ABI call (pinned host images in, host keypoints/descriptors/uR/depth
+          out), H2D and D2H inside the timed region.
+  roofline : dominant kernel (FAST detection) algorithmic bytes / its live CUDA-event duration vs MEASURED_PEAKS hbm_gbs.
+  cpu_baseline : the CPU oracle port (oracle/orb_oracle.c, all host threads) on a bounded sample of the same workload.
+
+`--impl reference` times the reference's CPU algorithm (the oracle port: the reference itself cannot be compiled
+here, DESIGN.md "Oracle") on the box's host cores with the same metric/config.
+Multi-GPU: one process per GPU (torchrun), frames sharded by rank, no data-path collective (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT = 1241, 376, 2000
+CAM = dict(mbf=386.1448, fx=718.856, mnMaxY=376.0)
+METRIC = "orb_stereo_frames_per_sec"
+UNIT = "frames/s"
+
+
+def workload_name(pairs):
+    return f"C2: {W}x{H} stereo pairs, {NFEAT} features/image, 8 levels, scale 1.2, extract L+R + ComputeStereoMatches; {pairs} pairs per step"
+
+
+def make_pairs(n_pairs, seed0=1000, distinct=8):
+    """[2*n_pairs, H, W] uint8, (left, right) interleaved.  `distinct` pairs come from the seeded generators
+    (hyslam_b200/synth.py, G-noise); the rest are horizontal rolls of them (distinct addresses and content
+    positions, same statistics) to keep host-side generation short."""
+    from hyslam_b200 import synth
+    base = [synth.stereo_pair(H, W, seed0 + i) for i in range(min(distinct, n_pairs))]
+    out = np.empty((2 * n_pairs, H, W), np.uint8)
+    for p in range(n_pairs):
+        L, R = base[p % len(base)]
+        s = 37 * (p // len(base))
+        out[2 * p] = np.roll(L, s, axis=1)
+        out[2 * p + 1] = np.roll(R, s, axis=1)
+    return out
+
+
+def level_bytes():
+    """sum of pyramid level pixels for one WxH image (ORBExtractor.cpp:569)"""
+    from oracle import oracle as O      # cpu-side constant tables only (bench.py may use oracle/ as the checker/baseline)
+    return [w * h for (w, h) in O.level_sizes(O.default_params(NFEAT), W, H)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, l in self.lines:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.2):
+                continue
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_run(images, n_threads):
+    """reference-shaped CPU run of the same step on host cores: the oracle's ORBExtractor restatement over all images
+    (pthread pool, one extractor per thread as ImageProcessing.cpp:82-84 does for L/R) + its Stereomatcher restatement."""
+    from oracle import oracle as O
+    p = O.default_params(NFEAT)
+    kps, desc, counts = O.extract_batch(images, p, nthreads=n_threads)
+    sp = O.StereoParams(CAM["mbf"], CAM["fx"], int(CAM["mnMaxY"]), 100.0, 50.0, 31.0)
+    nk = 0
+    for i in range(0, len(images), 2):
+        nl, nr = counts[i], counts[i + 1]
+        O.stereo_match(sp, kps[i, :nl], desc[i, :nl], kps[i + 1, :nr], desc[i + 1, :nr])
+        nk += int(nl + nr)
+    return nk
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm on host cores (oracle port; see module docstring)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    O.build()
+    cores = len(os.sched_getaffinity(0))
+    sample_pairs = max(1, min(args.pairs, cores // 2 if cores >= 2 else 1))    # ~one image per host thread per step
+    images = make_pairs(sample_pairs)
+    for _ in range(args.warmup):
+        cpu_port_run(images, cores)
+    t0 = time.perf_counter()
+    nk = 0
+    for _ in range(args.steps):
+        nk += cpu_port_run(images, cores)
+    dt = time.perf_counter() - t0
+    value = sample_pairs * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": {"workload": workload_name(args.pairs), "sample": f"{sample_pairs} pairs per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample_pairs} pairs x {args.steps} steps of the same workload, all {cores} host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "kpts_per_sec": nk / dt,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=32, help="stereo pairs per step (per GPU)")
+    ap.add_argument("--rotate", type=int, default=10, help="distinct device-resident batches cycled so inputs exceed L2")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import hyslam_b200 as hb
+    from hyslam_b200 import _ffi as F
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (libhyorb has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    P = args.pairs
+    B = 2 * P
+    cap = 2560                       # >= keypoints per image (about 2010 for 2000 requested features)
+    stream = torch.cuda.Stream(device=dev)     # an explicit stream: the handle enqueues on it and the events are recorded on it
+    torch.cuda.set_stream(stream)
+    ex = hb.ORBExtractor(hb.FeatureExtractorSettings(nFeatures=NFEAT), device=local, stream=stream.cuda_stream)
+    cam = hb.StereoCamera(**CAM)
+    sp = ex.stereo_params(cam)
+
+    # ---- inputs: `rotate` distinct batches resident in HBM (rotate * B * W*H bytes > 126 MB L2), rank-specific seeds
+    host_batches = [make_pairs(P, seed0=1000 + 100 * rank + 10 * r) for r in range(min(args.rotate, 3))]
+    pinned = [torch.from_numpy(hb_).pin_memory() for hb_ in host_batches]
+    dev_batches = []
+    for r in range(args.rotate):
+        t = pinned[r % len(pinned)].to(dev, non_blocking=True)
+        if r >= len(pinned):
+            t = torch.roll(t, shifts=11 * r, dims=2)
+        dev_batches.append(t.contiguous())
+    in_bytes = B * W * H
+    d_kps = torch.empty((B, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_counts = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_uR = torch.empty((P, cap), dtype=torch.float32, device=dev)
+    d_depth = torch.empty((P, cap), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device(i):
+        t = dev_batches[i % len(dev_batches)]
+        ex.process_stereo_batch_device(sp, t.data_ptr(), P, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                       d_counts.data_ptr(), d_uR.data_ptr(), d_depth.data_ptr())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (value)
+    for i in range(args.warmup):
+        step_device(i)
+    ex.sync()
+    ex.set_profiling(True)
+    ex.stage_times(reset=True)
+    launches0 = ex.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    ex.sync()                                         # surfaces device-side status (capacity etc.)
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms = e0.elapsed_time(e1)
+    launches = ex.launch_count() - launches0
+    stage_ms, stage_calls = ex.stage_times(reset=True)
+    ex.set_profiling(False)
+    counts = d_counts.cpu().numpy()
+    matched = int(((d_uR.cpu().numpy() >= 0) & (np.arange(cap)[None, :] < counts[0::2][:, None])).sum())
+    kp_per_step = int(counts.sum())
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_max = float(tmax.item())
+    value = world * P * args.steps / (ms_max / 1e3)
+
+    # ---- end to end through the host-buffer ABI call (pinned host in, host out)
+    h_in = pinned[0].numpy()
+    outs = (np.empty((B, cap), F.KP_DTYPE), np.empty((B, cap, 32), np.uint8), np.zeros(B, np.int32),
+            np.empty((P, cap), np.float32), np.empty((P, cap), np.float32))
+    pin_out = [torch.from_numpy(o.view(np.uint8).reshape(-1)).pin_memory() for o in outs]
+    outs = tuple(po.numpy().view(o.dtype).reshape(o.shape) for po, o in zip(pin_out, outs))
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ex.process_stereo_batch(h_in, cam, capacity=cap, out=outs)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        ex.process_stereo_batch(pinned[i % len(pinned)].numpy(), cam, capacity=cap, out=outs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tm = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * e2e_steps / float(tm.item())
+    d2h = sum(o.nbytes for o in outs)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    lv = level_bytes()
+    sumP = sum(lv)
+    alg = {   # algorithmic bytes per image
+        "pyramid": sum(lv[:-1]) + sum(lv[1:]),
+        "fast": sumP,
+        "blur": 2 * sumP,                                # materialised blur: read level + write blurred level
+        "describe": sumP + 60 * (kp_per_step / B),       # read blurred windows (<= one pass) + 28 B keypoint + 32 B descriptor
+        "quadtree": 0, "stereo": 0,
+    }
+    stages = {}
+    for k, v in stage_ms.items():
+        per_launch_ms = v / max(stage_calls, 1)
+        stages[k] = {"ms_per_step": per_launch_ms, "share": v / max(sum(stage_ms.values()), 1e-9),
+                     "algorithmic_GBps": (alg[k] * B / (per_launch_ms * 1e-3) / 1e9) if alg.get(k) and per_launch_ms > 0 else None}
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    dom_ms = stage_ms[dom] / max(stage_calls, 1)
+    achieved = alg[dom] * B / (dom_ms * 1e-3) / 1e9 if alg.get(dom) else 0.0
+    roofline = {"bound": "hbm", "kernel": {"fast": "k_fast", "pyramid": "k_resize", "blur": "k_blur", "describe": "k_describe",
+                                            "quadtree": "k_quadtree", "stereo": "k_stereo"}[dom],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom] * B, "launch_ms": dom_ms,
+                "note": "INT/LSU-bound kernel reported against the HBM roofline as the contract asks; see DESIGN.md"}
+
+    # ---- CPU baseline (oracle port, all host threads) on a bounded sample
+    cpu = None
+    if not args.no_cpu:
+        cores = len(os.sched_getaffinity(0))
+        sample_pairs = max(1, min(P, cores // 2 if cores >= 2 else 1))
+        imgs = host_batches[0][: 2 * sample_pairs]
+        t0 = time.perf_counter()
+        reps = 0
+        while True:
+            cpu_port_run(imgs, cores)
+            reps += 1
+            if time.perf_counter() - t0 > args.cpu_seconds or reps >= 50:
+                break
+        dtc = time.perf_counter() - t0
+        cpu = {"value": sample_pairs * reps / dtc, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{sample_pairs} pairs x {reps} repetitions of the same workload ({dtc:.1f} s), scalar C port of the reference "
+                         f"(oracle/orb_oracle.c) on all {cores} host threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": workload_name(P), "pairs_per_step_per_gpu": P, "partition": "frames sharded by rank, no collective on the data path",
+                   "l2": f"{args.rotate} distinct device-resident input batches cycled ({args.rotate * in_bytes / 1e6:.0f} MB of inputs > 126 MB L2); "
+                         f"per-step intermediates ({B} pyramids + blurred copies) also exceed L2"},
+        "kpts_per_sec": value * kp_per_step / P, "keypoints_per_frame": kp_per_step / P, "stereo_matches_per_frame": matched / P,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "hyorb_process_stereo_batch_host (pinned host buffers)"},
+        "gpu_launches": int(launches), "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

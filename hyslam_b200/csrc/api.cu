@@ -57,7 +57,14 @@ struct hyorb_extractor {
     int Bcap = 0;
     DevBuf d_pyr, d_blur, d_cand, d_qcode, d_qnode, d_qleaf, d_sel, d_candCount, d_selCount, d_status;
     DevBuf d_in, d_kps, d_desc, d_counts;       // staging of the _host entry points
+    DevBuf d_rowtab, d_bestd, d_uR, d_depth;    // stereo stage of the ProcessStereoImage entry points
     long launches = 0;
+    // per-stage CUDA-event timing (events on the launching stream; read back by hyorb_extractor_stage_times)
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_free;
+    std::vector<std::vector<cudaEvent_t>> ev_pending;   // HYORB_N_STAGES+1 events per profiled call
+    double stage_ms[HYORB_N_STAGES] = {0, 0, 0, 0, 0, 0};
+    long stage_calls = 0;
     // last call (for debug_read)
     int last_B = 0;
     Level0 last_l0{nullptr, 0, 0};
@@ -105,23 +112,53 @@ static int ex_ensure_workspace(hyorb_extractor *h, int B)
     return HYORB_OK;
 }
 
-static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_keypoint *d_kps, uint8_t *d_desc, int capacity, int32_t *d_counts)
+static int ex_event(hyorb_extractor *h, std::vector<cudaEvent_t> *set)
+{
+    if (!h->profile) return HYORB_OK;
+    cudaEvent_t e;
+    if (!h->ev_free.empty()) { e = h->ev_free.back(); h->ev_free.pop_back(); }
+    else HY_CUDA(cudaEventCreate(&e));
+    HY_CUDA(cudaEventRecord(e, h->stream));
+    set->push_back(e);
+    return HYORB_OK;
+}
+
+// the whole extraction pipeline (+ optional stereo association over consecutive image pairs) for B images
+static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_keypoint *d_kps, uint8_t *d_desc, int capacity, int32_t *d_counts,
+                  const hyorb_stereo_params *sp = nullptr, float *d_uR = nullptr, float *d_depth = nullptr)
 {
     HY_CUDA(cudaSetDevice(h->device));
     HY_TRY(ex_ensure_plan(h, w, hgt));
     HY_TRY(ex_ensure_workspace(h, B));
+    if (sp) {
+        HY_TRY(h->d_rowtab.ensure(sizeof(int32_t) * (size_t)capacity * 20 * (B / 2)));
+        HY_TRY(h->d_bestd.ensure(sizeof(int32_t) * (size_t)capacity * (B / 2)));
+    }
     const PlanDev &P = h->plan.dev;
     const PlanDev *dp = h->d_plan.as<PlanDev>();
     cudaStream_t st = h->stream;
+    std::vector<cudaEvent_t> evs;
     HY_CUDA(cudaMemsetAsync(h->d_candCount.p, 0, sizeof(int) * HYORB_MAX_LEVELS * (size_t)B, st));
+    HY_TRY(ex_event(h, &evs));
     HY_TRY(launch_pyramid(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_resize.as<ResizeTab>(), B, st, &h->launches));
+    HY_TRY(ex_event(h, &evs));
     HY_TRY(launch_fast(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_cand.as<uint32_t>(), h->d_candCount.as<int>(), h->d_status.as<int>(), B, st, &h->launches));
+    HY_TRY(ex_event(h, &evs));
     HY_TRY(launch_quadtree(P, dp, h->d_cand.as<uint32_t>(), h->d_candCount.as<int>(), h->d_lut.as<uint32_t>(), h->d_qcode.as<uint32_t>(),
                            h->d_qnode.as<uint16_t>(), h->d_qleaf.as<uint2>(), h->d_sel.as<uint32_t>(), h->d_selCount.as<int>(),
                            h->d_status.as<int>(), B, st, &h->launches));
+    HY_TRY(ex_event(h, &evs));
     HY_TRY(launch_blur(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_blur.as<uint8_t>(), B, st, &h->launches));
+    HY_TRY(ex_event(h, &evs));
     HY_TRY(launch_describe(P, dp, h->d_blur.as<uint8_t>(), h->d_sel.as<uint32_t>(), h->d_selCount.as<int>(), d_kps, d_desc, capacity, d_counts,
                            h->d_status.as<int>(), B, st, &h->launches));
+    HY_TRY(ex_event(h, &evs));
+    if (sp) {
+        HY_TRY(launch_stereo(*sp, B / 2, d_kps, d_desc, d_counts, capacity, h->d_rowtab.as<int32_t>(), capacity * 20, d_uR, d_depth, nullptr,
+                             h->d_bestd.as<int32_t>(), h->d_status.as<int>(), st, &h->launches));
+    }
+    HY_TRY(ex_event(h, &evs));
+    if (h->profile) h->ev_pending.push_back(evs);
     h->last_B = B; h->last_l0 = l0;
     return HYORB_OK;
 }
@@ -179,8 +216,11 @@ HYORB_API int hyorb_extractor_destroy(hyorb_extractor *h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf *bufs[] = {&h->d_plan, &h->d_resize, &h->d_lut, &h->d_pyr, &h->d_blur, &h->d_cand, &h->d_qcode, &h->d_qnode, &h->d_qleaf, &h->d_sel,
-                      &h->d_candCount, &h->d_selCount, &h->d_status, &h->d_in, &h->d_kps, &h->d_desc, &h->d_counts};
+                      &h->d_candCount, &h->d_selCount, &h->d_status, &h->d_in, &h->d_kps, &h->d_desc, &h->d_counts,
+                      &h->d_rowtab, &h->d_bestd, &h->d_uR, &h->d_depth};
     for (DevBuf *b : bufs) b->release();
+    for (auto &set : h->ev_pending) for (cudaEvent_t e : set) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_free) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return HYORB_OK;
@@ -275,6 +315,78 @@ HYORB_API int hyorb_extract_host(hyorb_extractor *h, const uint8_t *gray, int wi
         HY_CUDA(cudaStreamSynchronize(h->stream));
     }
     *n = cnt;
+    return HYORB_OK;
+}
+
+HYORB_API int hyorb_process_stereo_batch_device(hyorb_extractor *h, const hyorb_stereo_params *sp, const uint8_t *d_images, int n_pairs,
+                                                int width, int height, int stride, size_t image_stride, hyorb_keypoint *d_kps, uint8_t *d_desc,
+                                                int capacity, int32_t *d_counts, float *d_uR, float *d_depth)
+{
+    if (!h || !sp || !d_images || !d_kps || !d_desc || !d_counts || !d_uR || !d_depth) { set_error("null argument"); return HYORB_EINVAL; }
+    if (n_pairs < 1 || width < 1 || height < 1 || stride < width || capacity < 1) { set_error("bad shape"); return HYORB_EINVAL; }
+    if (2 * n_pairs > 65535) { set_error("at most 32767 pairs per batch"); return HYORB_EUNSUPPORTED; }
+    Level0 l0{d_images, stride, (unsigned long long)image_stride};
+    return ex_run(h, l0, 2 * n_pairs, width, height, d_kps, d_desc, capacity, d_counts, sp, d_uR, d_depth);
+}
+
+HYORB_API int hyorb_process_stereo_batch_host(hyorb_extractor *h, const hyorb_stereo_params *sp, const uint8_t *images, int n_pairs, int width,
+                                              int height, int stride, size_t image_stride, hyorb_keypoint *kps, uint8_t *desc, int capacity,
+                                              int32_t *counts, float *uR, float *depth)
+{
+    if (!h || !sp || !images || !kps || !desc || !counts || !uR || !depth) { set_error("null argument"); return HYORB_EINVAL; }
+    if (n_pairs < 1 || width < 1 || height < 1 || stride < width || capacity < 1) { set_error("bad shape"); return HYORB_EINVAL; }
+    if (2 * n_pairs > 65535) { set_error("at most 32767 pairs per batch"); return HYORB_EUNSUPPORTED; }
+    const int n_images = 2 * n_pairs;
+    HY_CUDA(cudaSetDevice(h->device));
+    HY_TRY(ex_ensure_plan(h, width, height));
+    const PlanDev &P = h->plan.dev;
+    const int pitch = P.lv[0].pitch;
+    const size_t dstride = ((size_t)pitch * height + 255) & ~(size_t)255;
+    HY_TRY(h->d_in.ensure(dstride * n_images + 256));
+    HY_TRY(h->d_kps.ensure(sizeof(hyorb_keypoint) * (size_t)capacity * n_images));
+    HY_TRY(h->d_desc.ensure((size_t)HYORB_DESC_BYTES * capacity * n_images));
+    HY_TRY(h->d_counts.ensure(sizeof(int32_t) * n_images));
+    HY_TRY(h->d_uR.ensure(sizeof(float) * (size_t)capacity * n_pairs));
+    HY_TRY(h->d_depth.ensure(sizeof(float) * (size_t)capacity * n_pairs));
+    for (int i = 0; i < n_images; i++)
+        HY_CUDA(cudaMemcpy2DAsync(h->d_in.as<uint8_t>() + dstride * i, pitch, images + image_stride * i, stride, width, height,
+                                  cudaMemcpyHostToDevice, h->stream));
+    Level0 l0{h->d_in.as<uint8_t>(), pitch, (unsigned long long)dstride};
+    HY_TRY(ex_run(h, l0, n_images, width, height, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), capacity, h->d_counts.as<int32_t>(), sp,
+                  h->d_uR.as<float>(), h->d_depth.as<float>()));
+    HY_CUDA(cudaMemcpyAsync(counts, h->d_counts.p, sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, h->stream));
+    HY_CUDA(cudaMemcpyAsync(kps, h->d_kps.p, sizeof(hyorb_keypoint) * (size_t)capacity * n_images, cudaMemcpyDeviceToHost, h->stream));
+    HY_CUDA(cudaMemcpyAsync(desc, h->d_desc.p, (size_t)HYORB_DESC_BYTES * capacity * n_images, cudaMemcpyDeviceToHost, h->stream));
+    HY_CUDA(cudaMemcpyAsync(uR, h->d_uR.p, sizeof(float) * (size_t)capacity * n_pairs, cudaMemcpyDeviceToHost, h->stream));
+    HY_CUDA(cudaMemcpyAsync(depth, h->d_depth.p, sizeof(float) * (size_t)capacity * n_pairs, cudaMemcpyDeviceToHost, h->stream));
+    return ex_sync(h);
+}
+
+HYORB_API int hyorb_extractor_set_profiling(hyorb_extractor *h, int enable)
+{
+    if (!h) { set_error("null handle"); return HYORB_EINVAL; }
+    h->profile = enable != 0;
+    return HYORB_OK;
+}
+
+HYORB_API int hyorb_extractor_stage_times(hyorb_extractor *h, double *ms, long *calls, int reset)
+{
+    if (!h) { set_error("null handle"); return HYORB_EINVAL; }
+    HY_CUDA(cudaSetDevice(h->device));
+    HY_CUDA(cudaStreamSynchronize(h->stream));
+    for (auto &set : h->ev_pending) {
+        for (size_t i = 0; i + 1 < set.size() && i < HYORB_N_STAGES; i++) {
+            float t = 0.f;
+            HY_CUDA(cudaEventElapsedTime(&t, set[i], set[i + 1]));
+            h->stage_ms[i] += t;
+        }
+        h->stage_calls++;
+        for (cudaEvent_t e : set) h->ev_free.push_back(e);
+    }
+    h->ev_pending.clear();
+    for (int i = 0; i < HYORB_N_STAGES; i++) { if (ms) ms[i] = h->stage_ms[i]; if (reset) h->stage_ms[i] = 0; }
+    if (calls) *calls = h->stage_calls;
+    if (reset) h->stage_calls = 0;
     return HYORB_OK;
 }
 

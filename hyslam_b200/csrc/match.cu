@@ -177,10 +177,10 @@ k_grid_fill(const int32_t *__restrict__ cell_of, int n, const int32_t *__restric
         for (int w = 0; w < 32; w++) {
             if (warp == w) {
                 const unsigned peers = __match_any_sync(0xffffffffu, c);
+                const int rank = __popc(peers & ((1u << lane) - 1));
+                const int first = c >= 0 ? s_fill[c] : 0;
+                __syncwarp();                      // every lane: all reads of s_fill precede the leaders' updates
                 if (c >= 0) {
-                    const int rank = __popc(peers & ((1u << lane) - 1));
-                    const int first = s_fill[c];
-                    __syncwarp();
                     if (rank == 0) s_fill[c] = first + __popc(peers);
                     cell_idx[s_off[c] + first + rank] = i;
                 }

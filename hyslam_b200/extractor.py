@@ -93,6 +93,42 @@ class ORBExtractor:
     def sync(self):
         F.check(F.lib().hyorb_extractor_sync(self._h))
 
+    # ---- ImageProcessing::ProcessStereoImage (src/main/ImageProcessing.cpp:69-116) over a batch of pairs
+    @staticmethod
+    def stereo_params(camera, matcher_settings=None, size_ref=31.0):
+        from .settings import FeatureMatcherSettings
+        ms = matcher_settings or FeatureMatcherSettings()
+        return F.StereoParams(float(camera.mbf), float(camera.fx), int(camera.mnMaxY), float(ms.TH_HIGH), float(ms.TH_LOW), float(size_ref))
+
+    def process_stereo_batch(self, images, camera, capacity=None, out=None):
+        """images: [2P,H,W] uint8 host array, (left, right) interleaved.  Returns (kps[2P,cap], desc[2P,cap,32], counts[2P],
+        uR[P,cap], depth[P,cap]).  `out` may hold preallocated (e.g. pinned) arrays of those shapes."""
+        B, H, W = images.shape
+        P = B // 2
+        cap = capacity or self.default_capacity()
+        if out is None:
+            out = (np.empty((B, cap), F.KP_DTYPE), np.empty((B, cap, 32), np.uint8), np.zeros(B, np.int32),
+                   np.empty((P, cap), np.float32), np.empty((P, cap), np.float32))
+        kps, desc, counts, uR, depth = out
+        sp = self.stereo_params(camera)
+        F.check(F.lib().hyorb_process_stereo_batch_host(self._h, C.byref(sp), F.ptr(images), P, W, H, images.strides[1], images.strides[0],
+                                                        F.ptr(kps), F.ptr(desc), cap, F.ptr(counts), F.ptr(uR), F.ptr(depth)))
+        return out
+
+    def process_stereo_batch_device(self, sp, d_images, P, W, H, stride, image_stride, d_kps, d_desc, capacity, d_counts, d_uR, d_depth):
+        F.check(F.lib().hyorb_process_stereo_batch_device(self._h, C.byref(sp), d_images, P, W, H, stride, image_stride, d_kps, d_desc,
+                                                          capacity, d_counts, d_uR, d_depth))
+
+    def set_profiling(self, on=True):
+        F.check(F.lib().hyorb_extractor_set_profiling(self._h, int(on)))
+
+    def stage_times(self, reset=True):
+        """{stage: accumulated ms} and the number of profiled calls since the last reset (synchronises)."""
+        ms = (C.c_double * F.N_STAGES)()
+        calls = C.c_long(0)
+        F.check(F.lib().hyorb_extractor_stage_times(self._h, ms, C.byref(calls), int(reset)))
+        return dict(zip(F.STAGE_NAMES, list(ms))), calls.value
+
     def launch_count(self):
         return int(F.lib().hyorb_extractor_launch_count(self._h))
 

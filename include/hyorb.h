@@ -132,6 +132,28 @@ typedef struct hyorb_stereo_params {
     float size_ref;  /* FeatureExtractorSettings::size_ref = 31 (FeatureExtractorSettings.h:27) */
 } hyorb_stereo_params;
 
+/* ImageProcessing::ProcessStereoImage (src/main/ImageProcessing.cpp:69-116) over n_pairs stereo pairs in one call:
+ * extractor_left(imL), extractor_right(imR) (:82-83), then Stereomatcher(...).computeStereoMatches() (:101-102).
+ * Images are interleaved: image 2p = left, 2p+1 = right of pair p.  kps/desc/counts as hyorb_extract_batch_*
+ * (2*n_pairs images); uR/depth are [n_pairs][capacity], indexed by left keypoint, -1 where unmatched. */
+HYORB_API int hyorb_process_stereo_batch_host(hyorb_extractor *h, const hyorb_stereo_params *sp, const uint8_t *images,
+                                              int n_pairs, int width, int height, int stride, size_t image_stride,
+                                              hyorb_keypoint *kps, uint8_t *desc, int capacity, int32_t *counts, float *uR,
+                                              float *depth);
+HYORB_API int hyorb_process_stereo_batch_device(hyorb_extractor *h, const hyorb_stereo_params *sp, const uint8_t *d_images,
+                                                int n_pairs, int width, int height, int stride, size_t image_stride,
+                                                hyorb_keypoint *d_kps, uint8_t *d_desc, int capacity, int32_t *d_counts,
+                                                float *d_uR, float *d_depth);
+
+/* Per-stage device time of the calls since the last reset, from CUDA events recorded on the handle's stream around
+ * each stage (the reference only has commented-out stopwatches, ImageProcessing.cpp:70,112-114).  Synchronises.
+ * ms[HYORB_N_STAGES]: accumulated milliseconds per stage; *calls: number of profiled calls. */
+enum { HYORB_STAGE_PYRAMID = 0, HYORB_STAGE_FAST = 1, HYORB_STAGE_QUADTREE = 2, HYORB_STAGE_BLUR = 3,
+       HYORB_STAGE_DESCRIBE = 4, HYORB_STAGE_STEREO = 5, HYORB_N_STAGES = 6 };
+HYORB_API int hyorb_extractor_set_profiling(hyorb_extractor *h, int enable);
+HYORB_API int hyorb_extractor_stage_times(hyorb_extractor *h, double *ms, long *calls, int reset);
+
+
 typedef struct hyorb_matcher hyorb_matcher; /* workspace + stream for the stereo / matching entry points */
 HYORB_API int hyorb_matcher_create(int device, void *cuda_stream, hyorb_matcher **out);
 HYORB_API int hyorb_matcher_destroy(hyorb_matcher *m);

@@ -142,3 +142,24 @@ def test_c2_extract_plus_stereo_matches_oracle(kind, seed):
     assert np.array_equal(uR.view(np.uint32), ouR.view(np.uint32)) and np.array_equal(depth.view(np.uint32), odepth.view(np.uint32))
     if kind == "noise":
         assert (uR >= 0).sum() > 300
+
+
+def test_process_stereo_batch_matches_oracle():
+    """ImageProcessing::ProcessStereoImage over a batch: extract L, extract R, stereo match, one ABI call."""
+    pairs = [synth.stereo_pair(376, 1241, 40 + i, "noise" if i != 1 else "blocks") for i in range(3)]
+    imgs = np.stack([im for p in pairs for im in p])
+    ex = hb.ORBExtractor(hb.FeatureExtractorSettings(nFeatures=2000))
+    cam = hb.StereoCamera(386.1448, 718.856, 376.0)
+    kps, desc, counts, uR, depth = ex.process_stereo_batch(imgs, cam, capacity=2560)
+    osp = O.StereoParams(386.1448, 718.856, 376, 100.0, 50.0, 31.0)
+    for p in range(3):
+        okl, odl = O.extract(imgs[2 * p], O.default_params(2000)); okr, odr = O.extract(imgs[2 * p + 1], O.default_params(2000))
+        nl, nr = counts[2 * p], counts[2 * p + 1]
+        assert nl == len(okl) and nr == len(okr)
+        assert np.array_equal(kps[2 * p, :nl], okl) and np.array_equal(kps[2 * p + 1, :nr], okr)
+        assert np.array_equal(desc[2 * p, :nl], odl) and np.array_equal(desc[2 * p + 1, :nr], odr)
+        ouR, odepth, _, _ = O.stereo_match(osp, okl, odl, okr, odr)
+        assert np.array_equal(uR[p, :nl].view(np.uint32), ouR.view(np.uint32))
+        assert np.array_equal(depth[p, :nl].view(np.uint32), odepth.view(np.uint32))
+    st, calls = ex.stage_times()
+    assert calls == 0                      # profiling is off by default
