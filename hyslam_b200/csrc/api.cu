@@ -131,7 +131,7 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
     HY_TRY(ex_ensure_plan(h, w, hgt));
     HY_TRY(ex_ensure_workspace(h, B));
     if (sp) {
-        HY_TRY(h->d_rowtab.ensure(sizeof(int32_t) * (size_t)capacity * 20 * (B / 2)));
+        HY_TRY(h->d_rowtab.ensure(sizeof(int32_t) * stereo_scratch_ints_per_pair(capacity) * (B / 2)));
         HY_TRY(h->d_bestd.ensure(sizeof(int32_t) * (size_t)capacity * (B / 2)));
     }
     const PlanDev &P = h->plan.dev;
@@ -154,7 +154,7 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
                            h->d_status.as<int>(), B, st, &h->launches));
     HY_TRY(ex_event(h, &evs));
     if (sp) {
-        HY_TRY(launch_stereo(*sp, B / 2, d_kps, d_desc, d_counts, capacity, h->d_rowtab.as<int32_t>(), capacity * 20, d_uR, d_depth, nullptr,
+        HY_TRY(launch_stereo(*sp, B / 2, d_kps, d_desc, d_counts, capacity, h->d_rowtab.as<int32_t>(), d_uR, d_depth, nullptr,
                              h->d_bestd.as<int32_t>(), h->d_status.as<int>(), st, &h->launches));
     }
     HY_TRY(ex_event(h, &evs));
@@ -662,13 +662,12 @@ HYORB_API int hyorb_stereo_match_batch_device(hyorb_matcher *m, const hyorb_ster
     HY_TRY(m_prepare(m));
     if (!sp || n_pairs < 0 || capacity < 1 || !d_kps || !d_desc || !d_counts || !d_uR || !d_depth) { set_error("bad argument"); return HYORB_EINVAL; }
     if (n_pairs == 0) return HYORB_OK;
-    const int tabCap = capacity * 20;
-    HY_TRY(m->d_rowtab.ensure(sizeof(int32_t) * (size_t)tabCap * n_pairs));
+    HY_TRY(m->d_rowtab.ensure(sizeof(int32_t) * stereo_scratch_ints_per_pair(capacity) * n_pairs));
     if (!d_best_dist) {
         HY_TRY(m->d_bestd.ensure(sizeof(int32_t) * (size_t)capacity * n_pairs));
         d_best_dist = m->d_bestd.as<int32_t>();
     }
-    return launch_stereo(*sp, n_pairs, d_kps, d_desc, d_counts, capacity, m->d_rowtab.as<int32_t>(), tabCap, d_uR, d_depth, d_best_r, d_best_dist,
+    return launch_stereo(*sp, n_pairs, d_kps, d_desc, d_counts, capacity, m->d_rowtab.as<int32_t>(), d_uR, d_depth, d_best_r, d_best_dist,
                          m->d_status.as<int>(), m->stream, &m->launches);
 }
 

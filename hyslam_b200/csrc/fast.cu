@@ -33,17 +33,25 @@ __device__ __forceinline__ uint32_t pick(uint32_t w0, uint32_t w1, uint32_t w2) 
     return __funnelshift_r(w1, w2, 8 * (O - 4));
 }
 
-// Bresenham circle of radius 3, OpenCV's order (features2d/fast_score.cpp makeOffsets)
-__device__ __constant__ int c_ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-__device__ __constant__ int c_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+// Bresenham circle of radius 3, OpenCV's order (features2d/fast_score.cpp makeOffsets); byte offset inside the staged tile
+__device__ __forceinline__ constexpr int ring_off(int k)
+{
+    constexpr int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    constexpr int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    return dy[k] * 192 + dx[k];
+}
 
 constexpr int EMIT_CAP = 1024;
+constexpr int RW = 48;            // shared-memory row stride in words: == 16 (mod 32), so the two rows a warp touches per
+                                  // load (16 groups x 2 rows) fall into disjoint banks
+constexpr int LW = 18;            // words actually loaded per row (70 pixels + 2)
+constexpr int PITCHB = RW * 4;    // row stride in bytes
 
 __global__ void __launch_bounds__(FT_THREADS)
 k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ pyr,
        uint32_t *__restrict__ cand, int *__restrict__ candCount, int *__restrict__ status)
 {
-    __shared__ uint32_t s_pix[FT_PH * (FT_PITCH / 4)];
+    __shared__ uint32_t s_pix[FT_PH * RW];
     __shared__ __align__(4) uint8_t s_score[FT_SH * FT_SW];
     __shared__ uint16_t s_list[FT_SH * FT_SW];
     __shared__ uint32_t s_emit[EMIT_CAP];
@@ -68,24 +76,24 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
     else { img = pyr + (size_t)b * plan->pyrStride + L.off; pitch = L.pitch; }
 
     if (tid == 0) { s_n = 0; s_ne = 0; }
-    // ---- stage pixels: 38 rows x 18 words
-    for (int i = tid; i < FT_PH * (FT_PITCH / 4); i += FT_THREADS) {
-        const int rr = i / (FT_PITCH / 4), ww = i - rr * (FT_PITCH / 4);
+    // ---- stage pixels: 38 rows x 18 words, aligned 32-bit global loads re-aligned with a funnel shift
+    for (int i = tid; i < FT_PH * LW; i += FT_THREADS) {
+        const int rr = i / LW, ww = i - rr * LW;
         const int y = gy0 + rr, x = gx0 + 4 * ww;
         uint32_t v = 0;
         if (y < h && x < w) {
             const uint8_t *p = img + (size_t)y * pitch;
-            const uintptr_t a = (uintptr_t)(p + x);
-            const uintptr_t a0 = a & ~(uintptr_t)3;
-            if ((long long)(a0 - (uintptr_t)p) + 7 < (long long)w) {
-                const uint32_t lo = *(const uint32_t *)a0, hi = *(const uint32_t *)(a0 + 4);
-                v = __funnelshift_r(lo, hi, (unsigned)(a & 3) * 8);
+            const unsigned mis = (unsigned)((uintptr_t)(p + x) & 3);
+            const int xa = x - (int)mis;                               // aligned-down start; gx0 >= 15 keeps xa >= 0
+            if (xa + 7 < w) {
+                const uint32_t *q = (const uint32_t *)(p + xa);
+                v = __funnelshift_r(__ldg(q), __ldg(q + 1), mis * 8);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; j++) if (x + j < w) v |= (uint32_t)p[x + j] << (8 * j);
             }
         }
-        s_pix[i] = v;
+        s_pix[rr * RW + ww] = v;
     }
     for (int i = tid; i < FT_SH * FT_SW / 4; i += FT_THREADS) ((uint32_t *)s_score)[i] = 0;
     if (tid < FT_SW) {
@@ -100,7 +108,8 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
 
     const int xEnd = L.maxBX - 3, yEnd = L.maxBY - 3;     // detect range [19, xEnd) x [19, yEnd)
     // ---- corner test, 4 pixels per item
-#pragma unroll 1
+    uint32_t nflag[2] = {0u, 0u};
+#pragma unroll
     for (int it = 0; it < 2; it++) {
         const int id = tid + it * FT_THREADS;
         const int g = id & 15, r = id >> 4;
@@ -112,9 +121,8 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
             if (sx >= DET_MIN && sx < xEnd) valid |= 0x80u << (8 * j);
         }
         if (sy < DET_MIN || sy >= yEnd) valid = 0;
-        if (valid == 0) continue;
-        const uint32_t *row = s_pix + (r + 3) * (FT_PITCH / 4) + g;
-        constexpr int RW = FT_PITCH / 4;
+        if (valid == 0) continue;       // nflag[it] stays 0
+        const uint32_t *row = s_pix + (r + 3) * RW + g;
         uint32_t a0, a1, a2;
         a0 = row[0]; a1 = row[1]; a2 = row[2];
         const uint32_t c = pick<3>(a0, a1, a2);
@@ -149,9 +157,28 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
             for (int k = 0; k < 16; k++) any |= t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
         }
         any &= valid;
-        if (any) {
-            const int n = __popc(any);
-            int pos = atomicAdd(&s_n, n);
+        nflag[it] = any;
+    }
+    // ---- compact the corner flags of both items into the CTA list: warp prefix sum + one atomic per warp
+    {
+        const int lane = tid & 31;
+        const int n0 = __popc(nflag[0]), n1 = __popc(nflag[1]);
+        int inc = n0 + n1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        int base = 0;
+        if (lane == 31 && total) base = atomicAdd(&s_n, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + inc - (n0 + n1);
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+            const int id = tid + it * FT_THREADS;
+            const int g = id & 15, r = id >> 4;
+            const uint32_t any = nflag[it];
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (any & (0x80u << (8 * j))) s_list[pos++] = (uint16_t)(r * FT_SW + 4 * g + j);
@@ -165,33 +192,40 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
     for (int i = tid; i < ncorner; i += FT_THREADS) {
         const int e = s_list[i];
         const int r = e / FT_SW, cidx = e - r * FT_SW;
-        const uint8_t *p = pix8 + (r + 3) * FT_PITCH + (cidx + 3);
+        const uint8_t *p = pix8 + (r + 3) * PITCHB + (cidx + 3);
         const int v = p[0];
-        int d[16];
+        // 16-bit lanes: low = centre - ring (dark arcs), high = ring - centre (bright arcs).  With R' = (ring+1)*65535 =
+        // (ring << 16 | -(ring+1)) and A' = (-centre << 16 | centre+1), the lane-wise sum A' + R' is exactly that pair.
+        const uint32_t A = ((uint32_t)(v + 1) & 0xFFFFu) | ((uint32_t)(-v) << 16);
+        uint32_t wv[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) d[k] = v - (int)p[c_ring_dy[k] * FT_PITCH + c_ring_dx[k]];
-        int mn3[16], mx3[16];
+        for (int k = 0; k < 16; k++) wv[k] = __vadd2(A, ((uint32_t)p[ring_off(k)] + 1u) * 65535u);
+        uint32_t m3[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            mn3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-            mx3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        }
-        int sd = -1000, sbn = 1000;    // max over arcs of min d ; min over arcs of max d
+        for (int k = 0; k < 16; k++) m3[k] = __vimin3_s16x2(wv[k], wv[(k + 1) & 15], wv[(k + 2) & 15]);
+        uint32_t m9[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            sd = max(sd, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
-            sbn = min(sbn, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
-        }
-        const int sc = __vimax3_s32(sd, -sbn, FAST_T) - 1;
+        for (int k = 0; k < 16; k++) m9[k] = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);   // min over the 9-arc starting at k
+        uint32_t mx = __vimax3_s16x2(m9[0], m9[1], m9[2]);
+        mx = __vimax3_s16x2(mx, m9[3], m9[4]); mx = __vimax3_s16x2(mx, m9[5], m9[6]); mx = __vimax3_s16x2(mx, m9[7], m9[8]);
+        mx = __vimax3_s16x2(mx, m9[9], m9[10]); mx = __vimax3_s16x2(mx, m9[11], m9[12]); mx = __vimax3_s16x2(mx, m9[13], m9[14]);
+        mx = __vimax3_s16x2(mx, m9[15], m9[15]);
+        const int sd = (int)(short)(mx & 0xFFFFu), sb = (int)mx >> 16;
+        const int sc = __vimax3_s32(sd, sb, FAST_T) - 1;
         s_score[e] = (uint8_t)sc;
     }
     __syncthreads();
 
     // ---- cell-local 3x3 NMS over the interior, stage survivors
-    for (int i = tid; i < ncorner; i += FT_THREADS) {
+    for (int i0 = 0; i0 < ncorner; i0 += FT_THREADS) {      // warp-uniform trip count: the ballot below needs all lanes
+        const int i = i0 + tid;
+        bool kept = false;
+        uint32_t packed = 0;
+        do {
+        if (i >= ncorner) break;
         const int e = s_list[i];
         const int r = e / FT_SW, cidx = e - r * FT_SW;
-        if (r < 1 || r > FT_OH || cidx < 1 || cidx > FT_OW) continue;   // halo: belongs to the neighbouring tile
+        if (r < 1 || r > FT_OH || cidx < 1 || cidx > FT_OW) break;      // halo: belongs to the neighbouring tile
         const int s = s_score[e];
         const int cf = s_cf[cidx], rf = s_rf[r];
         const bool L_ok = !(cf & 1), R_ok = !(cf & 2), U_ok = !(rf & 1), D_ok = !(rf & 2);
@@ -209,9 +243,17 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
             if (L_ok) keep = keep && s > q[FT_SW - 1];
             if (R_ok) keep = keep && s > q[FT_SW + 1];
         }
-        if (keep) {
-            const int pos = atomicAdd(&s_ne, 1);
-            if (pos < EMIT_CAP) s_emit[pos] = pack_cand(sx0 + cidx - LATTICE_MIN, sy0 + r - LATTICE_MIN, s);
+        kept = keep;
+        packed = pack_cand(sx0 + cidx - LATTICE_MIN, sy0 + r - LATTICE_MIN, s);
+        } while (0);
+        const unsigned bal = __ballot_sync(0xffffffffu, kept);
+        if (bal) {
+            const int lane = tid & 31;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_ne, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int pos = base + __popc(bal & ((1u << lane) - 1));
+            if (kept && pos < EMIT_CAP) s_emit[pos] = packed;
         }
     }
     __syncthreads();

@@ -166,6 +166,11 @@ int build_plan(const hyorb_extractor_params &p, int width, int height, HostPlan 
             L.area2x = (S.w == 2 * L.w && S.h == 2 * L.h);
             L.rsX = (int)out->resize.size(); out->resize.resize(out->resize.size() + L.w);
             linear_table(L.w, S.w, false, out->resize.data() + L.rsX);
+            if (!L.area2x)      // k_resize picks a thread's 8 horizontal taps out of 8 consecutive source bytes
+                for (int x = 0; x < L.w; x += 4) {
+                    const ResizeTab *t = out->resize.data() + L.rsX;
+                    if (t[x + 3 < L.w ? x + 3 : L.w - 1].ofs - t[x].ofs > 6) { set_error("scale_factor %.3f too large for the resize kernel (max 2)", p.scale_factor); return HYORB_EUNSUPPORTED; }
+                }
             L.rsY = (int)out->resize.size(); out->resize.resize(out->resize.size() + L.h);
             linear_table(L.h, S.h, true, out->resize.data() + L.rsY);
         }
