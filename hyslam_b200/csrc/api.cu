@@ -49,6 +49,8 @@ struct hyorb_extractor {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;                // blur runs here, concurrently with FAST + quadtree (it only needs the pyramid)
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
     float scale[HYORB_MAX_LEVELS], inv[HYORB_MAX_LEVELS], sigma2[HYORB_MAX_LEVELS], inv_sigma2[HYORB_MAX_LEVELS];
     int quota[HYORB_MAX_LEVELS];
     HostPlan plan;
@@ -139,16 +141,25 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
     cudaStream_t st = h->stream;
     std::vector<cudaEvent_t> evs;
     HY_CUDA(cudaMemsetAsync(h->d_candCount.p, 0, sizeof(int) * HYORB_MAX_LEVELS * (size_t)B, st));
+    // event slots: 0 start, 1 pyramid done, 2 FAST done, 3 quadtree done, 4 describe start (== blur joined), 5 describe done, 6 stereo done;
+    // blur runs on the side stream between its own pair of events (7, 8)
     HY_TRY(ex_event(h, &evs));
     HY_TRY(launch_pyramid(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_resize.as<ResizeTab>(), B, st, &h->launches));
     HY_TRY(ex_event(h, &evs));
+    HY_CUDA(cudaEventRecord(h->ev_pyr, st));
+    HY_CUDA(cudaStreamWaitEvent(h->side, h->ev_pyr, 0));
+    std::vector<cudaEvent_t> evb;
+    if (h->profile) { cudaStream_t keep = h->stream; h->stream = h->side; int rc = ex_event(h, &evb); h->stream = keep; HY_TRY(rc); }
+    HY_TRY(launch_blur(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_blur.as<uint8_t>(), B, h->side, &h->launches));
+    if (h->profile) { cudaStream_t keep = h->stream; h->stream = h->side; int rc = ex_event(h, &evb); h->stream = keep; HY_TRY(rc); }
+    HY_CUDA(cudaEventRecord(h->ev_blur, h->side));
     HY_TRY(launch_fast(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_cand.as<uint32_t>(), h->d_candCount.as<int>(), h->d_status.as<int>(), B, st, &h->launches));
     HY_TRY(ex_event(h, &evs));
     HY_TRY(launch_quadtree(P, dp, h->d_cand.as<uint32_t>(), h->d_candCount.as<int>(), h->d_lut.as<uint32_t>(), h->d_qcode.as<uint32_t>(),
                            h->d_qnode.as<uint16_t>(), h->d_qleaf.as<uint2>(), h->d_sel.as<uint32_t>(), h->d_selCount.as<int>(),
                            h->d_status.as<int>(), B, st, &h->launches));
     HY_TRY(ex_event(h, &evs));
-    HY_TRY(launch_blur(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_blur.as<uint8_t>(), B, st, &h->launches));
+    HY_CUDA(cudaStreamWaitEvent(st, h->ev_blur, 0));
     HY_TRY(ex_event(h, &evs));
     HY_TRY(launch_describe(P, dp, h->d_blur.as<uint8_t>(), h->d_sel.as<uint32_t>(), h->d_selCount.as<int>(), d_kps, d_desc, capacity, d_counts,
                            h->d_status.as<int>(), B, st, &h->launches));
@@ -158,7 +169,7 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
                              h->d_bestd.as<int32_t>(), h->d_status.as<int>(), st, &h->launches));
     }
     HY_TRY(ex_event(h, &evs));
-    if (h->profile) h->ev_pending.push_back(evs);
+    if (h->profile) { evs.insert(evs.end(), evb.begin(), evb.end()); h->ev_pending.push_back(evs); }
     h->last_B = B; h->last_l0 = l0;
     return HYORB_OK;
 }
@@ -205,6 +216,9 @@ HYORB_API int hyorb_extractor_create(const hyorb_extractor_params *params, int d
         if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
         else { e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking); h->own_stream = true; }
     }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("CUDA init: %s", cudaGetErrorString(e)); delete h; return HYORB_ECUDA; }
     *out = h;
     return HYORB_OK;
@@ -215,6 +229,9 @@ HYORB_API int hyorb_extractor_destroy(hyorb_extractor *h)
     if (!h) return HYORB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+    if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
+    if (h->ev_blur) cudaEventDestroy(h->ev_blur);
     DevBuf *bufs[] = {&h->d_plan, &h->d_resize, &h->d_lut, &h->d_pyr, &h->d_blur, &h->d_cand, &h->d_qcode, &h->d_qnode, &h->d_qleaf, &h->d_sel,
                       &h->d_candCount, &h->d_selCount, &h->d_status, &h->d_in, &h->d_kps, &h->d_desc, &h->d_counts,
                       &h->d_rowtab, &h->d_bestd, &h->d_uR, &h->d_depth};
@@ -375,11 +392,14 @@ HYORB_API int hyorb_extractor_stage_times(hyorb_extractor *h, double *ms, long *
     HY_CUDA(cudaSetDevice(h->device));
     HY_CUDA(cudaStreamSynchronize(h->stream));
     for (auto &set : h->ev_pending) {
-        for (size_t i = 0; i + 1 < set.size() && i < HYORB_N_STAGES; i++) {
-            float t = 0.f;
-            HY_CUDA(cudaEventElapsedTime(&t, set[i], set[i + 1]));
-            h->stage_ms[i] += t;
-        }
+        // slots: see ex_run.  pyramid 0-1, FAST 1-2, quadtree 2-3, describe 4-5, stereo 5-6, blur 7-8 (side stream, overlapped)
+        static const int from[HYORB_N_STAGES] = {0, 1, 2, 7, 4, 5}, to[HYORB_N_STAGES] = {1, 2, 3, 8, 5, 6};
+        if (set.size() >= 9)
+            for (int i = 0; i < HYORB_N_STAGES; i++) {
+                float t = 0.f;
+                HY_CUDA(cudaEventElapsedTime(&t, set[from[i]], set[to[i]]));
+                h->stage_ms[i] += t;
+            }
         h->stage_calls++;
         for (cudaEvent_t e : set) h->ev_free.push_back(e);
     }

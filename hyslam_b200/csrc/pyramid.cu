@@ -21,10 +21,10 @@ __device__ __forceinline__ HRow hrow(const uint8_t *__restrict__ row, int s0, in
     // bytes s0 .. s0+5 of the row, as two registers A (s0..s0+3) and B (s0+4..s0+7)
     uint32_t A, B;
     if (wordsafe && s0 + 12 <= roww) {
-        const uintptr_t a = (uintptr_t)(row + s0);
-        const uint32_t *p = (const uint32_t *)(a & ~(uintptr_t)3);
-        const unsigned sh = (unsigned)(a & 3) * 8;
-        const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+        const unsigned mis = (unsigned)((uintptr_t)(row + s0) & 3);
+        const uint32_t *p = (const uint32_t *)(row + s0 - mis);
+        const unsigned sh = mis * 8;
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
         A = __funnelshift_r(w0, w1, sh);
         B = __funnelshift_r(w1, w2, sh);
     } else {
@@ -74,12 +74,15 @@ k_resize(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride
         sel[j] = dlt | ((dlt + 1) << 4);                      // PRMT: byte0 = tap0, byte1 = tap1 (byte 2,3 = A[0], unused)
         c01[j] = (uint32_t)(uint16_t)t.c0 | ((uint32_t)(uint16_t)t.c1 << 16);
     }
-    const bool wordsafe = (((uintptr_t)s | (uintptr_t)spitch) & 3) == 0;   // aligned-down word loads never leave the row
+    // aligned-down word loads start at most 3 bytes before a row's first tap: inside the previous row / image, except
+    // for the very first bytes of an unaligned batch base
+    const bool base_aligned = ((uintptr_t)src & 3) == 0;
     int haveRow = -1;          // source row whose horizontal values sit in hb
     HRow ha, hb;
     for (int y = y0; y < y1; y++) {
         const ResizeTab vy = ty[y];
         const int sy0 = min(max(vy.ofs, 0), sh - 1), sy1 = min(max(vy.ofs + 1, 0), sh - 1);
+        const bool wordsafe = base_aligned || s0 >= 3 || sy0 > 0 || blockIdx.z > 0;
         if (sy0 == haveRow) ha = hb;
         else ha = hrow(s + (size_t)sy0 * spitch, s0, sw, wordsafe, sel, c01);
         if (sy1 == sy0) hb = ha;

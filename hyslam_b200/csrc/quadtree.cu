@@ -28,6 +28,7 @@ struct QtShared {
     int warp[QT / 32 + 1];
     int rootcnt[QT_MAX_ROOTS];
     int rootcrank[QT_MAX_ROOTS];
+    int rootmi[QT_MAX_ROOTS];
     int nleaf;
     int cut;
     int tmp;
@@ -121,14 +122,16 @@ k_quadtree(const PlanDev *__restrict__ plan, const uint32_t *__restrict__ cand_a
     const int maxN = L.qtMaxN;
     const int tid = threadIdx.x;
 
-    // dynamic shared memory carve-up (20 bytes per node slot)
-    uint32_t *cnt = (uint32_t *)smem_raw;                    // [maxN] points per node of the current depth, by creation rank
-    uint32_t *slotcnt = cnt + maxN;                          // [maxN] points per child slot (4 per visited parent)
-    uint32_t *skey = slotcnt + maxN;                         // [maxN] sort keys          } alias: best[maxN] (u64)
+    // dynamic shared memory carve-up (QT_SMEM_PER_SLOT = 26 bytes per node slot).  "mi" = index of a multi-point node
+    // among the multi-point nodes of its depth, in creation order; a node's four child slots are 4*mi + quadrant.
+    uint32_t *Hbase = (uint32_t *)smem_raw;                  // [maxN] x2: points per child slot, current / next depth
+    uint32_t *skey = (uint32_t *)smem_raw + 2 * maxN;        // [maxN] sort keys          } alias: best[maxN] (u64)
     uint32_t *sval = skey + maxN;                            // [maxN] sort payload       }
     unsigned long long *best = (unsigned long long *)skey;
-    uint16_t *pidx = (uint16_t *)(sval + maxN);              // [maxN] visiting position of a multi-point node
-    uint16_t *slotnew = pidx + maxN;                         // [maxN] creation rank of the child in a slot
+    uint16_t *crankBase = (uint16_t *)(sval + maxN);         // [maxN] x2: creation rank of multi node mi, current / next depth
+    uint16_t *P = crankBase + 2 * maxN;                      // [maxN] visiting position of multi node mi in this pass
+    uint16_t *ncrank = P + maxN;                             // [maxN] creation rank of the child in a slot
+    uint16_t *nmi = ncrank + maxN;                           // [maxN] mi of the child in a slot (if it holds > 1 point)
 
     int n = candCount[b * HYORB_MAX_LEVELS + l];
     if (n > L.candCap) n = L.candCap;
@@ -142,142 +145,155 @@ k_quadtree(const PlanDev *__restrict__ plan, const uint32_t *__restrict__ cand_a
     uint32_t *sel = sel_all + (size_t)b * plan->selStride + L.selOff;
     const uint32_t *lutX = lut + L.lutX, *lutY = lut + L.lutY;
     const int N = L.quota;
+    const int nIni = L.nIni;
 
-    // ---------------- depth 0: roots (:192-225)
+    // ---------------- depth 0: roots (:192-225).  One sweep computes every candidate's path code and histograms it
+    // into its root and into the root's four children.
     if (tid < QT_MAX_ROOTS) S.rootcnt[tid] = 0;
-    if (tid == 0) { S.nleaf = 0; }
+    for (int i = tid; i < 4 * nIni; i += QT) Hbase[maxN + i] = 0;
+    if (tid == 0) S.nleaf = 0;
     __syncthreads();
     for (int base = 0; base < n; base += QT) {
         const int i = base + tid;
-        int r = -1;
+        int r = -1, s1 = -1;
         if (i < n) {
             const uint32_t c = cand[i];
             const uint32_t code = lutX[cand_x(c)] | lutY[cand_y(c)];
             qcode[i] = code;
             r = (int)(code >> (2 * QT_DMAX));
+            s1 = 4 * r + (int)((code >> (2 * (QT_DMAX - 1))) & 3u);
         }
         agg_inc((uint32_t *)S.rootcnt, r);   // neighbouring candidates mostly share the root
+        agg_inc(Hbase + maxN, s1);
     }
     __syncthreads();
     if (tid == 0) {
-        int F0 = 0;
-        for (int r = L.nIni - 1; r >= 0; r--)
-            if (S.rootcnt[r]) { S.rootcrank[r] = F0; cnt[F0] = (uint32_t)S.rootcnt[r]; F0++; }
-        S.tmp = F0;
+        // creation rank of the roots counts from the right, so that "visit newest first" is ascending root index, which is what
+        // the reference's first pass does; mi enumerates the multi-point roots in creation order
+        int F0 = 0, M0 = 0;
+        for (int r = nIni - 1; r >= 0; r--) {
+            S.rootmi[r] = -1;
+            if (S.rootcnt[r]) {
+                S.rootcrank[r] = F0;
+                if (S.rootcnt[r] > 1) { S.rootmi[r] = M0; crankBase[M0] = (uint16_t)F0; M0++; }
+                F0++;
+            }
+        }
+        S.tmp = F0; S.cut = M0;
     }
     __syncthreads();
-    int F = S.tmp;            // nodes of the current depth
-    for (int i = tid; i < n; i += QT) {
-        const int r = (int)(qcode[i] >> (2 * QT_DMAX));
-        unsigned nd = (unsigned)S.rootcrank[r];
-        if (S.rootcnt[r] == 1) {
-            const int pos = atomicAdd(&S.nleaf, 1);
-            if (pos < L.selCap) qleaf[pos] = make_uint2(((0u << 13) | nd) + 1u, (uint32_t)i);
-            nd = NODE_FINAL;
-        }
-        qnode[i] = (uint16_t)nd;
+    for (int i = tid; i < 4 * nIni; i += QT) {          // child histograms re-indexed by mi
+        const int r = i >> 2;
+        if (S.rootmi[r] >= 0) Hbase[4 * S.rootmi[r] + (i & 3)] = Hbase[maxN + i];
     }
     __syncthreads();
 
-    int size = F, depth = 0, M = 0, m = 0;
+    int size = S.tmp, depth = 0, M = S.cut, m = 0, cur = 0, M2 = 0;
     bool phase2 = false, finish = false;
-    while (!finish) {
-        // ---- A. multi-point nodes of this depth and their visiting order
-        M = chunk_scan(F, S.warp, [&](int c) { return cnt[c] > 1 ? 1 : 0; },
-                       [&](int c, int pos) { if (cnt[c] > 1) { skey[pos] = ((phase2 ? cnt[c] : 0u) << 13) | (uint32_t)c; } });
-        __syncthreads();
+    __syncthreads();          // S.tmp / S.cut are reused below
+    while (true) {
+        uint32_t *H = Hbase + cur * maxN, *Hn = Hbase + (cur ^ 1) * maxN;
+        // ---- A. visiting order of the multi-point nodes: skey[p] = mi of the p-th visited node
         if (phase2) {
             // sort(vPrevSizeAndPointerToNode) then walk from the back (:324-326): (count desc, creation rank desc)
             const int n2 = pow2_at_least(M);
-            for (int i = M + tid; i < n2; i += QT) skey[i] = 0;
+            for (int i = tid; i < n2; i += QT)
+                skey[i] = i < M ? (((H[4 * i] + H[4 * i + 1] + H[4 * i + 2] + H[4 * i + 3]) << 13) | (uint32_t)i) : 0u;
             __syncthreads();
             bitonic_desc(skey, sval, n2);
-            for (int p = tid; p < M; p += QT) pidx[skey[p] & NODE_MASK] = (uint16_t)p;
+            for (int p = tid; p < M; p += QT) { const uint32_t mi = skey[p] & NODE_MASK; skey[p] = mi; P[mi] = (uint16_t)p; }
         } else {
             // list order: newest first (:257)
-            for (int p = tid; p < M; p += QT) pidx[skey[p] & NODE_MASK] = (uint16_t)(M - 1 - p);
+            for (int p = tid; p < M; p += QT) { skey[p] = (uint32_t)(M - 1 - p); P[M - 1 - p] = (uint16_t)p; }
         }
-        for (int s = tid; s < 4 * M; s += QT) slotcnt[s] = 0;
         __syncthreads();
-        // ---- C. histogram candidates into the 4 child slots of their node (DivideNode :151-166)
+        // ---- B. how many parents are expanded: all (phase 1) or until the list holds N nodes (:370-371)
+        if (tid == 0) S.cut = M;
+        auto kids = [&](int p) { const uint32_t *h4 = H + 4 * skey[p]; return (int)(h4[0] > 0) + (int)(h4[1] > 0) + (int)(h4[2] > 0) + (int)(h4[3] > 0); };
+        chunk_scan(M, S.warp, [&](int p) { return kids(p) - 1; },
+                   [&](int p, int before) {
+                       if (phase2) { const int k1 = kids(p) - 1; if (size + before < N && size + before + k1 >= N) S.cut = p + 1; }   // unique: the prefix is monotone
+                   });
+        __syncthreads();
+        m = S.cut;
+        // ---- C. creation ranks of the children, in (visiting order, quadrant) order; low half counts non-empty slots,
+        // high half counts slots with > 1 point (= the next depth's mi)
+        uint16_t *crankNext = crankBase + (cur ^ 1) * maxN;
+        const int tot = chunk_scan(4 * m, S.warp,
+            [&](int t) { const uint32_t c = H[4 * skey[t >> 2] + (t & 3)]; return (int)(c > 0) + ((int)(c > 1) << 16); },
+            [&](int t, int pos) {
+                const int slot = 4 * (int)skey[t >> 2] + (t & 3);
+                const uint32_t c = H[slot];
+                if (c > 0) ncrank[slot] = (uint16_t)(pos & 0xFFFF);
+                if (c > 1) { nmi[slot] = (uint16_t)(pos >> 16); crankNext[pos >> 16] = (uint16_t)(pos & 0xFFFF); }
+            });
+        const int F2 = tot & 0xFFFF;
+        M2 = tot >> 16;
+        // the list size after this pass is known before the candidates move: decide now whether another pass follows
+        const int prevSize = size;
+        size += F2 - m;                      // sum over expanded parents of (children - 1)
+        if (size >= N || size == prevSize) finish = true;                 // :309, :374
+        else if (!phase2 && size + 3 * M2 > N) phase2 = true;              // :313 (nToExpand = children with > 1 point)
+        if (!finish && (depth + 1 >= QT_DMAX || 4 * M2 > maxN)) { if (tid == 0) atomicOr(status, ST_QT_LIMIT); finish = true; }
+        // another pass => size < N => M2 < N => the next histogram (4*M2 slots) fits
+        if (!finish) for (int i = tid; i < 4 * M2; i += QT) Hn[i] = 0;
+        __syncthreads();
+        // ---- D. one sweep: move every candidate to its child (DivideNode :151-166), make singletons leaves (bNoMore,
+        // :168-175) and histogram the survivors into their child's four children for the next pass
         const int sh = 2 * (QT_DMAX - 1 - depth);
         for (int base = 0; base < n; base += QT) {
             const int i = base + tid;
-            int slot = -1;
+            int nslot = -1;
             if (i < n) {
-                const unsigned nd = qnode[i];
-                if (nd != NODE_FINAL) slot = 4 * (int)pidx[nd] + (int)((qcode[i] >> sh) & 3u);
+                const uint32_t code = qcode[i];
+                unsigned nd;
+                if (depth == 0) {
+                    const int r = (int)(code >> (2 * QT_DMAX));
+                    nd = S.rootmi[r] >= 0 ? (unsigned)S.rootmi[r] : NODE_FINAL;
+                    if (S.rootcnt[r] == 1) {
+                        const int pos = atomicAdd(&S.nleaf, 1);
+                        if (pos < L.selCap) qleaf[pos] = make_uint2(((0u << 13) | (uint32_t)S.rootcrank[r]) + 1u, (uint32_t)i);
+                    }
+                    if (nd == NODE_FINAL) qnode[i] = (uint16_t)NODE_FINAL;
+                } else nd = qnode[i];
+                if (nd != NODE_FINAL) {
+                    if ((int)P[nd] >= m) qnode[i] = (uint16_t)(nd | NODE_STAY);      // parent not expanded: only in the last pass
+                    else {
+                        const int slot = 4 * (int)nd + (int)((code >> sh) & 3u);
+                        if (H[slot] == 1) {
+                            const int pos = atomicAdd(&S.nleaf, 1);
+                            if (pos < L.selCap) qleaf[pos] = make_uint2((((uint32_t)(depth + 1) << 13) | ncrank[slot]) + 1u, (uint32_t)i);
+                            qnode[i] = (uint16_t)NODE_FINAL;
+                        } else {
+                            const unsigned c2 = nmi[slot];
+                            qnode[i] = (uint16_t)c2;
+                            if (!finish && sh >= 2) nslot = 4 * (int)c2 + (int)((code >> (sh - 2)) & 3u);
+                        }
+                    }
+                }
             }
-            agg_inc(slotcnt, slot);
+            agg_inc(Hn, nslot);
         }
         __syncthreads();
-        // ---- D. how many parents are expanded: all (phase 1) or until the list holds N nodes (:370-371)
-        if (tid == 0) S.cut = M;
-        const int grow = chunk_scan(M, S.warp,
-            [&](int p) { return (int)(slotcnt[4 * p] > 0) + (int)(slotcnt[4 * p + 1] > 0) + (int)(slotcnt[4 * p + 2] > 0) + (int)(slotcnt[4 * p + 3] > 0) - 1; },
-            [&](int p, int before) {
-                if (phase2) {
-                    const int k1 = (int)(slotcnt[4 * p] > 0) + (int)(slotcnt[4 * p + 1] > 0) + (int)(slotcnt[4 * p + 2] > 0) + (int)(slotcnt[4 * p + 3] > 0) - 1;
-                    if (size + before < N && size + before + k1 >= N) S.cut = p + 1;   // unique p: the prefix is monotone
-                }
-            });
-        __syncthreads();
-        m = S.cut;
-        // ---- E. creation ranks of the children, in (visiting order, quadrant) order
-        int nToExpand = 0;
-        {
-            int multi_local = 0;
-            const int F2 = chunk_scan(4 * m, S.warp, [&](int s) { return slotcnt[s] > 0 ? 1 : 0; },
-                                      [&](int s, int pos) {
-                                          if (slotcnt[s] > 0) { slotnew[s] = (uint16_t)pos; cnt[pos] = slotcnt[s]; if (slotcnt[s] > 1) multi_local++; }
-                                      });
-            // cnt[] (old depth) is dead after step A, so it was safe to overwrite above
-            int tot;
-            block_excl_scan(multi_local, S.warp, tot);
-            nToExpand = tot;
-            // size after this pass
-            int nsize;
-            if (m == M) nsize = size + grow;
-            else {
-                // sum of (k-1) over the first m parents = F2 - m
-                nsize = size + (F2 - m);
-            }
-            __syncthreads();
-            // ---- F. move candidates to their child; singletons become leaves (bNoMore, :168-175)
-            for (int i = tid; i < n; i += QT) {
-                unsigned nd = qnode[i];
-                if (nd == NODE_FINAL) continue;
-                const int p = pidx[nd];
-                if (p >= m) { qnode[i] = (uint16_t)(nd | NODE_STAY); continue; }
-                const int slot = 4 * p + (int)((qcode[i] >> sh) & 3u);
-                nd = slotnew[slot];
-                if (slotcnt[slot] == 1) {
-                    const int pos = atomicAdd(&S.nleaf, 1);
-                    if (pos < L.selCap) qleaf[pos] = make_uint2((((uint32_t)(depth + 1) << 13) | nd) + 1u, (uint32_t)i);
-                    nd = NODE_FINAL;
-                }
-                qnode[i] = (uint16_t)nd;
-            }
-            __syncthreads();
-            const int prevSize = size;
-            size = nsize; depth++; F = F2;
-            if (size >= N || size == prevSize) finish = true;                 // :309, :374
-            else if (!phase2 && size + 3 * nToExpand > N) phase2 = true;       // :313
-            if (!finish && (depth >= QT_DMAX || F > maxN || 4 * F > 4 * maxN)) { if (tid == 0) atomicOr(status, ST_QT_LIMIT); finish = true; }
-        }
+        depth++;
+        if (finish) break;               // M, m, cur keep describing the last pass for the final stage
+        M = M2; cur ^= 1;
     }
+    // after the loop: `M`, `m`, P[], crankBuf[cur] describe the parents of the last pass; crankBuf[cur^1], M2 its children
+    const uint16_t *crankPar = crankBase + cur * maxN, *crankKid = crankBase + (cur ^ 1) * maxN;
 
     // ---------------- leaves that still hold several candidates: keep the max response, first in the reference's
     // candidate order on ties (:381-400)
-    const int nStay = M - m;                      // unexpanded nodes of depth-1 (phase-2 cut)
-    const int nMulti = nStay + F;                 // ids: [0,nStay) unexpanded parents, [nStay, nStay+F) nodes of the last depth
+    const int nStay = M - m;                      // unexpanded parents of the last pass (phase-2 cut)
+    const int nMulti = nStay + M2;                // ids: [0,nStay) unexpanded parents, [nStay, nStay+M2) multi-point children
     if (nMulti > maxN) { if (tid == 0) { atomicOr(status, ST_QT_LIMIT); *outCount = 0; } return; }
+    __syncthreads();
     for (int i = tid; i < nMulti; i += QT) best[i] = 0ull;
     __syncthreads();
     for (int i = tid; i < n; i += QT) {
         const unsigned nd = qnode[i];
         if (nd == NODE_FINAL) continue;
-        const int id = (nd & NODE_STAY) ? (int)pidx[nd & NODE_MASK] - m : nStay + (int)nd;
+        const int id = (nd & NODE_STAY) ? (int)P[nd & NODE_MASK] - m : nStay + (int)nd;
         const uint32_t c = cand[i];
         const uint32_t ok = cand_order_key(cand_x(c), cand_y(c), L.wCell, L.hCell, L.nCols);
         const unsigned long long v = ((unsigned long long)cand_resp(c) << 32) | (unsigned long long)(0xFFFFFFFFu - ok);
@@ -288,13 +304,13 @@ k_quadtree(const PlanDev *__restrict__ plan, const uint32_t *__restrict__ cand_a
         const unsigned nd = qnode[i];
         if (nd == NODE_FINAL) continue;
         const bool stay = (nd & NODE_STAY) != 0;
-        const int id = stay ? (int)pidx[nd & NODE_MASK] - m : nStay + (int)nd;
+        const int id = stay ? (int)P[nd & NODE_MASK] - m : nStay + (int)nd;
         const uint32_t c = cand[i];
         const uint32_t ok = cand_order_key(cand_x(c), cand_y(c), L.wCell, L.hCell, L.nCols);
         const unsigned long long v = ((unsigned long long)cand_resp(c) << 32) | (unsigned long long)(0xFFFFFFFFu - ok);
         if (best[id] == v) {
             const int pos = atomicAdd(&S.nleaf, 1);
-            const uint32_t key = stay ? (((uint32_t)(depth - 1) << 13) | (nd & NODE_MASK)) : (((uint32_t)depth << 13) | nd);
+            const uint32_t key = stay ? (((uint32_t)(depth - 1) << 13) | crankPar[nd & NODE_MASK]) : (((uint32_t)depth << 13) | crankKid[nd]);
             if (pos < L.selCap) qleaf[pos] = make_uint2(key + 1u, (uint32_t)i);
         }
     }
@@ -321,7 +337,7 @@ int launch_quadtree(const PlanDev &hp, const PlanDev *dp, const uint32_t *cand, 
 {
     int maxN = 0;
     for (int l = 0; l < hp.nlevels; l++) if (hp.lv[l].qtMaxN > maxN) maxN = hp.lv[l].qtMaxN;
-    const size_t smem = (size_t)maxN * 20;
+    const size_t smem = (size_t)maxN * 26;
     static bool attr_set = false;   // idempotent: raising the limit again is harmless
     if (!attr_set || smem > 48 * 1024) {
         HY_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
