@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libhyorb (include/hyorb.h): handles, workspaces, staging, status plumbing.
 // Host side of the drop-in: what ORBExtractor / Stereomatcher / FeatureMatcher objects own in the reference
 // (per-object pyramid + scratch, src/features/ORBExtractor.h:102) lives in a handle here; nothing is global.
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
@@ -49,8 +50,14 @@ struct hyorb_extractor {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaStream_t side = nullptr;                // blur runs here, concurrently with FAST + quadtree (it only needs the pyramid)
-    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
+    // A batch is cut into `lanes` independent sub-batches, each enqueued on its own stream, so that the latency-bound
+    // kernels of one sub-batch (quadtree, stereo table) overlap the throughput-bound ones (FAST, blur) of another.
+    // Lane 0 runs on `stream`.  Inside a lane the blur runs on a side stream next to FAST + quadtree (it only needs the pyramid).
+    static constexpr int MAX_LANES = 8;
+    int lanes = 2;
+    bool side_blur = true;
+    cudaStream_t lane_stream[MAX_LANES] = {}, side[MAX_LANES] = {};
+    cudaEvent_t ev_start = nullptr, ev_pyr[MAX_LANES] = {}, ev_blur[MAX_LANES] = {}, ev_done[MAX_LANES] = {};
     float scale[HYORB_MAX_LEVELS], inv[HYORB_MAX_LEVELS], sigma2[HYORB_MAX_LEVELS], inv_sigma2[HYORB_MAX_LEVELS];
     int quota[HYORB_MAX_LEVELS];
     HostPlan plan;
@@ -114,13 +121,13 @@ static int ex_ensure_workspace(hyorb_extractor *h, int B)
     return HYORB_OK;
 }
 
-static int ex_event(hyorb_extractor *h, std::vector<cudaEvent_t> *set)
+static int ex_event(hyorb_extractor *h, cudaStream_t st, std::vector<cudaEvent_t> *set)
 {
     if (!h->profile) return HYORB_OK;
     cudaEvent_t e;
     if (!h->ev_free.empty()) { e = h->ev_free.back(); h->ev_free.pop_back(); }
     else HY_CUDA(cudaEventCreate(&e));
-    HY_CUDA(cudaEventRecord(e, h->stream));
+    HY_CUDA(cudaEventRecord(e, st));
     set->push_back(e);
     return HYORB_OK;
 }
@@ -132,44 +139,102 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
     HY_CUDA(cudaSetDevice(h->device));
     HY_TRY(ex_ensure_plan(h, w, hgt));
     HY_TRY(ex_ensure_workspace(h, B));
+    const size_t st_ints = sp ? stereo_scratch_ints_per_pair(capacity) : 0;
     if (sp) {
-        HY_TRY(h->d_rowtab.ensure(sizeof(int32_t) * stereo_scratch_ints_per_pair(capacity) * (B / 2)));
+        HY_TRY(h->d_rowtab.ensure(sizeof(int32_t) * st_ints * (B / 2)));
         HY_TRY(h->d_bestd.ensure(sizeof(int32_t) * (size_t)capacity * (B / 2)));
     }
     const PlanDev &P = h->plan.dev;
     const PlanDev *dp = h->d_plan.as<PlanDev>();
-    cudaStream_t st = h->stream;
-    std::vector<cudaEvent_t> evs;
-    HY_CUDA(cudaMemsetAsync(h->d_candCount.p, 0, sizeof(int) * HYORB_MAX_LEVELS * (size_t)B, st));
-    // event slots: 0 start, 1 pyramid done, 2 FAST done, 3 quadtree done, 4 describe start (== blur joined), 5 describe done, 6 stereo done;
-    // blur runs on the side stream between its own pair of events (7, 8)
-    HY_TRY(ex_event(h, &evs));
-    HY_TRY(launch_pyramid(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_resize.as<ResizeTab>(), B, st, &h->launches));
-    HY_TRY(ex_event(h, &evs));
-    HY_CUDA(cudaEventRecord(h->ev_pyr, st));
-    HY_CUDA(cudaStreamWaitEvent(h->side, h->ev_pyr, 0));
-    std::vector<cudaEvent_t> evb;
-    if (h->profile) { cudaStream_t keep = h->stream; h->stream = h->side; int rc = ex_event(h, &evb); h->stream = keep; HY_TRY(rc); }
-    HY_TRY(launch_blur(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_blur.as<uint8_t>(), B, h->side, &h->launches));
-    if (h->profile) { cudaStream_t keep = h->stream; h->stream = h->side; int rc = ex_event(h, &evb); h->stream = keep; HY_TRY(rc); }
-    HY_CUDA(cudaEventRecord(h->ev_blur, h->side));
-    HY_TRY(launch_fast(P, dp, l0, h->d_pyr.as<uint8_t>(), h->d_cand.as<uint32_t>(), h->d_candCount.as<int>(), h->d_status.as<int>(), B, st, &h->launches));
-    HY_TRY(ex_event(h, &evs));
-    HY_TRY(launch_quadtree(P, dp, h->d_cand.as<uint32_t>(), h->d_candCount.as<int>(), h->d_lut.as<uint32_t>(), h->d_qcode.as<uint32_t>(),
-                           h->d_qnode.as<uint16_t>(), h->d_qleaf.as<uint2>(), h->d_sel.as<uint32_t>(), h->d_selCount.as<int>(),
-                           h->d_status.as<int>(), B, st, &h->launches));
-    HY_TRY(ex_event(h, &evs));
-    HY_CUDA(cudaStreamWaitEvent(st, h->ev_blur, 0));
-    HY_TRY(ex_event(h, &evs));
-    HY_TRY(launch_describe(P, dp, h->d_blur.as<uint8_t>(), h->d_sel.as<uint32_t>(), h->d_selCount.as<int>(), d_kps, d_desc, capacity, d_counts,
-                           h->d_status.as<int>(), B, st, &h->launches));
-    HY_TRY(ex_event(h, &evs));
-    if (sp) {
-        HY_TRY(launch_stereo(*sp, B / 2, d_kps, d_desc, d_counts, capacity, h->d_rowtab.as<int32_t>(), d_uR, d_depth, nullptr,
-                             h->d_bestd.as<int32_t>(), h->d_status.as<int>(), st, &h->launches));
+    // ---- cut the batch into lanes (whole pairs when the stereo stage follows)
+    const int unit = sp ? 2 : 1, units = B / unit;
+    int nl = h->lanes < 1 ? 1 : (h->lanes > hyorb_extractor::MAX_LANES ? hyorb_extractor::MAX_LANES : h->lanes);
+    if (nl > units) nl = units;
+    int first[hyorb_extractor::MAX_LANES + 1];
+    for (int k = 0; k <= nl; k++) first[k] = unit * (int)((long long)units * k / nl);
+    std::vector<cudaEvent_t> evs[hyorb_extractor::MAX_LANES];
+    if (nl > 1 || h->side_blur) HY_CUDA(cudaEventRecord(h->ev_start, h->stream));
+    // stage-major issue order so the hardware queues alternate between lanes
+    for (int stage = 0; stage < 6; stage++) {
+        for (int k = 0; k < nl; k++) {
+            cudaStream_t st = h->lane_stream[k];
+            const int i0 = first[k], Bk = first[k + 1] - first[k];
+            Level0 l0k{l0.base + (size_t)i0 * l0.stride, l0.pitch, l0.stride};
+            uint8_t *pyr = h->d_pyr.as<uint8_t>() + (size_t)i0 * P.pyrStride, *blur = h->d_blur.as<uint8_t>() + (size_t)i0 * P.pyrStride;
+            uint32_t *cand = h->d_cand.as<uint32_t>() + (size_t)i0 * P.candStride;
+            int *candCount = h->d_candCount.as<int>() + (size_t)i0 * HYORB_MAX_LEVELS, *selCount = h->d_selCount.as<int>() + (size_t)i0 * HYORB_MAX_LEVELS;
+            uint32_t *sel = h->d_sel.as<uint32_t>() + (size_t)i0 * P.selStride;
+            int *status = h->d_status.as<int>();
+            // event slots per lane: 0 start, 1 pyramid done, 2 FAST done, 3 quadtree done, 4 describe start (blur joined), 5 describe done,
+            // 6 stereo done, 7-8 blur (side stream)
+            switch (stage) {
+            case 0:
+                if (k > 0) HY_CUDA(cudaStreamWaitEvent(st, h->ev_start, 0));
+                HY_CUDA(cudaMemsetAsync(candCount, 0, sizeof(int) * HYORB_MAX_LEVELS * (size_t)Bk, st));
+                HY_TRY(ex_event(h, st, &evs[k]));
+                HY_TRY(launch_pyramid(P, dp, l0k, pyr, h->d_resize.as<ResizeTab>(), Bk, st, &h->launches));
+                HY_TRY(ex_event(h, st, &evs[k]));
+                break;
+            case 1:
+                if (h->side_blur) {
+                    HY_CUDA(cudaEventRecord(h->ev_pyr[k], st));
+                    HY_CUDA(cudaStreamWaitEvent(h->side[k], h->ev_pyr[k], 0));
+                }
+                HY_TRY(launch_fast(P, dp, l0k, pyr, cand, candCount, status, Bk, st, &h->launches));
+                HY_TRY(ex_event(h, st, &evs[k]));
+                break;
+            case 2:
+                HY_TRY(launch_quadtree(P, dp, cand, candCount, h->d_lut.as<uint32_t>(), h->d_qcode.as<uint32_t>() + (size_t)i0 * P.candStride,
+                                       h->d_qnode.as<uint16_t>() + (size_t)i0 * P.candStride, h->d_qleaf.as<uint2>() + (size_t)i0 * P.selStride, sel,
+                                       selCount, status, Bk, st, &h->launches));
+                HY_TRY(ex_event(h, st, &evs[k]));
+                break;
+            case 3: {
+                cudaStream_t bs = h->side_blur ? h->side[k] : st;
+                std::vector<cudaEvent_t> evb;
+                HY_TRY(ex_event(h, bs, &evb));
+                HY_TRY(launch_blur(P, dp, l0k, pyr, blur, Bk, bs, &h->launches));
+                HY_TRY(ex_event(h, bs, &evb));
+                if (h->side_blur) {
+                    HY_CUDA(cudaEventRecord(h->ev_blur[k], bs));
+                    HY_CUDA(cudaStreamWaitEvent(st, h->ev_blur[k], 0));
+                }
+                HY_TRY(ex_event(h, st, &evs[k]));                   // slot 4
+                if (h->profile) { evs[k].resize(9); evs[k][7] = evb[0]; evs[k][8] = evb[1]; }
+                break;
+            }
+            case 4:
+                HY_TRY(launch_describe(P, dp, blur, sel, selCount, d_kps + (size_t)i0 * capacity, d_desc + (size_t)i0 * capacity * HYORB_DESC_BYTES, capacity,
+                                       d_counts + i0, status, Bk, st, &h->launches));
+                if (h->profile) {
+                    cudaEvent_t e;
+                    if (!h->ev_free.empty()) { e = h->ev_free.back(); h->ev_free.pop_back(); } else HY_CUDA(cudaEventCreate(&e));
+                    HY_CUDA(cudaEventRecord(e, st));
+                    evs[k][5] = e;
+                }
+                break;
+            case 5:
+                if (sp) {
+                    const int p0 = i0 / 2;
+                    HY_TRY(launch_stereo(*sp, Bk / 2, d_kps + (size_t)i0 * capacity, d_desc + (size_t)i0 * capacity * HYORB_DESC_BYTES, d_counts + i0, capacity,
+                                         h->d_rowtab.as<int32_t>() + st_ints * p0, d_uR + (size_t)p0 * capacity, d_depth + (size_t)p0 * capacity, nullptr,
+                                         h->d_bestd.as<int32_t>() + (size_t)p0 * capacity, status, st, &h->launches));
+                }
+                if (h->profile) {
+                    cudaEvent_t e;
+                    if (!h->ev_free.empty()) { e = h->ev_free.back(); h->ev_free.pop_back(); } else HY_CUDA(cudaEventCreate(&e));
+                    HY_CUDA(cudaEventRecord(e, st));
+                    evs[k][6] = e;
+                }
+                if (k > 0) {
+                    HY_CUDA(cudaEventRecord(h->ev_done[k], st));
+                    HY_CUDA(cudaStreamWaitEvent(h->stream, h->ev_done[k], 0));
+                }
+                break;
+            }
+        }
     }
-    HY_TRY(ex_event(h, &evs));
-    if (h->profile) { evs.insert(evs.end(), evb.begin(), evb.end()); h->ev_pending.push_back(evs); }
+    if (h->profile) { for (int k = 0; k < nl; k++) h->ev_pending.push_back(evs[k]); h->stage_calls++; }
     h->last_B = B; h->last_l0 = l0;
     return HYORB_OK;
 }
@@ -216,9 +281,17 @@ HYORB_API int hyorb_extractor_create(const hyorb_extractor_params *params, int d
         if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
         else { e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking); h->own_stream = true; }
     }
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming);
+    h->lane_stream[0] = h->stream;
+    for (int k = 0; k < hyorb_extractor::MAX_LANES && e == cudaSuccess; k++) {
+        if (k > 0) e = cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_blur[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming);
+    if (const char *v = getenv("HYORB_LANES")) h->lanes = atoi(v);
+    if (const char *v = getenv("HYORB_SIDE_BLUR")) h->side_blur = atoi(v) != 0;
     if (e != cudaSuccess) { set_error("CUDA init: %s", cudaGetErrorString(e)); delete h; return HYORB_ECUDA; }
     *out = h;
     return HYORB_OK;
@@ -229,9 +302,14 @@ HYORB_API int hyorb_extractor_destroy(hyorb_extractor *h)
     if (!h) return HYORB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
-    if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
-    if (h->ev_blur) cudaEventDestroy(h->ev_blur);
+    for (int k = 0; k < hyorb_extractor::MAX_LANES; k++) {
+        if (k > 0 && h->lane_stream[k]) { cudaStreamSynchronize(h->lane_stream[k]); cudaStreamDestroy(h->lane_stream[k]); }
+        if (h->side[k]) { cudaStreamSynchronize(h->side[k]); cudaStreamDestroy(h->side[k]); }
+        if (h->ev_pyr[k]) cudaEventDestroy(h->ev_pyr[k]);
+        if (h->ev_blur[k]) cudaEventDestroy(h->ev_blur[k]);
+        if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
+    }
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
     DevBuf *bufs[] = {&h->d_plan, &h->d_resize, &h->d_lut, &h->d_pyr, &h->d_blur, &h->d_cand, &h->d_qcode, &h->d_qnode, &h->d_qleaf, &h->d_sel,
                       &h->d_candCount, &h->d_selCount, &h->d_status, &h->d_in, &h->d_kps, &h->d_desc, &h->d_counts,
                       &h->d_rowtab, &h->d_bestd, &h->d_uR, &h->d_depth};
@@ -400,8 +478,7 @@ HYORB_API int hyorb_extractor_stage_times(hyorb_extractor *h, double *ms, long *
                 HY_CUDA(cudaEventElapsedTime(&t, set[from[i]], set[to[i]]));
                 h->stage_ms[i] += t;
             }
-        h->stage_calls++;
-        for (cudaEvent_t e : set) h->ev_free.push_back(e);
+        for (cudaEvent_t e : set) if (e) h->ev_free.push_back(e);
     }
     h->ev_pending.clear();
     for (int i = 0; i < HYORB_N_STAGES; i++) { if (ms) ms[i] = h->stage_ms[i]; if (reset) h->stage_ms[i] = 0; }

@@ -338,10 +338,12 @@ int launch_quadtree(const PlanDev &hp, const PlanDev *dp, const uint32_t *cand, 
     int maxN = 0;
     for (int l = 0; l < hp.nlevels; l++) if (hp.lv[l].qtMaxN > maxN) maxN = hp.lv[l].qtMaxN;
     const size_t smem = (size_t)maxN * 26;
-    static bool attr_set = false;   // idempotent: raising the limit again is harmless
-    if (!attr_set || smem > 48 * 1024) {
-        HY_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-        attr_set = true;
+    if (smem > 48 * 1024) {
+        int dev = 0, optin = 0;
+        HY_CUDA(cudaGetDevice(&dev));
+        HY_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        if ((int)smem + 1024 > optin) { set_error("quadtree needs %zu bytes of shared memory, device allows %d", smem, optin); return HYORB_EUNSUPPORTED; }
+        HY_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     dim3 grd(hp.nlevels, B);
     k_quadtree<<<grd, QT, smem, st>>>(dp, cand, candCount, lut, qcode, qnode, qleaf, sel, selCount, status);
