@@ -65,6 +65,7 @@ struct LevelDev {
     float scale;              // mvScaleFactor[l]
     float kpSize;             // (float)(int)(PATCH_SIZE*scale)  (:478)
     int qtMaxN;               // power of two >= 4*quota: node arrays of the quadtree kernel
+    unsigned mulW, mulH;      // ceil(2^20 / wCell), ceil(2^20 / hCell): exact division of a lattice coordinate (< 4096) by the cell size
 };
 
 struct PlanDev {
@@ -96,6 +97,12 @@ __host__ __device__ inline uint32_t cand_order_key(int x, int y, int wCell, int 
 {
     const int cj = (x - 3) / wCell, ci = (y - 3) / hCell;
     return ((uint32_t)(ci * nCols + cj) << 14) | ((uint32_t)(y - ci * hCell) << 7) | (uint32_t)(x - cj * wCell);
+}
+// same key with the two divisions replaced by multiply-shift: exact because (x-3) < 4096 and cell < 128 => (x-3)*cell < 2^20
+__device__ __forceinline__ uint32_t cand_order_key_fast(int x, int y, const LevelDev &L)
+{
+    const int cj = (int)(((unsigned)(x - 3) * L.mulW) >> 20), ci = (int)(((unsigned)(y - 3) * L.mulH) >> 20);
+    return ((uint32_t)(ci * L.nCols + cj) << 14) | ((uint32_t)(y - ci * L.hCell) << 7) | (uint32_t)(x - cj * L.wCell);
 }
 
 // ---- host-side plan (tables.cu) ----

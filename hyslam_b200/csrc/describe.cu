@@ -39,13 +39,18 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
+constexpr int PT_R = 18;                 // patch radius: |rotated pattern coordinate| <= 18 (pattern radius 13*sqrt2), disc radius 15
+constexpr int PT_ROWS = 2 * PT_R + 1;    // 37
+constexpr int PT_WORDS = 10;             // 37 columns + up to 3 bytes of alignment slack, as 32-bit words
+
 __global__ void __launch_bounds__(DS_WARPS * 32)
 k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, const uint32_t *__restrict__ sel_all,
            const int *__restrict__ selCount, hyorb_keypoint *__restrict__ kps, uint8_t *__restrict__ desc, int capacity,
            int *__restrict__ counts, int *__restrict__ status)
 {
-    // umax of ORBFinder::orientationSetup (ORBFinder.cpp:131-149), asserted against the oracle in tests
-    const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    // the 37x37 window of the blurred level around the keypoint, one per warp, staged with coalesced 32-bit loads: the
+    // 31 disc rows and the 512 rotated-pattern taps then hit shared memory instead of issuing byte gathers to L1
+    __shared__ uint32_t s_patch[DS_WARPS][PT_ROWS * PT_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int k = blockIdx.x * DS_WARPS + warp;
@@ -67,19 +72,35 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
     const LevelDev &L = plan->lv[l];
     const uint32_t c = sel_all[(size_t)b * plan->selStride + L.selOff + j];
     const int px = cand_x(c) + LATTICE_MIN, py = cand_y(c) + LATTICE_MIN;     // :484-485
-    const int pitch = L.pitch;
-    const uint8_t *center = blur + (size_t)b * plan->pyrStride + L.off + (size_t)py * pitch + px;
+    const int pitch = L.pitch;                                                  // multiple of 16; level base 256-aligned
+    const uint8_t *level = blur + (size_t)b * plan->pyrStride + L.off;
+    // stage rows py-18 .. py+18, bytes gx0 .. gx0+39 where gx0 = (px-18) rounded down to 4 (px >= 19 keeps it >= 0; the
+    // last word may run <= 2 bytes past the row, still inside the level's padded block, and is never read back)
+    const int gx0 = (px - PT_R) & ~3, off = (px - PT_R) - gx0;
+    uint32_t *patch = s_patch[warp];
+    {
+        const uint8_t *src = level + (size_t)(py - PT_R) * pitch + gx0;
+        for (int i = lane; i < PT_ROWS * PT_WORDS; i += 32) {
+            const int r = i / PT_WORDS, wd = i - r * PT_WORDS;
+            patch[i] = __ldg((const uint32_t *)(src + (size_t)r * pitch) + wd);
+        }
+    }
+    __syncwarp();
+    const uint8_t *center = (const uint8_t *)patch + PT_R * (PT_WORDS * 4) + off + PT_R;
+    constexpr int PP = PT_WORDS * 4;      // patch pitch in bytes
 
-    // ---- intensity centroid (ORBFinder.cpp:16-43)
+    // ---- intensity centroid (ORBFinder.cpp:16-43); umax of ORBFinder::orientationSetup (:131-149)
     int m10 = 0, m01 = 0;
     const int u = lane - HALF_PATCH;
     if (lane < 31) {
         const int au = u < 0 ? -u : u;
+        // rows with |v| <= vmax(au) contain column u: umax = {15,15,15,15,14,14,14,13,13,12,11,10,9,8,6,3}
+        const int vmax = au <= 3 ? 15 : au <= 6 ? 14 : au <= 8 ? 13 : au == 9 ? 12 : au == 10 ? 11 : au == 11 ? 10 : au == 12 ? 9 : au == 13 ? 8 : au == 14 ? 6 : 3;
 #pragma unroll
         for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {
             const int av = v < 0 ? -v : v;
-            if (au <= umax[av]) {
-                const int val = center[v * pitch + u];
+            if (av <= vmax) {
+                const int val = center[v * PP + u];
                 m10 += u * val;
                 m01 += v * val;
             }
@@ -105,7 +126,7 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bb)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bb), __fmul_rn(y1, a)));
         const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, bb)));
-        const int t0 = center[r0 * pitch + c0], t1 = center[r1 * pitch + c1];
+        const int t0 = center[r0 * PP + c0], t1 = center[r1 * PP + c1];
         val |= (t0 < t1) << t;
     }
     const size_t o = (size_t)b * capacity + k;

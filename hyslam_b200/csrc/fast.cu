@@ -128,7 +128,11 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
         const uint32_t c = pick<3>(a0, a1, a2);
         const uint32_t hi = __vaddus4(c, 0x01010101u * FAST_T), lo = __vsubus4(c, 0x01010101u * FAST_T);
         uint32_t B[16], D[16];
-#define RING(k, O) { const uint32_t rv = pick<O>(a0, a1, a2); B[k] = gt_msb(rv, hi); D[k] = gt_msb(lo, rv); }
+        // per byte, bit 7 of ((a & ~b) | (~(a ^ b) & s)) is (a > b) when s = (a & 0x7f) + (~b & 0x7f); the two sums that involve
+        // the ring pixel share its low 7 bits: bright s = r7 + Kb, dark s = Kd - r7 (no carry or borrow crosses a byte)
+        const uint32_t Kb = ~hi & 0x7f7f7f7fu, Kd = (lo & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+#define RING(k, O) { const uint32_t rv = pick<O>(a0, a1, a2); const uint32_t r7 = rv & 0x7f7f7f7fu; const uint32_t sb = r7 + Kb, sd = Kd - r7; \
+                     B[k] = (rv & ~hi) | (~(rv ^ hi) & sb); D[k] = (lo & ~rv) | (~(lo ^ rv) & sd); }
         RING(12, 0) RING(4, 6)                                           // dy = 0 : dx = -3, +3
         a0 = row[RW]; a1 = row[RW + 1]; a2 = row[RW + 2];                // dy = +1
         RING(13, 0) RING(3, 6)
@@ -144,17 +148,22 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
         RING(9, 2) RING(8, 3) RING(7, 4)
 #undef RING
         // 9 contiguous: a3[k] = m[k]&m[k+1]&m[k+2]; a9[k] = a3[k]&a3[k+3]&a3[k+6]
-        uint32_t any = 0;
+        uint32_t any;
         {
-            uint32_t t3[16];
+            uint32_t t3[16], t9[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) t3[k] = B[k] & B[(k + 1) & 15] & B[(k + 2) & 15];
 #pragma unroll
-            for (int k = 0; k < 16; k++) any |= t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
+            for (int k = 0; k < 16; k++) t9[k] = t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
+            uint32_t ob = (t9[0] | t9[1] | t9[2]) | (t9[3] | t9[4] | t9[5]) | (t9[6] | t9[7] | t9[8]);
+            ob |= (t9[9] | t9[10] | t9[11]) | (t9[12] | t9[13] | t9[14]) | t9[15];
 #pragma unroll
             for (int k = 0; k < 16; k++) t3[k] = D[k] & D[(k + 1) & 15] & D[(k + 2) & 15];
 #pragma unroll
-            for (int k = 0; k < 16; k++) any |= t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
+            for (int k = 0; k < 16; k++) t9[k] = t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
+            uint32_t od = (t9[0] | t9[1] | t9[2]) | (t9[3] | t9[4] | t9[5]) | (t9[6] | t9[7] | t9[8]);
+            od |= (t9[9] | t9[10] | t9[11]) | (t9[12] | t9[13] | t9[14]) | t9[15];
+            any = ob | od;
         }
         any &= valid;
         nflag[it] = any;

@@ -295,7 +295,7 @@ k_quadtree(const PlanDev *__restrict__ plan, const uint32_t *__restrict__ cand_a
         if (nd == NODE_FINAL) continue;
         const int id = (nd & NODE_STAY) ? (int)P[nd & NODE_MASK] - m : nStay + (int)nd;
         const uint32_t c = cand[i];
-        const uint32_t ok = cand_order_key(cand_x(c), cand_y(c), L.wCell, L.hCell, L.nCols);
+        const uint32_t ok = cand_order_key_fast(cand_x(c), cand_y(c), L);
         const unsigned long long v = ((unsigned long long)cand_resp(c) << 32) | (unsigned long long)(0xFFFFFFFFu - ok);
         atomicMax(&best[id], v);
     }
@@ -306,7 +306,7 @@ k_quadtree(const PlanDev *__restrict__ plan, const uint32_t *__restrict__ cand_a
         const bool stay = (nd & NODE_STAY) != 0;
         const int id = stay ? (int)P[nd & NODE_MASK] - m : nStay + (int)nd;
         const uint32_t c = cand[i];
-        const uint32_t ok = cand_order_key(cand_x(c), cand_y(c), L.wCell, L.hCell, L.nCols);
+        const uint32_t ok = cand_order_key_fast(cand_x(c), cand_y(c), L);
         const unsigned long long v = ((unsigned long long)cand_resp(c) << 32) | (unsigned long long)(0xFFFFFFFFu - ok);
         if (best[id] == v) {
             const int pos = atomicAdd(&S.nleaf, 1);

@@ -129,6 +129,7 @@ int build_plan(const hyorb_extractor_params &p, int width, int height, HostPlan 
         const float W = (float)p.cell_px;
         L.nCols = (int)(fw / W); L.nRows = (int)(fh / W);               // :425-426
         L.wCell = (int)ceilf(fw / (float)L.nCols); L.hCell = (int)ceilf(fh / (float)L.nRows);   // :427-428
+        L.mulW = (unsigned)(((1u << 20) + L.wCell - 1) / L.wCell); L.mulH = (unsigned)(((1u << 20) + L.hCell - 1) / L.hCell);
         if (L.wCell + 6 > 127 || L.hCell + 6 > 127) { set_error("cell of %dx%d px not supported", L.wCell, L.hCell); return HYORB_EUNSUPPORTED; }
         const int detW = (L.maxBX - 3) - DET_MIN, detH = (L.maxBY - 3) - DET_MIN;
         L.tilesX = detW > 0 ? (detW + FT_OW - 1) / FT_OW : 0;
