@@ -31,30 +31,30 @@ enum { HS_WORDS = 0,      // interior: aligned-down 32-bit loads + funnel shift 
 
 struct Raw { uint32_t q0, q1, q2, q3; unsigned sh; };     // loaded words of one row + the funnel shift that aligns them
 
+// right-edge threads (at most two per row band): per-byte gather with reflection.  Kept out of line: the main loop is
+// unrolled 7x and must stay small enough for the instruction cache.
+__device__ __noinline__ Raw fetch_bytes(const uint8_t *__restrict__ row, int x0, int w)
+{
+    Raw r;
+    r.q0 = r.q1 = r.q2 = r.q3 = 0; r.sh = 0;
+    for (int j = 0; j < 4; j++) {
+        r.q0 |= (uint32_t)row[reflect101(x0 - 4 + j, w)] << (8 * j);
+        r.q1 |= (uint32_t)row[reflect101(x0 + j, w)] << (8 * j);
+        r.q2 |= (uint32_t)row[reflect101(x0 + 4 + j, w)] << (8 * j);
+    }
+    return r;
+}
+
 // issue the loads of one source row (no use of the loaded values here, so rows can be fetched ahead of their use)
 __device__ __forceinline__ Raw fetch_row(const uint8_t *__restrict__ row, int x0, int w, int mode)
 {
+    if (mode == HS_BYTES) return fetch_bytes(row, x0, w);
     Raw r;
-    if (mode == HS_WORDS) {
-        const uint8_t *a = row + x0 - 4;
-        const unsigned mis = (unsigned)((uintptr_t)a & 3);
-        const uint32_t *q = (const uint32_t *)(a - mis);
-        r.q0 = __ldg(q); r.q1 = __ldg(q + 1); r.q2 = __ldg(q + 2); r.q3 = __ldg(q + 3);
-        r.sh = mis * 8;
-    } else if (mode == HS_LEFT) {
-        const unsigned mis = (unsigned)((uintptr_t)row & 3);
-        const uint32_t *q = (const uint32_t *)(row - mis);
-        r.q0 = 0; r.q1 = __ldg(q); r.q2 = __ldg(q + 1); r.q3 = __ldg(q + 2);
-        r.sh = mis * 8;
-    } else {
-        r.q0 = r.q1 = r.q2 = r.q3 = 0; r.sh = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            r.q0 |= (uint32_t)row[reflect101(x0 - 4 + j, w)] << (8 * j);
-            r.q1 |= (uint32_t)row[reflect101(x0 + j, w)] << (8 * j);
-            r.q2 |= (uint32_t)row[reflect101(x0 + 4 + j, w)] << (8 * j);
-        }
-    }
+    const uint8_t *a = row + x0 - (mode == HS_LEFT ? 0 : 4);    // left edge: the window starts at byte 0, see hsum4
+    const unsigned mis = (unsigned)((uintptr_t)a & 3);
+    const uint32_t *q = (const uint32_t *)(a - mis);
+    r.q0 = __ldg(q); r.q1 = __ldg(q + 1); r.q2 = __ldg(q + 2); r.q3 = __ldg(q + 3);
+    r.sh = mis * 8;
     return r;
 }
 
@@ -62,8 +62,8 @@ __device__ __forceinline__ Raw fetch_row(const uint8_t *__restrict__ row, int x0
 __device__ __forceinline__ void hsum4(const Raw &r, int mode, int (&h)[4])
 {
     uint32_t w0 = __funnelshift_r(r.q0, r.q1, r.sh), w1 = __funnelshift_r(r.q1, r.q2, r.sh), w2 = __funnelshift_r(r.q2, r.q3, r.sh);
-    if (mode == HS_LEFT) {                                      // q0 is a dummy: (w1, w2) sit one word further
-        w1 = __funnelshift_r(r.q1, r.q2, r.sh); w2 = __funnelshift_r(r.q2, r.q3, r.sh);
+    if (mode == HS_LEFT) {                                      // fetched bytes 0..11: (w0, w1) are really (w1, w2)
+        w2 = w1; w1 = w0;
         w0 = __byte_perm(w1, w2, 0x1234);                       // REFLECT_101: pixels -4,-3,-2,-1 = pixels 4,3,2,1
     }
     const uint32_t G0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // taps -3..0

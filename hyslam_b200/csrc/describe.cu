@@ -14,6 +14,15 @@ namespace hyorb {
 __device__ const int8_t d_brief_pattern[1024] = {
 #include "../../include/hyorb_brief_pattern.inc"
 };
+// the same table as floats (x0, y0, x1, y1 per test), filled once per device by k_pattern_to_float so that a lane fetches
+// its 8 tests with 8 x 128-bit loads and no int->float conversions
+__device__ float4 d_brief_pattern_f[256];
+__global__ void k_pattern_to_float()
+{
+    const int t = threadIdx.x;
+    d_brief_pattern_f[t] = make_float4((float)d_brief_pattern[4 * t], (float)d_brief_pattern[4 * t + 1], (float)d_brief_pattern[4 * t + 2],
+                                       (float)d_brief_pattern[4 * t + 3]);
+}
 
 constexpr int DS_WARPS = 8;
 
@@ -43,7 +52,7 @@ constexpr int PT_R = 18;                 // patch radius: |rotated pattern coord
 constexpr int PT_ROWS = 2 * PT_R + 1;    // 37
 constexpr int PT_WORDS = 10;             // 37 columns + up to 3 bytes of alignment slack, as 32-bit words
 
-__global__ void __launch_bounds__(DS_WARPS * 32)
+__global__ void __launch_bounds__(DS_WARPS * 32, 5)
 k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, const uint32_t *__restrict__ sel_all,
            const int *__restrict__ selCount, hyorb_keypoint *__restrict__ kps, uint8_t *__restrict__ desc, int capacity,
            int *__restrict__ counts, int *__restrict__ status)
@@ -55,15 +64,20 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
     const int b = blockIdx.y;
     const int k = blockIdx.x * DS_WARPS + warp;
     const int nl = plan->nlevels;
-    // locate output slot k: levels are concatenated in order (ORBExtractor.cpp:523-555)
-    int acc = 0, l = -1, j = 0, total = 0;
-    for (int i = 0; i < nl; i++) {
-        int c = selCount[b * HYORB_MAX_LEVELS + i];
-        if (c > plan->lv[i].selCap) c = plan->lv[i].selCap;
-        if (l < 0 && k < acc + c) { l = i; j = k - acc; }
-        acc += c;
+    // locate output slot k: levels are concatenated in order (ORBExtractor.cpp:523-555).  Lane i holds level i's count;
+    // an inclusive warp scan gives the level boundaries.
+    int cnt = 0;
+    if (lane < nl) { cnt = selCount[b * HYORB_MAX_LEVELS + lane]; cnt = min(cnt, plan->lv[lane].selCap); }
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < HYORB_MAX_LEVELS; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
-    total = acc;
+    const int total = __shfl_sync(0xffffffffu, inc, HYORB_MAX_LEVELS - 1);      // lanes >= nl add 0
+    const unsigned below = __ballot_sync(0xffffffffu, lane < nl && inc <= k);    // levels that end at or before slot k
+    const int l = k < total ? __popc(below) : -1;
+    const int j = k - __shfl_sync(0xffffffffu, inc - cnt, l < 0 ? 0 : l);
     if (k == 0 && lane == 0) {
         if (total > capacity) { atomicOr(status, ST_OUT_OVERFLOW); counts[b] = capacity; }
         else counts[b] = total;
@@ -79,10 +93,20 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
     const int gx0 = (px - PT_R) & ~3, off = (px - PT_R) - gx0;
     uint32_t *patch = s_patch[warp];
     {
-        const uint8_t *src = level + (size_t)(py - PT_R) * pitch + gx0;
-        for (int i = lane; i < PT_ROWS * PT_WORDS; i += 32) {
-            const int r = i / PT_WORDS, wd = i - r * PT_WORDS;
-            patch[i] = __ldg((const uint32_t *)(src + (size_t)r * pitch) + wd);
+        // lanes 0..29 cover 3 rows x 10 words per step; all 13 loads are issued before the first store
+        const int lr = lane / PT_WORDS, wd = lane - lr * PT_WORDS;
+        const uint32_t *src = (const uint32_t *)(level + (size_t)(py - PT_R + lr) * pitch + gx0) + wd;
+        const size_t step = (size_t)3 * pitch / 4;
+        uint32_t v[13];
+#pragma unroll
+        for (int t = 0; t < 13; t++) {
+            const int r = 3 * t + lr;
+            v[t] = (lane < 30 && r < PT_ROWS) ? __ldg(src + t * step) : 0u;
+        }
+#pragma unroll
+        for (int t = 0; t < 13; t++) {
+            const int r = 3 * t + lr;
+            if (lane < 30 && r < PT_ROWS) patch[r * PT_WORDS + wd] = v[t];
         }
     }
     __syncwarp();
@@ -117,11 +141,11 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     const float rad = __fmul_rn(angle, factorPI);
     const float a = (float)cos((double)rad), bb = (float)sin((double)rad);
-    const int8_t *pat = d_brief_pattern + lane * 32;
     int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
-        const float x0 = (float)pat[4 * t], y0 = (float)pat[4 * t + 1], x1 = (float)pat[4 * t + 2], y1 = (float)pat[4 * t + 3];
+        const float4 pt = d_brief_pattern_f[lane * 8 + t];
+        const float x0 = pt.x, y0 = pt.y, x1 = pt.z, y1 = pt.w;
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, bb), __fmul_rn(y0, a)));
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bb)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bb), __fmul_rn(y1, a)));
@@ -144,6 +168,14 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
 int launch_describe(const PlanDev &hp, const PlanDev *dp, const uint8_t *blur, const uint32_t *sel, const int *selCount,
                     hyorb_keypoint *kps, uint8_t *desc, int capacity, int *counts, int *status, int B, cudaStream_t st, long *launches)
 {
+    static bool pattern_ready[64] = {};
+    int dev = 0;
+    HY_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !pattern_ready[dev]) {        // once per device; synchronous so that other handles' streams see the table
+        k_pattern_to_float<<<1, 256, 0, st>>>();
+        HY_CUDA(cudaStreamSynchronize(st));
+        pattern_ready[dev] = true; ++*launches;
+    }
     int slots = hp.selTotalCap < capacity ? hp.selTotalCap : capacity;
     if (slots < 1) slots = 1;
     dim3 grd((slots + DS_WARPS - 1) / DS_WARPS, B);

@@ -106,14 +106,16 @@ k_resize(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride
         prev = cur;
         cur = finish_src(raw, sel, c01);
         while (y < y1 && r1 == sr) {
-            const int b0 = vy.c0, b1 = vy.c1;
+            // OpenCV's VResizeLinear: ((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2.  Everything is non-negative and the
+            // result cannot exceed 255 (h <= 255*2049, b0+b1 <= 2049), so the products are taken as umulhi((b<<16), h>>4)
+            // and the saturating cast is a no-op.
+            const uint32_t b0 = (uint32_t)vy.c0 << 16, b1 = (uint32_t)vy.c1 << 16;
             uint32_t out = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int ha = (r0 == sr) ? cur.h[j] : prev.h[j];
-                int v = (((b0 * (ha >> 4)) >> 16) + ((b1 * (cur.h[j] >> 4)) >> 16) + 2) >> 2;
-                v = min(max(v, 0), 255);
-                out |= (uint32_t)v << (8 * j);
+                const uint32_t ha = (uint32_t)((r0 == sr) ? cur.h[j] : prev.h[j]);
+                const uint32_t v = (__umulhi(b0, ha >> 4) + __umulhi(b1, (uint32_t)cur.h[j] >> 4) + 2u) >> 2;
+                out |= v << (8 * j);
             }
             uint8_t *o = d + (size_t)y * dpitch;
             if (x4 + 3 < dw) *(uint32_t *)o = out;     // pitch and level offsets are multiples of 16
