@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhyorb.so")
+LIB_PATH = os.environ.get("HYORB_LIB") or os.path.join(_HERE, "lib", "libhyorb.so")     # HYORB_LIB: A/B-test another build
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, EINVAL, ECAPACITY, EUNSUPPORTED, ENOMEM, ECUDA = 0, -1, -2, -3, -4, -5

@@ -54,7 +54,8 @@ struct hyorb_extractor {
     // kernels of one sub-batch (quadtree, stereo table) overlap the throughput-bound ones (FAST, blur) of another.
     // Lane 0 runs on `stream`.  Inside a lane the blur runs on a side stream next to FAST + quadtree (it only needs the pyramid).
     static constexpr int MAX_LANES = 8;
-    int lanes = 2;
+    int lanes = 2;           // device-pointer entry points
+    int host_lanes = 4;      // host-buffer entry points: more, smaller lanes so the PCIe copies pipeline against the kernels
     bool side_blur = true;
     cudaStream_t lane_stream[MAX_LANES] = {}, side[MAX_LANES] = {};
     cudaEvent_t ev_start = nullptr, ev_pyr[MAX_LANES] = {}, ev_blur[MAX_LANES] = {}, ev_done[MAX_LANES] = {};
@@ -132,9 +133,16 @@ static int ex_event(hyorb_extractor *h, cudaStream_t st, std::vector<cudaEvent_t
     return HYORB_OK;
 }
 
+// host buffers of a "_host" entry point: each lane uploads its own slice before its first kernel and downloads its own
+// results after its last one, so PCIe traffic of one lane overlaps the kernels of the others
+struct HostIO {
+    const uint8_t *images; int stride; size_t image_stride;     // source images (host)
+    hyorb_keypoint *kps; uint8_t *desc; int32_t *counts; float *uR; float *depth;   // destinations (host), uR/depth optional
+};
+
 // the whole extraction pipeline (+ optional stereo association over consecutive image pairs) for B images
 static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_keypoint *d_kps, uint8_t *d_desc, int capacity, int32_t *d_counts,
-                  const hyorb_stereo_params *sp = nullptr, float *d_uR = nullptr, float *d_depth = nullptr)
+                  const hyorb_stereo_params *sp = nullptr, float *d_uR = nullptr, float *d_depth = nullptr, const HostIO *io = nullptr)
 {
     HY_CUDA(cudaSetDevice(h->device));
     HY_TRY(ex_ensure_plan(h, w, hgt));
@@ -148,7 +156,8 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
     const PlanDev *dp = h->d_plan.as<PlanDev>();
     // ---- cut the batch into lanes (whole pairs when the stereo stage follows)
     const int unit = sp ? 2 : 1, units = B / unit;
-    int nl = h->lanes < 1 ? 1 : (h->lanes > hyorb_extractor::MAX_LANES ? hyorb_extractor::MAX_LANES : h->lanes);
+    const int want = io ? h->host_lanes : h->lanes;
+    int nl = want < 1 ? 1 : (want > hyorb_extractor::MAX_LANES ? hyorb_extractor::MAX_LANES : want);
     if (nl > units) nl = units;
     int first[hyorb_extractor::MAX_LANES + 1];
     for (int k = 0; k <= nl; k++) first[k] = unit * (int)((long long)units * k / nl);
@@ -170,6 +179,16 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
             switch (stage) {
             case 0:
                 if (k > 0) HY_CUDA(cudaStreamWaitEvent(st, h->ev_start, 0));
+                if (io) {       // upload this lane's images into the staging copy (same geometry as the host buffer when it is dense)
+                    uint8_t *dst = const_cast<uint8_t *>(l0k.base);
+                    const uint8_t *src = io->images + (size_t)i0 * io->image_stride;
+                    if (l0.pitch == io->stride && l0.stride == io->image_stride)
+                        HY_CUDA(cudaMemcpyAsync(dst, src, (size_t)(Bk - 1) * io->image_stride + (size_t)io->stride * (hgt - 1) + w, cudaMemcpyHostToDevice, st));
+                    else
+                        for (int i = 0; i < Bk; i++)
+                            HY_CUDA(cudaMemcpy2DAsync(dst + (size_t)i * l0.stride, l0.pitch, src + (size_t)i * io->image_stride, io->stride, w, hgt,
+                                                      cudaMemcpyHostToDevice, st));
+                }
                 HY_CUDA(cudaMemsetAsync(candCount, 0, sizeof(int) * HYORB_MAX_LEVELS * (size_t)Bk, st));
                 HY_TRY(ex_event(h, st, &evs[k]));
                 HY_TRY(launch_pyramid(P, dp, l0k, pyr, h->d_resize.as<ResizeTab>(), Bk, st, &h->launches));
@@ -225,6 +244,20 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
                     if (!h->ev_free.empty()) { e = h->ev_free.back(); h->ev_free.pop_back(); } else HY_CUDA(cudaEventCreate(&e));
                     HY_CUDA(cudaEventRecord(e, st));
                     evs[k][6] = e;
+                }
+                if (io) {       // download this lane's results
+                    HY_CUDA(cudaMemcpyAsync(io->counts + i0, d_counts + i0, sizeof(int32_t) * Bk, cudaMemcpyDeviceToHost, st));
+                    HY_CUDA(cudaMemcpyAsync(io->kps + (size_t)i0 * capacity, d_kps + (size_t)i0 * capacity, sizeof(hyorb_keypoint) * (size_t)capacity * Bk,
+                                            cudaMemcpyDeviceToHost, st));
+                    HY_CUDA(cudaMemcpyAsync(io->desc + (size_t)i0 * capacity * HYORB_DESC_BYTES, d_desc + (size_t)i0 * capacity * HYORB_DESC_BYTES,
+                                            (size_t)HYORB_DESC_BYTES * capacity * Bk, cudaMemcpyDeviceToHost, st));
+                    if (sp && io->uR && io->depth) {
+                        const int p0 = i0 / 2;
+                        HY_CUDA(cudaMemcpyAsync(io->uR + (size_t)p0 * capacity, d_uR + (size_t)p0 * capacity, sizeof(float) * (size_t)capacity * (Bk / 2),
+                                                cudaMemcpyDeviceToHost, st));
+                        HY_CUDA(cudaMemcpyAsync(io->depth + (size_t)p0 * capacity, d_depth + (size_t)p0 * capacity, sizeof(float) * (size_t)capacity * (Bk / 2),
+                                                cudaMemcpyDeviceToHost, st));
+                    }
                 }
                 if (k > 0) {
                     HY_CUDA(cudaEventRecord(h->ev_done[k], st));
@@ -291,6 +324,7 @@ HYORB_API int hyorb_extractor_create(const hyorb_extractor_params *params, int d
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming);
     if (const char *v = getenv("HYORB_LANES")) h->lanes = atoi(v);
+    if (const char *v = getenv("HYORB_HOST_LANES")) h->host_lanes = atoi(v);
     if (const char *v = getenv("HYORB_SIDE_BLUR")) h->side_blur = atoi(v) != 0;
     if (e != cudaSuccess) { set_error("CUDA init: %s", cudaGetErrorString(e)); delete h; return HYORB_ECUDA; }
     *out = h;
@@ -353,6 +387,21 @@ HYORB_API int hyorb_extractor_sync(hyorb_extractor *h)
     return ex_sync(h);
 }
 
+// staging copy of a host batch: dense host batches (any stride) are mirrored byte for byte with one flat copy per lane --
+// the kernels accept any row alignment; otherwise rows are repacked to the plan's aligned pitch
+static int ex_stage_geometry(hyorb_extractor *h, int n_images, int width, int height, int stride, size_t image_stride, Level0 *l0)
+{
+    const PlanDev &P = h->plan.dev;
+    const bool dense = image_stride >= (size_t)stride * height && image_stride <= (size_t)stride * height + 4096;
+    int pitch; size_t dstride;
+    if (dense) { pitch = stride; dstride = image_stride; }
+    else { pitch = P.lv[0].pitch; dstride = ((size_t)pitch * height + 255) & ~(size_t)255; }
+    HY_TRY(h->d_in.ensure(dstride * n_images + 512));
+    *l0 = Level0{h->d_in.as<uint8_t>(), pitch, (unsigned long long)dstride};
+    (void)width;
+    return HYORB_OK;
+}
+
 HYORB_API int hyorb_extract_batch_host(hyorb_extractor *h, const uint8_t *images, int n_images, int width, int height, int stride,
                                        size_t image_stride, hyorb_keypoint *kps, uint8_t *desc, int capacity, int32_t *counts)
 {
@@ -361,25 +410,14 @@ HYORB_API int hyorb_extract_batch_host(hyorb_extractor *h, const uint8_t *images
     if (n_images > 65535) { set_error("at most 65535 images per batch"); return HYORB_EUNSUPPORTED; }
     HY_CUDA(cudaSetDevice(h->device));
     HY_TRY(ex_ensure_plan(h, width, height));
-    const PlanDev &P = h->plan.dev;
-    const int pitch = P.lv[0].pitch;
-    const size_t dstride = ((size_t)pitch * height + 255) & ~(size_t)255;
-    HY_TRY(h->d_in.ensure(dstride * n_images + 256));
+    Level0 l0;
+    HY_TRY(ex_stage_geometry(h, n_images, width, height, stride, image_stride, &l0));
     HY_TRY(h->d_kps.ensure(sizeof(hyorb_keypoint) * (size_t)capacity * n_images));
     HY_TRY(h->d_desc.ensure((size_t)HYORB_DESC_BYTES * capacity * n_images));
     HY_TRY(h->d_counts.ensure(sizeof(int32_t) * n_images));
-    if ((size_t)stride * height == image_stride && n_images > 1) {
-        // images are back to back: one 2D copy over all rows of the batch is not possible with a padded destination stride,
-        // so fall through to per-image copies unless the destination is equally dense
-    }
-    for (int i = 0; i < n_images; i++)
-        HY_CUDA(cudaMemcpy2DAsync(h->d_in.as<uint8_t>() + dstride * i, pitch, images + image_stride * i, stride, width, height,
-                                  cudaMemcpyHostToDevice, h->stream));
-    Level0 l0{h->d_in.as<uint8_t>(), pitch, (unsigned long long)dstride};
-    HY_TRY(ex_run(h, l0, n_images, width, height, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), capacity, h->d_counts.as<int32_t>()));
-    HY_CUDA(cudaMemcpyAsync(counts, h->d_counts.p, sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, h->stream));
-    HY_CUDA(cudaMemcpyAsync(kps, h->d_kps.p, sizeof(hyorb_keypoint) * (size_t)capacity * n_images, cudaMemcpyDeviceToHost, h->stream));
-    HY_CUDA(cudaMemcpyAsync(desc, h->d_desc.p, (size_t)HYORB_DESC_BYTES * capacity * n_images, cudaMemcpyDeviceToHost, h->stream));
+    HostIO io{images, stride, image_stride, kps, desc, counts, nullptr, nullptr};
+    HY_TRY(ex_run(h, l0, n_images, width, height, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), capacity, h->d_counts.as<int32_t>(),
+                  nullptr, nullptr, nullptr, &io));
     return ex_sync(h);
 }
 
@@ -434,26 +472,16 @@ HYORB_API int hyorb_process_stereo_batch_host(hyorb_extractor *h, const hyorb_st
     const int n_images = 2 * n_pairs;
     HY_CUDA(cudaSetDevice(h->device));
     HY_TRY(ex_ensure_plan(h, width, height));
-    const PlanDev &P = h->plan.dev;
-    const int pitch = P.lv[0].pitch;
-    const size_t dstride = ((size_t)pitch * height + 255) & ~(size_t)255;
-    HY_TRY(h->d_in.ensure(dstride * n_images + 256));
+    Level0 l0;
+    HY_TRY(ex_stage_geometry(h, n_images, width, height, stride, image_stride, &l0));
     HY_TRY(h->d_kps.ensure(sizeof(hyorb_keypoint) * (size_t)capacity * n_images));
     HY_TRY(h->d_desc.ensure((size_t)HYORB_DESC_BYTES * capacity * n_images));
     HY_TRY(h->d_counts.ensure(sizeof(int32_t) * n_images));
     HY_TRY(h->d_uR.ensure(sizeof(float) * (size_t)capacity * n_pairs));
     HY_TRY(h->d_depth.ensure(sizeof(float) * (size_t)capacity * n_pairs));
-    for (int i = 0; i < n_images; i++)
-        HY_CUDA(cudaMemcpy2DAsync(h->d_in.as<uint8_t>() + dstride * i, pitch, images + image_stride * i, stride, width, height,
-                                  cudaMemcpyHostToDevice, h->stream));
-    Level0 l0{h->d_in.as<uint8_t>(), pitch, (unsigned long long)dstride};
+    HostIO io{images, stride, image_stride, kps, desc, counts, uR, depth};
     HY_TRY(ex_run(h, l0, n_images, width, height, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), capacity, h->d_counts.as<int32_t>(), sp,
-                  h->d_uR.as<float>(), h->d_depth.as<float>()));
-    HY_CUDA(cudaMemcpyAsync(counts, h->d_counts.p, sizeof(int32_t) * n_images, cudaMemcpyDeviceToHost, h->stream));
-    HY_CUDA(cudaMemcpyAsync(kps, h->d_kps.p, sizeof(hyorb_keypoint) * (size_t)capacity * n_images, cudaMemcpyDeviceToHost, h->stream));
-    HY_CUDA(cudaMemcpyAsync(desc, h->d_desc.p, (size_t)HYORB_DESC_BYTES * capacity * n_images, cudaMemcpyDeviceToHost, h->stream));
-    HY_CUDA(cudaMemcpyAsync(uR, h->d_uR.p, sizeof(float) * (size_t)capacity * n_pairs, cudaMemcpyDeviceToHost, h->stream));
-    HY_CUDA(cudaMemcpyAsync(depth, h->d_depth.p, sizeof(float) * (size_t)capacity * n_pairs, cudaMemcpyDeviceToHost, h->stream));
+                  h->d_uR.as<float>(), h->d_depth.as<float>(), &io));
     return ex_sync(h);
 }
 
