@@ -27,44 +27,32 @@ __device__ __forceinline__ int reflect101(int i, int n)
 // how a thread fetches the 12 source bytes x0-4 .. x0+7 of a row
 enum { HS_WORDS = 0,      // interior: aligned-down 32-bit loads + funnel shift (any row alignment)
        HS_LEFT = 1,       // x0 == 0: bytes -4..-1 are the reflection of bytes 4..1
-       HS_BYTES = 2 };    // right edge: per-byte gather through reflected column indices
+       HS_BYTES = 2 };    // right edge: per-byte gather through precomputed reflected column indices
 
-struct Raw { uint32_t q0, q1, q2, q3; unsigned sh; };     // loaded words of one row + the funnel shift that aligns them
-
-// right-edge threads (at most two per row band): per-byte gather with reflection.  Kept out of line: the main loop is
-// unrolled 7x and must stay small enough for the instruction cache.
-__device__ __noinline__ Raw fetch_bytes(const uint8_t *__restrict__ row, int x0, int w)
+// horizontal 7-tap sums of the 4 pixels x0..x0+3 of one source row
+__device__ __forceinline__ void hsum4(const uint8_t *__restrict__ row, int x0, int mode, const int (&xi)[12], int (&h)[4])
 {
-    Raw r;
-    r.q0 = r.q1 = r.q2 = r.q3 = 0; r.sh = 0;
-    for (int j = 0; j < 4; j++) {
-        r.q0 |= (uint32_t)row[reflect101(x0 - 4 + j, w)] << (8 * j);
-        r.q1 |= (uint32_t)row[reflect101(x0 + j, w)] << (8 * j);
-        r.q2 |= (uint32_t)row[reflect101(x0 + 4 + j, w)] << (8 * j);
-    }
-    return r;
-}
-
-// issue the loads of one source row (no use of the loaded values here, so rows can be fetched ahead of their use)
-__device__ __forceinline__ Raw fetch_row(const uint8_t *__restrict__ row, int x0, int w, int mode)
-{
-    if (mode == HS_BYTES) return fetch_bytes(row, x0, w);
-    Raw r;
-    const uint8_t *a = row + x0 - (mode == HS_LEFT ? 0 : 4);    // left edge: the window starts at byte 0, see hsum4
-    const unsigned mis = (unsigned)((uintptr_t)a & 3);
-    const uint32_t *q = (const uint32_t *)(a - mis);
-    r.q0 = __ldg(q); r.q1 = __ldg(q + 1); r.q2 = __ldg(q + 2); r.q3 = __ldg(q + 3);
-    r.sh = mis * 8;
-    return r;
-}
-
-// horizontal 7-tap sums of the 4 pixels x0..x0+3 from the fetched words of a row
-__device__ __forceinline__ void hsum4(const Raw &r, int mode, int (&h)[4])
-{
-    uint32_t w0 = __funnelshift_r(r.q0, r.q1, r.sh), w1 = __funnelshift_r(r.q1, r.q2, r.sh), w2 = __funnelshift_r(r.q2, r.q3, r.sh);
-    if (mode == HS_LEFT) {                                      // fetched bytes 0..11: (w0, w1) are really (w1, w2)
-        w2 = w1; w1 = w0;
-        w0 = __byte_perm(w1, w2, 0x1234);                       // REFLECT_101: pixels -4,-3,-2,-1 = pixels 4,3,2,1
+    uint32_t w0, w1, w2;
+    if (mode == HS_WORDS) {
+        const uint8_t *a = row + x0 - 4;
+        const unsigned mis = (unsigned)((uintptr_t)a & 3);
+        const uint32_t *q = (const uint32_t *)(a - mis);
+        const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+        w0 = __funnelshift_r(q0, q1, mis * 8); w1 = __funnelshift_r(q1, q2, mis * 8); w2 = __funnelshift_r(q2, q3, mis * 8);
+    } else if (mode == HS_LEFT) {
+        const unsigned mis = (unsigned)((uintptr_t)row & 3);
+        const uint32_t *q = (const uint32_t *)(row - mis);     // mis > 0 only for rows > 0 or an unaligned base inside an allocation
+        const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        w1 = __funnelshift_r(q0, q1, mis * 8); w2 = __funnelshift_r(q1, q2, mis * 8);
+        w0 = __byte_perm(w1, w2, 0x1234);                      // REFLECT_101: pixels -4,-3,-2,-1 = pixels 4,3,2,1
+    } else {
+        w0 = w1 = w2 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            w0 |= (uint32_t)row[xi[j]] << (8 * j);
+            w1 |= (uint32_t)row[xi[4 + j]] << (8 * j);
+            w2 |= (uint32_t)row[xi[8 + j]] << (8 * j);
+        }
     }
     const uint32_t G0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // taps -3..0
     const uint32_t G1 = 48u | (34u << 8) | (18u << 16);                   // taps +1..+3
@@ -92,37 +80,28 @@ k_blur(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
     const uint8_t *img; int pitch;
     if (l == 0) { img = l0.base + (size_t)b * l0.stride; pitch = l0.pitch; }
     else { img = pyr + (size_t)b * plan->pyrStride + L.off; pitch = L.pitch; }
-    // aligned-down word loads read at most 3 bytes before x0-4 (inside the row, or the previous row / image) and up to byte x0+11
-    const bool base_ok = ((uintptr_t)img & 3) == 0 || b > 0;
+    // aligned-down word loads read at most 3 bytes before x0-4 (still inside the row because x0 >= 4) and up to byte x0+11
     int mode = HS_BYTES;
-    if (x0 >= 4 && x0 + 12 <= w && (x0 >= 8 || base_ok)) mode = HS_WORDS;
-    else if (x0 == 0 && base_ok) mode = HS_LEFT;                // w >= 62 always holds (tables.cu)
+    if (x0 >= 4 && x0 + 12 <= w && (x0 >= 8 || ((uintptr_t)img & 3) == 0 || b > 0)) mode = HS_WORDS;
+    else if (x0 == 0 && (((uintptr_t)img & 3) == 0 || b > 0)) mode = HS_LEFT;     // w >= 62 always holds (tables.cu)
+    int xi[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) xi[j] = reflect101(x0 - 4 + j, w);
     uint8_t *out = blur + (size_t)b * plan->pyrStride + L.off + x0;
     const int opitch = L.pitch;
     const int yEnd = min(y0 + BL_ROWS, h);
 
     int win[7][4];       // win[k] = horizontal sums of source row (y - 3 + k) relative to the current output row
-    // prime rows y0-3 .. y0+2 into slots 0..5; the loads of all six rows are issued before the first use
-    {
-        Raw pr[6];
+    // prime rows y0-3 .. y0+2 into slots 0..5
 #pragma unroll
-        for (int k = 0; k < 6; k++) pr[k] = fetch_row(img + (size_t)reflect101(y0 - 3 + k, h) * pitch, x0, w, mode);
-#pragma unroll
-        for (int k = 0; k < 6; k++) hsum4(pr[k], mode, win[k]);
-    }
-    // rows are fetched two iterations ahead of their use
-    Raw nx0 = fetch_row(img + (size_t)reflect101(y0 + 3, h) * pitch, x0, w, mode);
-    Raw nx1 = fetch_row(img + (size_t)reflect101(y0 + 4, h) * pitch, x0, w, mode);
+    for (int k = 0; k < 6; k++) hsum4(img + (size_t)reflect101(y0 - 3 + k, h) * pitch, x0, mode, xi, win[k]);
     for (int yb = y0; yb < yEnd; yb += 7) {
 #pragma unroll
         for (int k = 0; k < 7; k++) {
             const int y = yb + k;
             if (y < yEnd) {
-                const Raw cur = nx0;
-                nx0 = nx1;
-                nx1 = fetch_row(img + (size_t)reflect101(y + 5, h) * pitch, x0, w, mode);
                 // the newest source row (y+3) goes into slot (6+k)%7; output row y then reads slots (k .. k+6)%7
-                hsum4(cur, mode, win[(6 + k) % 7]);
+                hsum4(img + (size_t)reflect101(y + 3, h) * pitch, x0, mode, xi, win[(6 + k) % 7]);
                 uint32_t o = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {

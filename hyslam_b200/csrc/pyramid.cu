@@ -12,40 +12,33 @@
 
 namespace hyorb {
 
-constexpr int RS_BX = 64, RS_BY = 4, RS_ROWS = 16;
+constexpr int RS_BX = 64, RS_BY = 4, RS_ROWS = 8;
 
 struct HRow { int h[4]; };
-struct RawRow { uint32_t w0, w1, w2; unsigned sh; };
 
-// issue the loads of the <= 9 source bytes under a thread's 4 columns (bytes s0 .. s0+8 of the row); nothing here
-// depends on the loaded values, so rows can be fetched ahead of their use
-__device__ __forceinline__ RawRow fetch_src(const uint8_t *__restrict__ row, int s0, int roww, bool wordsafe)
+__device__ __forceinline__ HRow hrow(const uint8_t *__restrict__ row, int s0, int roww, bool wordsafe, const uint32_t (&sel)[4], const uint32_t (&c01)[4])
 {
-    RawRow r;
+    // bytes s0 .. s0+5 of the row, as two registers A (s0..s0+3) and B (s0+4..s0+7)
+    uint32_t A, B;
     if (wordsafe && s0 + 12 <= roww) {
         const unsigned mis = (unsigned)((uintptr_t)(row + s0) & 3);
         const uint32_t *p = (const uint32_t *)(row + s0 - mis);
-        r.w0 = __ldg(p); r.w1 = __ldg(p + 1); r.w2 = __ldg(p + 2);
-        r.sh = mis * 8;
+        const unsigned sh = mis * 8;
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        A = __funnelshift_r(w0, w1, sh);
+        B = __funnelshift_r(w1, w2, sh);
     } else {
-        r.w0 = r.w1 = r.w2 = 0; r.sh = 0;
+        A = B = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (s0 + j < roww) r.w0 |= (uint32_t)row[s0 + j] << (8 * j);
-            if (s0 + 4 + j < roww) r.w1 |= (uint32_t)row[s0 + 4 + j] << (8 * j);
+            if (s0 + j < roww) A |= (uint32_t)row[s0 + j] << (8 * j);
+            if (s0 + 4 + j < roww) B |= (uint32_t)row[s0 + 4 + j] << (8 * j);
         }
     }
-    return r;
-}
-
-// horizontal interpolation of the 4 columns: one PRMT (pick the two taps) + one DP2A (taps x Q11 coefficient pair) each
-__device__ __forceinline__ HRow finish_src(const RawRow &r, const uint32_t (&sel)[4], const uint32_t (&c01)[4])
-{
-    const uint32_t A = __funnelshift_r(r.w0, r.w1, r.sh), B = __funnelshift_r(r.w1, r.w2, r.sh);   // bytes s0..s0+3, s0+4..s0+7
-    HRow o;
+    HRow r;
 #pragma unroll
-    for (int j = 0; j < 4; j++) o.h[j] = (int)__dp2a_lo(c01[j], __byte_perm(A, B, sel[j]), 0u);      // src[s]*c0 + src[s+1]*c1
-    return o;
+    for (int j = 0; j < 4; j++) r.h[j] = (int)__dp2a_lo(c01[j], __byte_perm(A, B, sel[j]), 0u);   // src[s0]*c0 + src[s0+1]*c1
+    return r;
 }
 
 __global__ void __launch_bounds__(RS_BX * RS_BY)
@@ -77,55 +70,35 @@ k_resize(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride
     for (int j = 0; j < 4; j++) {
         const ResizeTab t = tx[min(x4 + j, dw - 1)];
         if (j == 0) s0 = t.ofs;
-        const uint32_t dlt = (uint32_t)(t.ofs - s0);          // <= 6 (checked on the host): both taps lie in bytes s0..s0+7
-        sel[j] = dlt | ((dlt + 1) << 4);                      // PRMT: byte0 = tap0, byte1 = tap1 (bytes 2,3 unused)
+        const uint32_t dlt = (uint32_t)(t.ofs - s0);          // 0..4 for a downscale by <= 1.33; checked on the host
+        sel[j] = dlt | ((dlt + 1) << 4);                      // PRMT: byte0 = tap0, byte1 = tap1 (byte 2,3 = A[0], unused)
         c01[j] = (uint32_t)(uint16_t)t.c0 | ((uint32_t)(uint16_t)t.c1 << 16);
     }
-    // aligned-down word loads start at most 3 bytes before a row's first tap: inside the previous row / image, except for
-    // the very first bytes of an unaligned batch base
-    const bool base_ok = ((uintptr_t)src & 3) == 0 || blockIdx.z > 0 || s0 >= 3;
-
-    // The vertical taps of consecutive destination rows walk down the source rows one at a time (scale < 2), so the thread
-    // streams source rows ys..ye, fetched two rows ahead, keeps the horizontal values of the last two, and emits every
-    // destination row whose lower tap is the row just finished.
-    ResizeTab vy = ty[y0];
-    int r0 = min(max(vy.ofs, 0), sh - 1), r1 = min(max(vy.ofs + 1, 0), sh - 1);
-    const int ys = r0;
-    const ResizeTab vl = ty[y1 - 1];
-    const int ye = min(max(vl.ofs + 1, 0), sh - 1);
-    RawRow nx0 = fetch_src(s + (size_t)ys * spitch, s0, sw, base_ok || ys > 0);
-    RawRow nx1 = fetch_src(s + (size_t)min(ys + 1, sh - 1) * spitch, s0, sw, true);
-    HRow prev, cur;
+    // aligned-down word loads start at most 3 bytes before a row's first tap: inside the previous row / image, except
+    // for the very first bytes of an unaligned batch base
+    const bool base_aligned = ((uintptr_t)src & 3) == 0;
+    int haveRow = -1;          // source row whose horizontal values sit in hb
+    HRow ha, hb;
+    for (int y = y0; y < y1; y++) {
+        const ResizeTab vy = ty[y];
+        const int sy0 = min(max(vy.ofs, 0), sh - 1), sy1 = min(max(vy.ofs + 1, 0), sh - 1);
+        const bool wordsafe = base_aligned || s0 >= 3 || sy0 > 0 || blockIdx.z > 0;
+        if (sy0 == haveRow) ha = hb;
+        else ha = hrow(s + (size_t)sy0 * spitch, s0, sw, wordsafe, sel, c01);
+        if (sy1 == sy0) hb = ha;
+        else hb = hrow(s + (size_t)sy1 * spitch, s0, sw, wordsafe, sel, c01);
+        haveRow = sy1;
+        const int b0 = vy.c0, b1 = vy.c1;
+        uint32_t out = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) { prev.h[j] = 0; cur.h[j] = 0; }
-    int y = y0;
-    for (int sr = ys; sr <= ye; sr++) {
-        const RawRow raw = nx0;
-        nx0 = nx1;
-        nx1 = fetch_src(s + (size_t)min(sr + 2, sh - 1) * spitch, s0, sw, true);
-        prev = cur;
-        cur = finish_src(raw, sel, c01);
-        while (y < y1 && r1 == sr) {
-            // OpenCV's VResizeLinear: ((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2.  Everything is non-negative and the
-            // result cannot exceed 255 (h <= 255*2049, b0+b1 <= 2049), so the products are taken as umulhi((b<<16), h>>4)
-            // and the saturating cast is a no-op.
-            const uint32_t b0 = (uint32_t)vy.c0 << 16, b1 = (uint32_t)vy.c1 << 16;
-            uint32_t out = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t ha = (uint32_t)((r0 == sr) ? cur.h[j] : prev.h[j]);
-                const uint32_t v = (__umulhi(b0, ha >> 4) + __umulhi(b1, (uint32_t)cur.h[j] >> 4) + 2u) >> 2;
-                out |= v << (8 * j);
-            }
-            uint8_t *o = d + (size_t)y * dpitch;
-            if (x4 + 3 < dw) *(uint32_t *)o = out;     // pitch and level offsets are multiples of 16
-            else for (int j = 0; x4 + j < dw; j++) o[j] = (uint8_t)(out >> (8 * j));
-            y++;
-            if (y < y1) {
-                vy = ty[y];
-                r0 = min(max(vy.ofs, 0), sh - 1); r1 = min(max(vy.ofs + 1, 0), sh - 1);
-            }
+        for (int j = 0; j < 4; j++) {
+            int v = (((b0 * (ha.h[j] >> 4)) >> 16) + ((b1 * (hb.h[j] >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+            out |= (uint32_t)v << (8 * j);
         }
+        uint8_t *o = d + (size_t)y * dpitch;
+        if (x4 + 3 < dw) *(uint32_t *)o = out;     // pitch and level offsets are multiples of 16
+        else for (int j = 0; x4 + j < dw; j++) o[j] = (uint8_t)(out >> (8 * j));
     }
 }
 
