@@ -56,7 +56,7 @@ struct hyorb_extractor {
     static constexpr int MAX_LANES = 8;
     int lanes = 2;           // device-pointer entry points
     int host_lanes = 4;      // host-buffer entry points: more, smaller lanes so the PCIe copies pipeline against the kernels
-    bool side_blur = true;
+    bool side_blur = false;   // measured: no gain once lanes overlap whole pipelines (HYORB_SIDE_BLUR=1 to enable)
     cudaStream_t lane_stream[MAX_LANES] = {}, side[MAX_LANES] = {};
     cudaEvent_t ev_start = nullptr, ev_pyr[MAX_LANES] = {}, ev_blur[MAX_LANES] = {}, ev_done[MAX_LANES] = {};
     float scale[HYORB_MAX_LEVELS], inv[HYORB_MAX_LEVELS], sigma2[HYORB_MAX_LEVELS], inv_sigma2[HYORB_MAX_LEVELS];

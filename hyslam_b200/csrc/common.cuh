@@ -34,12 +34,15 @@ constexpr int FAST_T = 20;           // ORBFinder.h:92 + setter bug ORBFinder.cp
 constexpr int LATTICE_MIN = 16;      // minBorderX = EDGE_THRESHOLD-3 (ORBExtractor.cpp:417)
 constexpr int DET_MIN = 19;          // first pixel FAST can report: lattice min + 3
 
-// FAST tile geometry: a CTA scores a 64x32 region (one 4-pixel group x one row per work item, two items per
-// thread) and emits the 62x30 interior, so the 3x3 NMS never leaves the CTA.
-constexpr int FT_SW = 64, FT_SH = 32;          // score region
+// FAST tile geometry: a CTA scores a 64 x (16*FT_ITEMS) region (one 4-pixel group x one row per work item, FT_ITEMS items
+// per thread) and emits the interior (2 pixels less each way), so the 3x3 NMS never leaves the CTA.
+#ifndef HYORB_FT_ITEMS
+#define HYORB_FT_ITEMS 4
+#endif
+constexpr int FT_ITEMS = HYORB_FT_ITEMS;
+constexpr int FT_SW = 64, FT_SH = 16 * FT_ITEMS;       // score region
 constexpr int FT_OW = FT_SW - 2, FT_OH = FT_SH - 2;   // emitted interior
 constexpr int FT_PW = FT_SW + 6, FT_PH = FT_SH + 6;   // pixel region (ring radius 3)
-constexpr int FT_PITCH = 72;                           // bytes, 18 words
 constexpr int FT_THREADS = 256;
 
 constexpr int QT_DMAX = 13;          // quadtree path bits per axis

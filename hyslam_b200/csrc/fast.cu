@@ -41,7 +41,7 @@ __device__ __forceinline__ constexpr int ring_off(int k)
     return dy[k] * 192 + dx[k];
 }
 
-constexpr int EMIT_CAP = 1024;
+constexpr int EMIT_CAP = 512 * FT_ITEMS;     // NMS survivors of one tile: < (FT_OW/2+1)*(FT_OH/2+1), doubled for cell edges
 constexpr int RW = 48;            // shared-memory row stride in words: == 16 (mod 32), so the two rows a warp touches per
                                   // load (16 groups x 2 rows) fall into disjoint banks
 constexpr int LW = 18;            // words actually loaded per row (70 pixels + 2)
@@ -76,30 +76,41 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
     else { img = pyr + (size_t)b * plan->pyrStride + L.off; pitch = L.pitch; }
 
     if (tid == 0) { s_n = 0; s_ne = 0; }
-    // ---- stage pixels: 38 rows x 18 words, aligned 32-bit global loads re-aligned with a funnel shift
-    for (int i = tid; i < FT_PH * LW; i += FT_THREADS) {
-        const int rr = i / LW, ww = i - rr * LW;
-        const int y = gy0 + rr, x = gx0 + 4 * ww;
-        uint32_t v = 0;
-        if (y < h && x < w) {
-            const uint8_t *p = img + (size_t)y * pitch;
-            const unsigned mis = (unsigned)((uintptr_t)(p + x) & 3);
-            const int xa = x - (int)mis;                               // aligned-down start; gx0 >= 15 keeps xa >= 0
-            if (xa + 7 < w) {
-                const uint32_t *q = (const uint32_t *)(p + xa);
-                v = __funnelshift_r(__ldg(q), __ldg(q + 1), mis * 8);
-            } else {
+    // ---- stage pixels: FT_PH rows x 18 words; warp `wy` takes rows wy, wy+8, ...; lanes 0..17 one word each: aligned
+    // 32-bit global loads re-aligned with a funnel shift, all loads of a thread issued before the first store
+    {
+        const int lane = tid & 31, wy = tid >> 5;
+        constexpr int NR = (FT_PH + 7) / 8;
+        uint32_t v[NR];
+        const int x = gx0 + 4 * lane;
 #pragma unroll
-                for (int j = 0; j < 4; j++) if (x + j < w) v |= (uint32_t)p[x + j] << (8 * j);
+        for (int k = 0; k < NR; k++) {
+            const int rr = wy + 8 * k, y = gy0 + rr;
+            v[k] = 0;
+            if (lane < LW && rr < FT_PH && y < h && x < w) {
+                const uint8_t *p = img + (size_t)y * pitch;
+                const unsigned mis = (unsigned)((uintptr_t)(p + x) & 3);
+                const int xa = x - (int)mis;                           // aligned-down start; gx0 >= 15 keeps xa >= 0
+                if (xa + 7 < w) {
+                    const uint32_t *q = (const uint32_t *)(p + xa);
+                    v[k] = __funnelshift_r(__ldg(q), __ldg(q + 1), mis * 8);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (x + j < w) v[k] |= (uint32_t)p[x + j] << (8 * j);
+                }
             }
         }
-        s_pix[rr * RW + ww] = v;
+#pragma unroll
+        for (int k = 0; k < NR; k++) {
+            const int rr = wy + 8 * k;
+            if (lane < LW && rr < FT_PH) s_pix[rr * RW + lane] = v[k];
+        }
     }
     for (int i = tid; i < FT_SH * FT_SW / 4; i += FT_THREADS) ((uint32_t *)s_score)[i] = 0;
     if (tid < FT_SW) {
         const int m = (sx0 + tid - DET_MIN) % L.wCell;      // sx0+tid >= 18; the halo column left of x=19 is never valid
         s_cf[tid] = (uint8_t)((m == 0 ? 1 : 0) | (m == L.wCell - 1 ? 2 : 0));
-    } else if (tid >= 64 && tid < 64 + FT_SH) {
+    } else if (tid >= 64 && tid < 64 + FT_SH) {      // FT_SH <= 128
         const int r = tid - 64;
         const int m = (sy0 + r - DET_MIN) % L.hCell;
         s_rf[r] = (uint8_t)((m == 0 ? 1 : 0) | (m == L.hCell - 1 ? 2 : 0));
@@ -108,9 +119,11 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
 
     const int xEnd = L.maxBX - 3, yEnd = L.maxBY - 3;     // detect range [19, xEnd) x [19, yEnd)
     // ---- corner test, 4 pixels per item
-    uint32_t nflag[2] = {0u, 0u};
+    uint32_t nflag[FT_ITEMS];
 #pragma unroll
-    for (int it = 0; it < 2; it++) {
+    for (int it = 0; it < FT_ITEMS; it++) nflag[it] = 0u;
+#pragma unroll 1
+    for (int it = 0; it < FT_ITEMS; it++) {
         const int id = tid + it * FT_THREADS;
         const int g = id & 15, r = id >> 4;
         const int sy = sy0 + r;
@@ -168,29 +181,33 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
         any &= valid;
         nflag[it] = any;
     }
-    // ---- compact the corner flags of both items into the CTA list: warp prefix sum + one atomic per warp
+    // ---- compact the corner flags into the CTA list: one ballot per (item, pixel) slot gives every lane its offset inside
+    // the warp's contiguous chunk; one shared-memory atomic per warp reserves the chunk
     {
         const int lane = tid & 31;
-        const int n0 = __popc(nflag[0]), n1 = __popc(nflag[1]);
-        int inc = n0 + n1;
+        const unsigned lt = (1u << lane) - 1u;
+        unsigned bal[FT_ITEMS * 4];
+        int total = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        for (int it = 0; it < FT_ITEMS; it++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                bal[it * 4 + j] = __ballot_sync(0xffffffffu, (nflag[it] >> (8 * j + 7)) & 1u);
+                total += __popc(bal[it * 4 + j]);
+            }
         int base = 0;
-        if (lane == 31 && total) base = atomicAdd(&s_n, total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        int pos = base + inc - (n0 + n1);
+        if (lane == 0 && total) base = atomicAdd(&s_n, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
-        for (int it = 0; it < 2; it++) {
+        for (int it = 0; it < FT_ITEMS; it++) {
             const int id = tid + it * FT_THREADS;
-            const int g = id & 15, r = id >> 4;
-            const uint32_t any = nflag[it];
+            const int e0 = (id >> 4) * FT_SW + 4 * (id & 15);
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (any & (0x80u << (8 * j))) s_list[pos++] = (uint16_t)(r * FT_SW + 4 * g + j);
+            for (int j = 0; j < 4; j++) {
+                const unsigned bj = bal[it * 4 + j];
+                if (bj & (1u << lane)) s_list[base + __popc(bj & lt)] = (uint16_t)(e0 + j);
+                base += __popc(bj);
+            }
         }
     }
     __syncthreads();
