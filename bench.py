@@ -196,12 +196,17 @@ def main():
     # ---- inputs: `rotate` distinct batches resident in HBM (rotate * B * W*H bytes > 126 MB L2), rank-specific seeds
     host_batches = [make_pairs(P, seed0=1000 + 100 * rank + 10 * r) for r in range(min(args.rotate, 3))]
     pinned = [torch.from_numpy(hb_).pin_memory() for hb_ in host_batches]
+    # device-resident frames are pitched 2-D images (row pitch rounded up to 16 bytes, as cudaMallocPitch / GpuMat give):
+    # the library then reads them in place through TMA; a dense odd-pitch batch would first be repacked on the device
+    WP = (W + 15) & ~15
     dev_batches = []
     for r in range(args.rotate):
         t = pinned[r % len(pinned)].to(dev, non_blocking=True)
         if r >= len(pinned):
             t = torch.roll(t, shifts=11 * r, dims=2)
-        dev_batches.append(t.contiguous())
+        tp = torch.zeros((B, H, WP), dtype=torch.uint8, device=dev)
+        tp[:, :, :W] = t
+        dev_batches.append(tp)
     in_bytes = B * W * H
     d_kps = torch.empty((B, cap, 7), dtype=torch.float32, device=dev)
     d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
@@ -212,7 +217,7 @@ def main():
 
     def step_device(i):
         t = dev_batches[i % len(dev_batches)]
-        ex.process_stereo_batch_device(sp, t.data_ptr(), P, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+        ex.process_stereo_batch_device(sp, t.data_ptr(), P, W, H, WP, WP * H, d_kps.data_ptr(), d_desc.data_ptr(), cap,
                                        d_counts.data_ptr(), d_uR.data_ptr(), d_depth.data_ptr())
 
     def barrier():

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace hyorb {
 struct DevBuf {
@@ -66,7 +67,14 @@ struct hyorb_extractor {
     DevBuf d_plan, d_resize, d_lut;
     int Bcap = 0;
     DevBuf d_pyr, d_blur, d_cand, d_qcode, d_qnode, d_qleaf, d_sel, d_candCount, d_selCount, d_status;
-    DevBuf d_in, d_kps, d_desc, d_counts;       // staging of the _host entry points
+    DevBuf d_in, d_raw, d_kps, d_desc, d_counts;   // staging of the _host entry points: d_raw = byte-for-byte mirror of a dense host batch,
+                                                   // d_in = level 0 in TMA-compatible layout (repacked on the device when the source is not)
+    // TMA: tensor maps of the pyramid levels (FAST tile boxes) live in device memory, level 0's travels as a kernel parameter
+    DevBuf d_tmaps;
+    CUtensorMap h_tmaps[HYORB_MAX_LEVELS];
+    CUtensorMap tm0;
+    struct { const void *base; int pitch; unsigned long long stride; int B, w, h; } tm0_key = {nullptr, 0, 0, 0, 0, 0};
+    int sm_count = 0;
     DevBuf d_rowtab, d_bestd, d_uR, d_depth;    // stereo stage of the ProcessStereoImage entry points
     long launches = 0;
     // per-stage CUDA-event timing (events on the launching stream; read back by hyorb_extractor_stage_times)
@@ -118,7 +126,25 @@ static int ex_ensure_workspace(hyorb_extractor *h, int B)
         HY_TRY(h->d_status.ensure(sizeof(int)));
         HY_CUDA(cudaMemsetAsync(h->d_status.p, 0, sizeof(int), h->stream));
     }
+    // tensor maps of pyramid levels 1.. over the whole workspace (image index = z coordinate); slot 0 is unused
+    HY_TRY(h->d_tmaps.ensure(sizeof(CUtensorMap) * HYORB_MAX_LEVELS));
+    memset(h->h_tmaps, 0, sizeof(h->h_tmaps));
+    for (int l = 1; l < P.nlevels; l++)
+        HY_TRY(tma_encode_u8_3d(&h->h_tmaps[l], h->d_pyr.as<uint8_t>() + P.lv[l].off, P.lv[l].w, P.lv[l].h, B, (size_t)P.lv[l].pitch,
+                                (size_t)P.pyrStride, FT_BOXW, FT_PH));
+    HY_CUDA(cudaMemcpyAsync(h->d_tmaps.p, h->h_tmaps, sizeof(h->h_tmaps), cudaMemcpyHostToDevice, h->stream));
+    HY_CUDA(cudaStreamSynchronize(h->stream));      // h_tmaps is pageable host memory
     h->Bcap = B;
+    return HYORB_OK;
+}
+
+// level-0 tensor map of the current call (cached while the caller keeps passing the same buffer)
+static int ex_ensure_tm0(hyorb_extractor *h, Level0 l0, int B, int w, int hgt)
+{
+    auto &k = h->tm0_key;
+    if (k.base == l0.base && k.pitch == l0.pitch && k.stride == l0.stride && k.B == B && k.w == w && k.h == hgt) return HYORB_OK;
+    HY_TRY(tma_encode_u8_3d(&h->tm0, l0.base, w, hgt, B, (size_t)l0.pitch, (size_t)l0.stride, FT_BOXW, FT_PH));
+    k.base = l0.base; k.pitch = l0.pitch; k.stride = l0.stride; k.B = B; k.w = w; k.h = hgt;
     return HYORB_OK;
 }
 
@@ -154,6 +180,18 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
     }
     const PlanDev &P = h->plan.dev;
     const PlanDev *dp = h->d_plan.as<PlanDev>();
+    // ---- level 0 must be TMA-addressable (16-byte aligned base, pitch, image stride): the staging copy of the host entry
+    // points is; a caller's device batch that is not gets repacked once (each lane repacks its own images)
+    Level0 src0 = l0;
+    bool repack = false;
+    if (!tma_compatible(l0.base, (size_t)l0.pitch, (size_t)l0.stride)) {
+        const int pitch = P.lv[0].pitch;
+        const size_t dstride = (size_t)pitch * hgt;
+        HY_TRY(h->d_in.ensure(dstride * B + 512));
+        l0 = Level0{h->d_in.as<uint8_t>(), pitch, (unsigned long long)dstride};
+        repack = true;
+    }
+    HY_TRY(ex_ensure_tm0(h, l0, B, w, hgt));
     // ---- cut the batch into lanes (whole pairs when the stereo stage follows)
     const int unit = sp ? 2 : 1, units = B / unit;
     const int want = io ? h->host_lanes : h->lanes;
@@ -179,15 +217,19 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
             switch (stage) {
             case 0:
                 if (k > 0) HY_CUDA(cudaStreamWaitEvent(st, h->ev_start, 0));
-                if (io) {       // upload this lane's images into the staging copy (same geometry as the host buffer when it is dense)
-                    uint8_t *dst = const_cast<uint8_t *>(l0k.base);
+                if (io) {       // upload this lane's images into the staging copy: one flat copy when it mirrors a dense host batch
+                    uint8_t *dst = const_cast<uint8_t *>(src0.base) + (size_t)i0 * src0.stride;
                     const uint8_t *src = io->images + (size_t)i0 * io->image_stride;
-                    if (l0.pitch == io->stride && l0.stride == io->image_stride)
+                    if (src0.pitch == io->stride && src0.stride == io->image_stride)
                         HY_CUDA(cudaMemcpyAsync(dst, src, (size_t)(Bk - 1) * io->image_stride + (size_t)io->stride * (hgt - 1) + w, cudaMemcpyHostToDevice, st));
                     else
                         for (int i = 0; i < Bk; i++)
-                            HY_CUDA(cudaMemcpy2DAsync(dst + (size_t)i * l0.stride, l0.pitch, src + (size_t)i * io->image_stride, io->stride, w, hgt,
+                            HY_CUDA(cudaMemcpy2DAsync(dst + (size_t)i * src0.stride, src0.pitch, src + (size_t)i * io->image_stride, io->stride, w, hgt,
                                                       cudaMemcpyHostToDevice, st));
+                }
+                if (repack) {
+                    HY_TRY(launch_repack(src0.base + (size_t)i0 * src0.stride, src0.pitch, (size_t)src0.stride, const_cast<uint8_t *>(l0k.base), l0.pitch,
+                                         (size_t)l0.stride, w, hgt, Bk, st, &h->launches));
                 }
                 HY_CUDA(cudaMemsetAsync(candCount, 0, sizeof(int) * HYORB_MAX_LEVELS * (size_t)Bk, st));
                 HY_TRY(ex_event(h, st, &evs[k]));
@@ -199,7 +241,7 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
                     HY_CUDA(cudaEventRecord(h->ev_pyr[k], st));
                     HY_CUDA(cudaStreamWaitEvent(h->side[k], h->ev_pyr[k], 0));
                 }
-                HY_TRY(launch_fast(P, dp, l0k, pyr, cand, candCount, status, Bk, st, &h->launches));
+                HY_TRY(launch_fast(P, dp, h->tm0, h->d_tmaps.as<CUtensorMap>(), i0, cand, candCount, status, Bk, h->sm_count, st, &h->launches));
                 HY_TRY(ex_event(h, st, &evs[k]));
                 break;
             case 2:
@@ -323,6 +365,7 @@ HYORB_API int hyorb_extractor_create(const hyorb_extractor_params *params, int d
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *v = getenv("HYORB_LANES")) h->lanes = atoi(v);
     if (const char *v = getenv("HYORB_HOST_LANES")) h->host_lanes = atoi(v);
     if (const char *v = getenv("HYORB_SIDE_BLUR")) h->side_blur = atoi(v) != 0;
@@ -345,8 +388,8 @@ HYORB_API int hyorb_extractor_destroy(hyorb_extractor *h)
     }
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     DevBuf *bufs[] = {&h->d_plan, &h->d_resize, &h->d_lut, &h->d_pyr, &h->d_blur, &h->d_cand, &h->d_qcode, &h->d_qnode, &h->d_qleaf, &h->d_sel,
-                      &h->d_candCount, &h->d_selCount, &h->d_status, &h->d_in, &h->d_kps, &h->d_desc, &h->d_counts,
-                      &h->d_rowtab, &h->d_bestd, &h->d_uR, &h->d_depth};
+                      &h->d_candCount, &h->d_selCount, &h->d_status, &h->d_in, &h->d_raw, &h->d_kps, &h->d_desc, &h->d_counts,
+                      &h->d_rowtab, &h->d_bestd, &h->d_uR, &h->d_depth, &h->d_tmaps};
     for (DevBuf *b : bufs) b->release();
     for (auto &set : h->ev_pending) for (cudaEvent_t e : set) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_free) cudaEventDestroy(e);
@@ -387,17 +430,23 @@ HYORB_API int hyorb_extractor_sync(hyorb_extractor *h)
     return ex_sync(h);
 }
 
-// staging copy of a host batch: dense host batches (any stride) are mirrored byte for byte with one flat copy per lane --
-// the kernels accept any row alignment; otherwise rows are repacked to the plan's aligned pitch
+// staging copy of a host batch.  Level 0 must end up TMA-addressable (16-byte aligned pitch and image stride).  A 2-D
+// copy of odd-pitch rows runs at a fraction of the PCIe rate, so dense host batches are mirrored with one flat copy per
+// lane and repacked by a kernel
 static int ex_stage_geometry(hyorb_extractor *h, int n_images, int width, int height, int stride, size_t image_stride, Level0 *l0)
 {
     const PlanDev &P = h->plan.dev;
     const bool dense = image_stride >= (size_t)stride * height && image_stride <= (size_t)stride * height + 4096;
-    int pitch; size_t dstride;
-    if (dense) { pitch = stride; dstride = image_stride; }
-    else { pitch = P.lv[0].pitch; dstride = ((size_t)pitch * height + 255) & ~(size_t)255; }
-    HY_TRY(h->d_in.ensure(dstride * n_images + 512));
-    *l0 = Level0{h->d_in.as<uint8_t>(), pitch, (unsigned long long)dstride};
+    if (dense) {        // mirror: one flat copy per lane; ex_run repacks on the device unless the layout is already TMA-compatible
+        DevBuf &buf = tma_compatible(nullptr, (size_t)stride, image_stride) ? h->d_in : h->d_raw;
+        HY_TRY(buf.ensure(image_stride * n_images + 512));
+        *l0 = Level0{buf.as<uint8_t>(), stride, (unsigned long long)image_stride};
+    } else {            // scattered host images: the copy engine repacks rows to the plan's aligned pitch
+        const int pitch = P.lv[0].pitch;
+        const size_t dstride = (size_t)pitch * height;
+        HY_TRY(h->d_in.ensure(dstride * n_images + 512));
+        *l0 = Level0{h->d_in.as<uint8_t>(), pitch, (unsigned long long)dstride};
+    }
     (void)width;
     return HYORB_OK;
 }

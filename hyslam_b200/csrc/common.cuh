@@ -1,5 +1,6 @@
 // common.cuh -- shared declarations of libhyorb (host + device).  B200 / sm_100a only.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -35,7 +36,8 @@ constexpr int LATTICE_MIN = 16;      // minBorderX = EDGE_THRESHOLD-3 (ORBExtrac
 constexpr int DET_MIN = 19;          // first pixel FAST can report: lattice min + 3
 
 // FAST tile geometry: a CTA scores a 64 x (16*FT_ITEMS) region (one 4-pixel group x one row per work item, FT_ITEMS items
-// per thread) and emits the interior (2 pixels less each way), so the 3x3 NMS never leaves the CTA.
+// per thread) and emits the interior (2 pixels less each way), so the 3x3 NMS never leaves the CTA.  The pixel region
+// (ring radius 3 around the score region) arrives as one TMA box whose left edge is rounded down to a multiple of 16.
 #ifndef HYORB_FT_ITEMS
 #define HYORB_FT_ITEMS 4
 #endif
@@ -43,6 +45,7 @@ constexpr int FT_ITEMS = HYORB_FT_ITEMS;
 constexpr int FT_SW = 64, FT_SH = 16 * FT_ITEMS;       // score region
 constexpr int FT_OW = FT_SW - 2, FT_OH = FT_SH - 2;   // emitted interior
 constexpr int FT_PW = FT_SW + 6, FT_PH = FT_SH + 6;   // pixel region (ring radius 3)
+constexpr int FT_BOXW = (FT_PW + 15 + 15) & ~15;       // TMA box width in bytes: pixel region + up to 15 bytes of left alignment slack
 constexpr int FT_THREADS = 256;
 
 constexpr int QT_DMAX = 13;          // quadtree path bits per axis
@@ -121,7 +124,10 @@ const char *last_error();
 
 // ---- kernel launchers (each returns a HYORB status; all enqueue on `st`) ----
 int launch_pyramid(const PlanDev &hp, const PlanDev *dp, Level0 l0, uint8_t *pyr, const ResizeTab *tabs, int B, cudaStream_t st, long *launches);
-int launch_fast(const PlanDev &hp, const PlanDev *dp, Level0 l0, const uint8_t *pyr, uint32_t *cand, int *candCount, int *status, int B, cudaStream_t st, long *launches);
+// img0 = index of the lane's first image inside the tensors tm0 (level 0) / tmaps[l] (pyramid levels >= 1) describe
+int launch_fast(const PlanDev &hp, const PlanDev *dp, const CUtensorMap &tm0, const CUtensorMap *tmaps, int img0, uint32_t *cand, int *candCount,
+                int *status, int B, int sm_count, cudaStream_t st, long *launches);
+int launch_repack(const uint8_t *src, int spitch, size_t sstride, uint8_t *dst, int dpitch, size_t dstride, int w, int h, int B, cudaStream_t st, long *launches);
 int launch_quadtree(const PlanDev &hp, const PlanDev *dp, const uint32_t *cand, const int *candCount, const uint32_t *lut,
                     uint32_t *qcode, uint16_t *qnode, uint2 *qleaf, uint32_t *sel, int *selCount, int *status, int B, cudaStream_t st, long *launches);
 int launch_blur(const PlanDev &hp, const PlanDev *dp, Level0 l0, const uint8_t *pyr, uint8_t *blur, int B, cudaStream_t st, long *launches);

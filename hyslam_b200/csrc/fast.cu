@@ -11,26 +11,32 @@
 // Output: unordered candidate list per (image, level), packed lattice x | y<<12 | response<<24; the reference's
 // generation order is recovered downstream from cand_order_key().
 //
-// Mapping: one CTA per 62x30 output tile; pixels staged once in shared memory (coalesced 32-bit loads); the
-// corner test runs 4 pixels per thread on packed bytes (SWAR compares, LOP3 arc logic); scores are then computed
-// only for the compacted corner list with 3-input integer min/max (VIMNMX3).
+// Mapping: persistent CTAs (a few per SM) walk the list of 62x62 output tiles of the whole batch.  The 70x70 pixel
+// region of a tile arrives in shared memory as ONE TMA box (cp.async.bulk.tensor; the box starts at the region's left
+// edge rounded down to 16 bytes, as the TMA requires, and the hardware zero-fills past the image edge) into a double
+// buffer: the box of the CTA's next tile is in flight while the current one is processed, so no thread spends
+// instructions or scoreboard stalls on staging.  The corner test runs 4 pixels per thread on packed bytes (SWAR
+// compares, LOP3 arc logic), instantiated for the four byte alignments the region can have inside the box; scores are
+// then computed only for the compacted corner list with 3-input integer min/max (VIMNMX3); cell-local NMS and a
+// CTA-aggregated emit follow.
+#include <algorithm>
+#include <atomic>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace hyorb {
 
-__device__ __forceinline__ uint32_t gt_msb(uint32_t a, uint32_t b)   // per byte: bit 7 = (a > b), unsigned
-{
-    const uint32_t s = (a & 0x7f7f7f7fu) + (~b & 0x7f7f7f7fu);
-    return (a & ~b) | (~(a ^ b) & s);
-}
-
+// 4 bytes starting at byte O (0..11) of w0:w1:w2:w3
 template <int O>
-__device__ __forceinline__ uint32_t pick(uint32_t w0, uint32_t w1, uint32_t w2)   // 4 bytes starting at byte O of w0:w1:w2
+__device__ __forceinline__ uint32_t pick(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
 {
     if (O == 0) return w0;
     if (O < 4) return __funnelshift_r(w0, w1, 8 * O);
     if (O == 4) return w1;
-    return __funnelshift_r(w1, w2, 8 * (O - 4));
+    if (O < 8) return __funnelshift_r(w1, w2, 8 * (O & 3));
+    if (O == 8) return w2;
+    return __funnelshift_r(w2, w3, 8 * (O & 3));
 }
 
 // Bresenham circle of radius 3, OpenCV's order (features2d/fast_score.cpp makeOffsets); byte offset inside the staged tile
@@ -38,90 +44,80 @@ __device__ __forceinline__ constexpr int ring_off(int k)
 {
     constexpr int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
     constexpr int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-    return dy[k] * 192 + dx[k];
+    return dy[k] * FT_BOXW + dx[k];
 }
 
 constexpr int EMIT_CAP = 512 * FT_ITEMS;     // NMS survivors of one tile: < (FT_OW/2+1)*(FT_OH/2+1), doubled for cell edges
-constexpr int RW = 48;            // shared-memory row stride in words: == 16 (mod 32), so the two rows a warp touches per
-                                  // load (16 groups x 2 rows) fall into disjoint banks
-constexpr int LW = 18;            // words actually loaded per row (70 pixels + 2)
-constexpr int PITCHB = RW * 4;    // row stride in bytes
+constexpr int RW = FT_BOXW / 4;   // shared-memory row stride in words = the TMA box width (dense box, no padding)
+constexpr int PITCHB = FT_BOXW;   // row stride in bytes
+constexpr int FT_BUF_BYTES = (FT_BOXW * FT_PH + 16 + 127) & ~127;   // one pixel buffer (+ one word of read slack), 128-byte aligned for TMA
 
-__global__ void __launch_bounds__(FT_THREADS)
-k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ pyr,
-       uint32_t *__restrict__ cand, int *__restrict__ candCount, int *__restrict__ status)
+struct FastTile { int b, l, sx0, sy0; };      // image, level, score-region origin
+
+// tile id -> image, level, score-region origin
+__device__ __forceinline__ FastTile fast_tile(const PlanDev *__restrict__ plan, int T)
 {
-    __shared__ uint32_t s_pix[FT_PH * RW];
-    __shared__ __align__(4) uint8_t s_score[FT_SH * FT_SW];
-    __shared__ uint16_t s_list[FT_SH * FT_SW];
-    __shared__ uint32_t s_emit[EMIT_CAP];
-    __shared__ uint8_t s_cf[FT_SW], s_rf[FT_SH];
-    __shared__ int s_n, s_ne, s_base;
-
-    const int tid = threadIdx.x;
-    const int b = blockIdx.y;
-    // which level does this tile belong to
+    FastTile t;
+    t.b = T / plan->tilesPerImage;
+    const int ti = T - t.b * plan->tilesPerImage;
     int l = 0;
     const int nl = plan->nlevels;
-    while (l + 1 < nl && (int)blockIdx.x >= plan->lv[l + 1].tileBase) l++;
+    while (l + 1 < nl && ti >= plan->lv[l + 1].tileBase) l++;
     const LevelDev &L = plan->lv[l];
-    const int t = blockIdx.x - L.tileBase;
-    const int tX = t % L.tilesX, tY = t / L.tilesX;
-    const int tx0 = DET_MIN + tX * FT_OW, ty0 = DET_MIN + tY * FT_OH;   // first emitted pixel
-    const int sx0 = tx0 - 1, sy0 = ty0 - 1;                             // score region origin
-    const int gx0 = sx0 - 3, gy0 = sy0 - 3;                             // pixel region origin
-    const int w = L.w, h = L.h;
-    const uint8_t *img; int pitch;
-    if (l == 0) { img = l0.base + (size_t)b * l0.stride; pitch = l0.pitch; }
-    else { img = pyr + (size_t)b * plan->pyrStride + L.off; pitch = L.pitch; }
+    const int k = ti - L.tileBase;
+    const int tY = k / L.tilesX, tX = k - tY * L.tilesX;
+    t.l = l;
+    t.sx0 = DET_MIN + tX * FT_OW - 1;     // score region origin = first emitted pixel - 1
+    t.sy0 = DET_MIN + tY * FT_OH - 1;
+    return t;
+}
 
-    if (tid == 0) { s_n = 0; s_ne = 0; }
-    // ---- stage pixels: FT_PH rows x 18 words; warp `wy` takes rows wy, wy+8, ...; lanes 0..17 one word each: aligned
-    // 32-bit global loads re-aligned with a funnel shift, all loads of a thread issued before the first store
-    {
-        const int lane = tid & 31, wy = tid >> 5;
-        constexpr int NR = (FT_PH + 7) / 8;
-        uint32_t v[NR];
-        const int x = gx0 + 4 * lane;
+// FAST-9/16 corner flags (bit 7 of each byte) of the 4 pixels of one work item.  `row` points at the word that holds the
+// item's leftmost ring column (centre - 3) on the centre row; S = that column's byte position inside the word.
+template <int S>
+__device__ __forceinline__ uint32_t corner_flags(const uint32_t *__restrict__ row)
+{
+    uint32_t a0, a1, a2, a3 = 0;
+#define LOADROW(dy) { a0 = row[(dy) * RW]; a1 = row[(dy) * RW + 1]; a2 = row[(dy) * RW + 2]; if (S + 6 > 8) a3 = row[(dy) * RW + 3]; }
+    LOADROW(0)
+    const uint32_t c = pick<S + 3>(a0, a1, a2, a3);
+    const uint32_t hi = __vaddus4(c, 0x01010101u * FAST_T), lo = __vsubus4(c, 0x01010101u * FAST_T);
+    uint32_t B[16], D[16];
+    // per byte, bit 7 of ((a & ~b) | (~(a ^ b) & s)) is (a > b) when s = (a & 0x7f) + (~b & 0x7f); the two sums that involve
+    // the ring pixel share its low 7 bits: bright s = r7 + Kb, dark s = Kd - r7 (no carry or borrow crosses a byte)
+    const uint32_t Kb = ~hi & 0x7f7f7f7fu, Kd = (lo & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+#define RING(k, O) { const uint32_t rv = pick<S + O>(a0, a1, a2, a3); const uint32_t r7 = rv & 0x7f7f7f7fu; const uint32_t sb = r7 + Kb, sd = Kd - r7; \
+                     B[k] = (rv & ~hi) | (~(rv ^ hi) & sb); D[k] = (lo & ~rv) | (~(lo ^ rv) & sd); }
+    RING(12, 0) RING(4, 6)              // dy = 0 : dx = -3, +3
+    LOADROW(1) RING(13, 0) RING(3, 6)
+    LOADROW(2) RING(14, 1) RING(2, 5)
+    LOADROW(3) RING(15, 2) RING(0, 3) RING(1, 4)       // dy = +3 : dx = -1, 0, +1
+    LOADROW(-1) RING(11, 0) RING(5, 6)
+    LOADROW(-2) RING(10, 1) RING(6, 5)
+    LOADROW(-3) RING(9, 2) RING(8, 3) RING(7, 4)
+#undef RING
+#undef LOADROW
+    // 9 contiguous: a3[k] = m[k]&m[k+1]&m[k+2]; a9[k] = a3[k]&a3[k+3]&a3[k+6]
+    uint32_t t3[16], t9[16];
 #pragma unroll
-        for (int k = 0; k < NR; k++) {
-            const int rr = wy + 8 * k, y = gy0 + rr;
-            v[k] = 0;
-            if (lane < LW && rr < FT_PH && y < h && x < w) {
-                const uint8_t *p = img + (size_t)y * pitch;
-                const unsigned mis = (unsigned)((uintptr_t)(p + x) & 3);
-                const int xa = x - (int)mis;                           // aligned-down start; gx0 >= 15 keeps xa >= 0
-                if (xa + 7 < w) {
-                    const uint32_t *q = (const uint32_t *)(p + xa);
-                    v[k] = __funnelshift_r(__ldg(q), __ldg(q + 1), mis * 8);
-                } else {
+    for (int k = 0; k < 16; k++) t3[k] = B[k] & B[(k + 1) & 15] & B[(k + 2) & 15];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) if (x + j < w) v[k] |= (uint32_t)p[x + j] << (8 * j);
-                }
-            }
-        }
+    for (int k = 0; k < 16; k++) t9[k] = t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
+    uint32_t ob = (t9[0] | t9[1] | t9[2]) | (t9[3] | t9[4] | t9[5]) | (t9[6] | t9[7] | t9[8]);
+    ob |= (t9[9] | t9[10] | t9[11]) | (t9[12] | t9[13] | t9[14]) | t9[15];
 #pragma unroll
-        for (int k = 0; k < NR; k++) {
-            const int rr = wy + 8 * k;
-            if (lane < LW && rr < FT_PH) s_pix[rr * RW + lane] = v[k];
-        }
-    }
-    for (int i = tid; i < FT_SH * FT_SW / 4; i += FT_THREADS) ((uint32_t *)s_score)[i] = 0;
-    if (tid < FT_SW) {
-        const int m = (sx0 + tid - DET_MIN) % L.wCell;      // sx0+tid >= 18; the halo column left of x=19 is never valid
-        s_cf[tid] = (uint8_t)((m == 0 ? 1 : 0) | (m == L.wCell - 1 ? 2 : 0));
-    } else if (tid >= 64 && tid < 64 + FT_SH) {      // FT_SH <= 128
-        const int r = tid - 64;
-        const int m = (sy0 + r - DET_MIN) % L.hCell;
-        s_rf[r] = (uint8_t)((m == 0 ? 1 : 0) | (m == L.hCell - 1 ? 2 : 0));
-    }
-    __syncthreads();
+    for (int k = 0; k < 16; k++) t3[k] = D[k] & D[(k + 1) & 15] & D[(k + 2) & 15];
+#pragma unroll
+    for (int k = 0; k < 16; k++) t9[k] = t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
+    uint32_t od = (t9[0] | t9[1] | t9[2]) | (t9[3] | t9[4] | t9[5]) | (t9[6] | t9[7] | t9[8]);
+    od |= (t9[9] | t9[10] | t9[11]) | (t9[12] | t9[13] | t9[14]) | t9[15];
+    return ob | od;
+}
 
-    const int xEnd = L.maxBX - 3, yEnd = L.maxBY - 3;     // detect range [19, xEnd) x [19, yEnd)
-    // ---- corner test, 4 pixels per item
-    uint32_t nflag[FT_ITEMS];
-#pragma unroll
-    for (int it = 0; it < FT_ITEMS; it++) nflag[it] = 0u;
+// corner test of a thread's FT_ITEMS work items; pix = word that holds pixel-region column 0 of row 0
+template <int S>
+__device__ __forceinline__ void corner_test(const uint32_t *__restrict__ pix, int tid, int sx0, int sy0, int xEnd, int yEnd, uint32_t (&nflag)[FT_ITEMS])
+{
 #pragma unroll 1
     for (int it = 0; it < FT_ITEMS; it++) {
         const int id = tid + it * FT_THREADS;
@@ -134,79 +130,110 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
             if (sx >= DET_MIN && sx < xEnd) valid |= 0x80u << (8 * j);
         }
         if (sy < DET_MIN || sy >= yEnd) valid = 0;
-        if (valid == 0) continue;       // nflag[it] stays 0
-        const uint32_t *row = s_pix + (r + 3) * RW + g;
-        uint32_t a0, a1, a2;
-        a0 = row[0]; a1 = row[1]; a2 = row[2];
-        const uint32_t c = pick<3>(a0, a1, a2);
-        const uint32_t hi = __vaddus4(c, 0x01010101u * FAST_T), lo = __vsubus4(c, 0x01010101u * FAST_T);
-        uint32_t B[16], D[16];
-        // per byte, bit 7 of ((a & ~b) | (~(a ^ b) & s)) is (a > b) when s = (a & 0x7f) + (~b & 0x7f); the two sums that involve
-        // the ring pixel share its low 7 bits: bright s = r7 + Kb, dark s = Kd - r7 (no carry or borrow crosses a byte)
-        const uint32_t Kb = ~hi & 0x7f7f7f7fu, Kd = (lo & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-#define RING(k, O) { const uint32_t rv = pick<O>(a0, a1, a2); const uint32_t r7 = rv & 0x7f7f7f7fu; const uint32_t sb = r7 + Kb, sd = Kd - r7; \
-                     B[k] = (rv & ~hi) | (~(rv ^ hi) & sb); D[k] = (lo & ~rv) | (~(lo ^ rv) & sd); }
-        RING(12, 0) RING(4, 6)                                           // dy = 0 : dx = -3, +3
-        a0 = row[RW]; a1 = row[RW + 1]; a2 = row[RW + 2];                // dy = +1
-        RING(13, 0) RING(3, 6)
-        a0 = row[2 * RW]; a1 = row[2 * RW + 1]; a2 = row[2 * RW + 2];    // dy = +2
-        RING(14, 1) RING(2, 5)
-        a0 = row[3 * RW]; a1 = row[3 * RW + 1];                          // dy = +3 : dx = -1, 0, +1
-        RING(15, 2) RING(0, 3) RING(1, 4)
-        a0 = row[-RW]; a1 = row[-RW + 1]; a2 = row[-RW + 2];             // dy = -1
-        RING(11, 0) RING(5, 6)
-        a0 = row[-2 * RW]; a1 = row[-2 * RW + 1]; a2 = row[-2 * RW + 2]; // dy = -2
-        RING(10, 1) RING(6, 5)
-        a0 = row[-3 * RW]; a1 = row[-3 * RW + 1];                        // dy = -3
-        RING(9, 2) RING(8, 3) RING(7, 4)
-#undef RING
-        // 9 contiguous: a3[k] = m[k]&m[k+1]&m[k+2]; a9[k] = a3[k]&a3[k+3]&a3[k+6]
-        uint32_t any;
-        {
-            uint32_t t3[16], t9[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) t3[k] = B[k] & B[(k + 1) & 15] & B[(k + 2) & 15];
-#pragma unroll
-            for (int k = 0; k < 16; k++) t9[k] = t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
-            uint32_t ob = (t9[0] | t9[1] | t9[2]) | (t9[3] | t9[4] | t9[5]) | (t9[6] | t9[7] | t9[8]);
-            ob |= (t9[9] | t9[10] | t9[11]) | (t9[12] | t9[13] | t9[14]) | t9[15];
-#pragma unroll
-            for (int k = 0; k < 16; k++) t3[k] = D[k] & D[(k + 1) & 15] & D[(k + 2) & 15];
-#pragma unroll
-            for (int k = 0; k < 16; k++) t9[k] = t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
-            uint32_t od = (t9[0] | t9[1] | t9[2]) | (t9[3] | t9[4] | t9[5]) | (t9[6] | t9[7] | t9[8]);
-            od |= (t9[9] | t9[10] | t9[11]) | (t9[12] | t9[13] | t9[14]) | t9[15];
-            any = ob | od;
-        }
-        any &= valid;
-        nflag[it] = any;
+        uint32_t f = 0;
+        if (valid) f = corner_flags<S>(pix + (r + 3) * RW + g) & valid;
+        nflag[it] = f;
     }
-    // ---- compact the corner flags into the CTA list: one ballot per (item, pixel) slot gives every lane its offset inside
-    // the warp's contiguous chunk; one shared-memory atomic per warp reserves the chunk
+}
+
+__global__ void __launch_bounds__(FT_THREADS)
+k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0, const CUtensorMap *__restrict__ tmaps, int img0, int nTiles,
+       uint32_t *__restrict__ cand, int *__restrict__ candCount, int *__restrict__ status)
+{
+    __shared__ __align__(128) uint8_t s_pixbuf[2][FT_BUF_BYTES];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(4) uint8_t s_score[FT_SH * FT_SW];
+    __shared__ uint16_t s_list[FT_SH * FT_SW];
+    __shared__ uint32_t s_emit[EMIT_CAP];
+    __shared__ uint8_t s_cf[FT_SW], s_rf[FT_SH];
+    __shared__ int s_n, s_ne, s_base;
+
+    const int tid = threadIdx.x;
+    // pixel box of tile T -> buffer `buf`; issued by one thread, completion lands on s_bar[buf]
+    auto issue = [&](int T, int buf) {
+        const FastTile t = fast_tile(plan, T);
+        mbar_arrive_expect_tx(&s_bar[buf], FT_BOXW * FT_PH);
+        tma_load_3d(s_pixbuf[buf], t.l == 0 ? &tm0 : &tmaps[t.l], &s_bar[buf], (t.sx0 - 3) & ~15, t.sy0 - 3, img0 + t.b);
+    };
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        fence_proxy_async();
+        if ((int)blockIdx.x < nTiles) issue(blockIdx.x, 0);
+    }
+    __syncthreads();
+
+    int it = 0;
+    for (int T = blockIdx.x; T < nTiles; T += gridDim.x, it++) {
+    const int buf = it & 1;
+    // the other buffer was last read before the barrier that ended the previous iteration: refill it now
+    if (tid == 0 && T + (int)gridDim.x < nTiles) { fence_proxy_async(); issue(T + gridDim.x, buf ^ 1); }
+    const FastTile tile = fast_tile(plan, T);
+    const int l = tile.l, b = tile.b;
+    const LevelDev &L = plan->lv[l];
+    const int sx0 = tile.sx0, sy0 = tile.sy0;
+    const int off = (sx0 - 3) & 15;                         // byte position of pixel-region column 0 inside the box
+    const uint8_t *pix8 = s_pixbuf[buf] + off;              // pixel region, row pitch PITCHB
+
+    if (tid == 0) { s_n = 0; s_ne = 0; }
+    for (int i = tid; i < FT_SH * FT_SW / 4; i += FT_THREADS) ((uint32_t *)s_score)[i] = 0;
+    if (tid < FT_SW) {
+        const int m = (sx0 + tid - DET_MIN) % L.wCell;      // sx0+tid >= 18; the halo column left of x=19 is never valid
+        s_cf[tid] = (uint8_t)((m == 0 ? 1 : 0) | (m == L.wCell - 1 ? 2 : 0));
+    } else if (tid >= 64 && tid < 64 + FT_SH) {      // FT_SH <= 128
+        const int r = tid - 64;
+        const int m = (sy0 + r - DET_MIN) % L.hCell;
+        s_rf[r] = (uint8_t)((m == 0 ? 1 : 0) | (m == L.hCell - 1 ? 2 : 0));
+    }
+    mbar_wait(&s_bar[buf], (it >> 1) & 1);      // the pixel box has landed
+    __syncthreads();
+
+    const int xEnd = L.maxBX - 3, yEnd = L.maxBY - 3;     // detect range [19, xEnd) x [19, yEnd)
+    // ---- corner test, 4 pixels per item; the byte alignment of the region inside the box is CTA-uniform
+    uint32_t nflag[FT_ITEMS];
+    {
+        const uint32_t *pixw = (const uint32_t *)s_pixbuf[buf] + (off >> 2);
+        switch (off & 3) {
+        case 0: corner_test<0>(pixw, tid, sx0, sy0, xEnd, yEnd, nflag); break;
+        case 1: corner_test<1>(pixw, tid, sx0, sy0, xEnd, yEnd, nflag); break;
+        case 2: corner_test<2>(pixw, tid, sx0, sy0, xEnd, yEnd, nflag); break;
+        default: corner_test<3>(pixw, tid, sx0, sy0, xEnd, yEnd, nflag); break;
+        }
+    }
+    // ---- compact the corner flags into the CTA list.  A lane's FT_ITEMS corner counts (<= 4 each) ride in one register,
+    // one byte per item: a single packed warp scan (no byte overflows: a warp holds <= 128 corners per item) gives every
+    // lane its offsets for all items at once; one shared-memory atomic per warp reserves the chunk.
     {
         const int lane = tid & 31;
-        const unsigned lt = (1u << lane) - 1u;
-        unsigned bal[FT_ITEMS * 4];
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < FT_ITEMS; k++) cnt |= (uint32_t)__popc(nflag[k] & 0x80808080u) << (8 * k);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);      // per-item warp totals, one byte each
+        const uint32_t excl = inc - cnt;
         int total = 0;
+        int ibase[FT_ITEMS];
 #pragma unroll
-        for (int it = 0; it < FT_ITEMS; it++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                bal[it * 4 + j] = __ballot_sync(0xffffffffu, (nflag[it] >> (8 * j + 7)) & 1u);
-                total += __popc(bal[it * 4 + j]);
-            }
+        for (int k = 0; k < FT_ITEMS; k++) { ibase[k] = total + (int)((excl >> (8 * k)) & 0xFFu); total += (int)((tot >> (8 * k)) & 0xFFu); }
         int base = 0;
         if (lane == 0 && total) base = atomicAdd(&s_n, total);
         base = __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
-        for (int it = 0; it < FT_ITEMS; it++) {
-            const int id = tid + it * FT_THREADS;
-            const int e0 = (id >> 4) * FT_SW + 4 * (id & 15);
+        for (int k = 0; k < FT_ITEMS; k++) {
+            const uint32_t f = nflag[k];
+            if (f) {
+                const int id = tid + k * FT_THREADS;
+                const int e0 = (id >> 4) * FT_SW + 4 * (id & 15);
+                int pos = base + ibase[k];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const unsigned bj = bal[it * 4 + j];
-                if (bj & (1u << lane)) s_list[base + __popc(bj & lt)] = (uint16_t)(e0 + j);
-                base += __popc(bj);
+                for (int j = 0; j < 4; j++)
+                    if ((f >> (8 * j + 7)) & 1u) s_list[pos++] = (uint16_t)(e0 + j);
             }
         }
     }
@@ -214,7 +241,6 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
 
     // ---- scores of the compacted corners
     const int ncorner = s_n;
-    const uint8_t *pix8 = (const uint8_t *)s_pix;
     for (int i = tid; i < ncorner; i += FT_THREADS) {
         const int e = s_list[i];
         const int r = e / FT_SW, cidx = e - r * FT_SW;
@@ -284,28 +310,41 @@ k_fast(const PlanDev *__restrict__ plan, Level0 l0, const uint8_t *__restrict__ 
     }
     __syncthreads();
     int ne = s_ne;
-    if (ne == 0) return;
-    int *cnt = candCount + b * HYORB_MAX_LEVELS + l;
-    if (tid == 0) {
-        if (ne > EMIT_CAP) { atomicOr(status, ST_CAND_OVERFLOW); }
-        s_base = atomicAdd(cnt, min(ne, EMIT_CAP));
+    if (ne > 0) {       // CTA-uniform
+        int *cnt = candCount + b * HYORB_MAX_LEVELS + l;
+        if (tid == 0) {
+            if (ne > EMIT_CAP) { atomicOr(status, ST_CAND_OVERFLOW); }
+            s_base = atomicAdd(cnt, min(ne, EMIT_CAP));
+        }
+        __syncthreads();
+        ne = min(ne, EMIT_CAP);
+        const int base = s_base;
+        uint32_t *out = cand + (size_t)b * plan->candStride + L.candOff;
+        for (int i = tid; i < ne; i += FT_THREADS) {
+            if (base + i < L.candCap) out[base + i] = s_emit[i];
+            else atomicOr(status, ST_CAND_OVERFLOW);
+        }
     }
-    __syncthreads();
-    ne = min(ne, EMIT_CAP);
-    const int base = s_base;
-    uint32_t *out = cand + (size_t)b * plan->candStride + L.candOff;
-    for (int i = tid; i < ne; i += FT_THREADS) {
-        if (base + i < L.candCap) out[base + i] = s_emit[i];
-        else atomicOr(status, ST_CAND_OVERFLOW);
+    __syncthreads();      // every shared array (and the pixel buffer) is free for the next tile
     }
 }
 
-int launch_fast(const PlanDev &hp, const PlanDev *dp, Level0 l0, const uint8_t *pyr, uint32_t *cand, int *candCount, int *status,
-                int B, cudaStream_t st, long *launches)
+int launch_fast(const PlanDev &hp, const PlanDev *dp, const CUtensorMap &tm0, const CUtensorMap *tmaps, int img0, uint32_t *cand, int *candCount,
+                int *status, int B, int sm_count, cudaStream_t st, long *launches)
 {
     if (hp.tilesPerImage == 0) return HYORB_OK;
-    dim3 grd(hp.tilesPerImage, B);
-    k_fast<<<grd, FT_THREADS, 0, st>>>(dp, l0, pyr, cand, candCount, status);
+    static std::atomic<int> ctas_per_sm{0};          // a property of the compiled kernel, identical on every sm_100a device
+    int per = ctas_per_sm.load(std::memory_order_relaxed);
+    if (!per) {
+        HY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_fast, FT_THREADS, 0));
+        if (per < 1) per = 1;
+        ctas_per_sm.store(per, std::memory_order_relaxed);
+    }
+    const int sms = sm_count > 0 ? sm_count : 148;
+    const long long nTiles = (long long)hp.tilesPerImage * B;
+    if (nTiles > 0x7fffffffLL) { set_error("too many FAST tiles in one batch"); return HYORB_EUNSUPPORTED; }
+    const int grid = (int)std::min<long long>(nTiles, (long long)sms * per);
+    k_fast<<<grid, FT_THREADS, 0, st>>>(dp, tm0, tmaps, img0, (int)nTiles, cand, candCount, status);
     ++*launches;
     HY_CUDA(cudaGetLastError());
     return HYORB_OK;

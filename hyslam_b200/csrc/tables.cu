@@ -134,6 +134,7 @@ int build_plan(const hyorb_extractor_params &p, int width, int height, HostPlan 
         const int detW = (L.maxBX - 3) - DET_MIN, detH = (L.maxBY - 3) - DET_MIN;
         L.tilesX = detW > 0 ? (detW + FT_OW - 1) / FT_OW : 0;
         L.tilesY = detH > 0 ? (detH + FT_OH - 1) / FT_OH : 0;
+        if (L.tilesX == 0 || L.tilesY == 0) L.tilesX = L.tilesY = 0;
         L.tileBase = tileBase; tileBase += L.tilesX * L.tilesY;
         L.quota = quota[l];
         // DistributeOctTree roots (:183-185); minX..maxX = lattice bounds
