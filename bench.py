@@ -159,8 +159,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=32, help="stereo pairs per step (per GPU)")
-    ap.add_argument("--rotate", type=int, default=10, help="distinct device-resident batches cycled so inputs exceed L2")
+    ap.add_argument("--pairs", type=int, default=128, help="stereo pairs per step (per GPU)")
+    ap.add_argument("--rotate", type=int, default=4, help="distinct device-resident batches cycled so inputs exceed L2")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -57,7 +57,7 @@ struct hyorb_extractor {
     static constexpr int MAX_LANES = 8;
     int lanes = 2;           // device-pointer entry points
     int host_lanes = 4;      // host-buffer entry points: more, smaller lanes so the PCIe copies pipeline against the kernels
-    bool side_blur = false;   // measured: no gain once lanes overlap whole pipelines (HYORB_SIDE_BLUR=1 to enable)
+    int side_blur = 2;        // 1: blur on a side stream next to FAST + quadtree; 2: next to the quadtree only (HYORB_SIDE_BLUR)
     cudaStream_t lane_stream[MAX_LANES] = {}, side[MAX_LANES] = {};
     cudaEvent_t ev_start = nullptr, ev_pyr[MAX_LANES] = {}, ev_blur[MAX_LANES] = {}, ev_done[MAX_LANES] = {};
     float scale[HYORB_MAX_LEVELS], inv[HYORB_MAX_LEVELS], sigma2[HYORB_MAX_LEVELS], inv_sigma2[HYORB_MAX_LEVELS];
@@ -237,11 +237,15 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
                 HY_TRY(ex_event(h, st, &evs[k]));
                 break;
             case 1:
-                if (h->side_blur) {
+                if (h->side_blur == 1) {
                     HY_CUDA(cudaEventRecord(h->ev_pyr[k], st));
                     HY_CUDA(cudaStreamWaitEvent(h->side[k], h->ev_pyr[k], 0));
                 }
                 HY_TRY(launch_fast(P, dp, h->tm0, h->d_tmaps.as<CUtensorMap>(), i0, cand, candCount, status, Bk, h->sm_count, st, &h->launches));
+                if (h->side_blur == 2) {        // the latency-bound quadtree CTAs are dispatched first, the blur fills the rest of each SM
+                    HY_CUDA(cudaEventRecord(h->ev_pyr[k], st));
+                    HY_CUDA(cudaStreamWaitEvent(h->side[k], h->ev_pyr[k], 0));
+                }
                 HY_TRY(ex_event(h, st, &evs[k]));
                 break;
             case 2:
@@ -368,7 +372,7 @@ HYORB_API int hyorb_extractor_create(const hyorb_extractor_params *params, int d
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *v = getenv("HYORB_LANES")) h->lanes = atoi(v);
     if (const char *v = getenv("HYORB_HOST_LANES")) h->host_lanes = atoi(v);
-    if (const char *v = getenv("HYORB_SIDE_BLUR")) h->side_blur = atoi(v) != 0;
+    if (const char *v = getenv("HYORB_SIDE_BLUR")) h->side_blur = atoi(v);
     if (e != cudaSuccess) { set_error("CUDA init: %s", cudaGetErrorString(e)); delete h; return HYORB_ECUDA; }
     *out = h;
     return HYORB_OK;
