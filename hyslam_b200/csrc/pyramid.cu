@@ -3,41 +3,47 @@
 // (b*(h>>4))>>16 vertical combine, (+2)>>2).  The 19-px reflected border the reference adds is never read
 // downstream and is not materialised.
 //
-// HBM-bound streaming kernel; one launch per level covers the whole batch.  A thread owns 4 adjacent destination
-// columns and walks down RS_ROWS destination rows.  For each source row it needs, it loads three aligned 32-bit
-// words (the <= 9 source bytes under its 4 columns), funnel-shifts them to the first tap and forms each horizontal
-// interpolation with one PRMT (pick the two taps) + one DP2A (taps x Q11 coefficient pair); a source row's four
-// horizontal values are reused by the next destination row when the vertical taps overlap (most rows at 1.2x).
+// Streaming kernel; one launch per level covers the whole batch.  A thread owns 4 adjacent destination columns and
+// walks down RS_ROWS destination rows.  Source rows are 16-byte aligned (pyramid layout; level 0 is TMA-addressable by
+// construction, api.cu): for each source row it needs, a thread loads three aligned 32-bit words (the <= 9 source bytes
+// under its 4 columns), funnel-shifts them to the first tap and forms each horizontal interpolation with one PRMT (pick
+// the two taps) + one DP2A (taps x Q11 coefficient pair); a source row's four horizontal values are reused by the next
+// destination row when the vertical taps overlap (most rows at 1.2x).  The vertical combine (b*(h>>4))>>16 is one
+// IMAD.HI per tap against the coefficient pre-shifted by 16.
 #include "common.cuh"
 
 namespace hyorb {
 
 constexpr int RS_BX = 64, RS_BY = 4, RS_ROWS = 8;
 
-struct HRow { int h[4]; };
+struct HRow { uint32_t h[4]; };      // horizontal values, already >> 4
+struct RowW { uint32_t A, B; };      // bytes s0 .. s0+7 of a source row
 
-__device__ __forceinline__ HRow hrow(const uint8_t *__restrict__ row, int s0, int roww, bool wordsafe, const uint32_t (&sel)[4], const uint32_t (&c01)[4])
+__device__ __forceinline__ RowW load_roww(const uint8_t *__restrict__ row, int s0, int roww, int rowpitch, unsigned sh)
 {
-    // bytes s0 .. s0+5 of the row, as two registers A (s0..s0+3) and B (s0+4..s0+7)
-    uint32_t A, B;
-    if (wordsafe && s0 + 12 <= roww) {
-        const unsigned mis = (unsigned)((uintptr_t)(row + s0) & 3);
-        const uint32_t *p = (const uint32_t *)(row + s0 - mis);
-        const unsigned sh = mis * 8;
+    RowW r;
+    // words may run past the image width into the row padding: those bytes only ever meet a zero coefficient (the table
+    // clamps the last taps to src[w-1] with c1 = 0)
+    if ((s0 & ~3) + 12 <= rowpitch) {
+        const uint32_t *p = (const uint32_t *)(row + (s0 & ~3));
         const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-        A = __funnelshift_r(w0, w1, sh);
-        B = __funnelshift_r(w1, w2, sh);
+        r.A = __funnelshift_r(w0, w1, sh);
+        r.B = __funnelshift_r(w1, w2, sh);
     } else {
-        A = B = 0;
+        r.A = r.B = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (s0 + j < roww) A |= (uint32_t)row[s0 + j] << (8 * j);
-            if (s0 + 4 + j < roww) B |= (uint32_t)row[s0 + 4 + j] << (8 * j);
+            if (s0 + j < roww) r.A |= (uint32_t)row[s0 + j] << (8 * j);
+            if (s0 + 4 + j < roww) r.B |= (uint32_t)row[s0 + 4 + j] << (8 * j);
         }
     }
+    return r;
+}
+__device__ __forceinline__ HRow hrow(const RowW &w, const uint32_t (&sel)[4], const uint32_t (&c01)[4])
+{
     HRow r;
 #pragma unroll
-    for (int j = 0; j < 4; j++) r.h[j] = (int)__dp2a_lo(c01[j], __byte_perm(A, B, sel[j]), 0u);   // src[s0]*c0 + src[s0+1]*c1
+    for (int j = 0; j < 4; j++) r.h[j] = __dp2a_lo(c01[j], __byte_perm(w.A, w.B, sel[j]), 0u) >> 4;   // (src[s0]*c0 + src[s0+1]*c1) >> 4, non-negative
     return r;
 }
 
@@ -70,35 +76,53 @@ k_resize(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride
     for (int j = 0; j < 4; j++) {
         const ResizeTab t = tx[min(x4 + j, dw - 1)];
         if (j == 0) s0 = t.ofs;
-        const uint32_t dlt = (uint32_t)(t.ofs - s0);          // 0..4 for a downscale by <= 1.33; checked on the host
+        const uint32_t dlt = (uint32_t)(t.ofs - s0);          // 0..6 for a downscale by <= 2; checked on the host
         sel[j] = dlt | ((dlt + 1) << 4);                      // PRMT: byte0 = tap0, byte1 = tap1 (byte 2,3 = A[0], unused)
         c01[j] = (uint32_t)(uint16_t)t.c0 | ((uint32_t)(uint16_t)t.c1 << 16);
     }
-    // aligned-down word loads start at most 3 bytes before a row's first tap: inside the previous row / image, except
-    // for the very first bytes of an unaligned batch base
-    const bool base_aligned = ((uintptr_t)src & 3) == 0;
-    int haveRow = -1;          // source row whose horizontal values sit in hb
+    const unsigned shf = (unsigned)(s0 & 3) * 8;
+    const bool full = x4 + 3 < dw;
+    // software pipeline over destination rows: the source words of row y+1 are requested before row y is combined and stored
+    ResizeTab vy = ty[y0];
+    int sy0 = min(max(vy.ofs, 0), sh - 1), sy1 = min(max(vy.ofs + 1, 0), sh - 1);
     HRow ha, hb;
+    {
+        const RowW wa = load_roww(s + (size_t)sy0 * spitch, s0, sw, spitch, shf);
+        RowW wb = wa;
+        if (sy1 != sy0) wb = load_roww(s + (size_t)sy1 * spitch, s0, sw, spitch, shf);
+        ha = hrow(wa, sel, c01);
+        hb = sy1 != sy0 ? hrow(wb, sel, c01) : ha;
+    }
+    int haveRow = sy1;          // source row whose horizontal values sit in hb
     for (int y = y0; y < y1; y++) {
-        const ResizeTab vy = ty[y];
-        const int sy0 = min(max(vy.ofs, 0), sh - 1), sy1 = min(max(vy.ofs + 1, 0), sh - 1);
-        const bool wordsafe = base_aligned || s0 >= 3 || sy0 > 0 || blockIdx.z > 0;
-        if (sy0 == haveRow) ha = hb;
-        else ha = hrow(s + (size_t)sy0 * spitch, s0, sw, wordsafe, sel, c01);
-        if (sy1 == sy0) hb = ha;
-        else hb = hrow(s + (size_t)sy1 * spitch, s0, sw, wordsafe, sel, c01);
-        haveRow = sy1;
-        const int b0 = vy.c0, b1 = vy.c1;
+        const bool more = y + 1 < y1;
+        ResizeTab vn = vy;
+        int ny0 = sy0, ny1 = sy1;
+        RowW na, nb;
+        na.A = na.B = nb.A = nb.B = 0;
+        if (more) {
+            vn = ty[y + 1];
+            ny0 = min(max(vn.ofs, 0), sh - 1); ny1 = min(max(vn.ofs + 1, 0), sh - 1);
+            if (ny0 != haveRow) na = load_roww(s + (size_t)ny0 * spitch, s0, sw, spitch, shf);
+            if (ny1 != ny0) nb = load_roww(s + (size_t)ny1 * spitch, s0, sw, spitch, shf);
+        }
+        // ((b0 * h0) >> 16) + ((b1 * h1) >> 16): high halves of products with the coefficients pre-shifted by 16 (0 <= b <= 2048)
+        const uint32_t b0 = (uint32_t)vy.c0 << 16, b1 = (uint32_t)vy.c1 << 16;
         uint32_t out = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            int v = (((b0 * (ha.h[j] >> 4)) >> 16) + ((b1 * (hb.h[j] >> 4)) >> 16) + 2) >> 2;
-            v = min(max(v, 0), 255);
-            out |= (uint32_t)v << (8 * j);
+            const uint32_t v = (__umulhi(b0, ha.h[j]) + __umulhi(b1, hb.h[j]) + 2u) >> 2;     // <= 255: the coefficients sum to 2048 (+-1)
+            out |= v << (8 * j);
         }
         uint8_t *o = d + (size_t)y * dpitch;
-        if (x4 + 3 < dw) *(uint32_t *)o = out;     // pitch and level offsets are multiples of 16
+        if (full) *(uint32_t *)o = out;     // pitch and level offsets are multiples of 16
         else for (int j = 0; x4 + j < dw; j++) o[j] = (uint8_t)(out >> (8 * j));
+        if (more) {
+            const HRow nha = ny0 != haveRow ? hrow(na, sel, c01) : hb;
+            hb = ny1 != ny0 ? hrow(nb, sel, c01) : nha;
+            ha = nha;
+            haveRow = ny1; vy = vn; sy0 = ny0; sy1 = ny1;
+        }
     }
 }
 
