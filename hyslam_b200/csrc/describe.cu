@@ -15,13 +15,22 @@ __device__ const int8_t d_brief_pattern[1024] = {
 #include "../../include/hyorb_brief_pattern.inc"
 };
 // the same table as floats (x0, y0, x1, y1 per test), filled once per device by k_pattern_to_float so that a lane fetches
-// its 8 tests with 8 x 128-bit loads and no int->float conversions
+// its 8 tests with 8 x 128-bit loads and no int->float conversions.  Lane i owns descriptor byte i = tests 8i .. 8i+7; the
+// table is stored test-slot major ([slot t][lane i]) so that one warp-wide load reads 512 contiguous bytes (4 L1
+// wavefronts) instead of 32 different cache lines.
 __device__ float4 d_brief_pattern_f[256];
 __global__ void k_pattern_to_float()
 {
-    const int t = threadIdx.x;
-    d_brief_pattern_f[t] = make_float4((float)d_brief_pattern[4 * t], (float)d_brief_pattern[4 * t + 1], (float)d_brief_pattern[4 * t + 2],
-                                       (float)d_brief_pattern[4 * t + 3]);
+    const int i = threadIdx.x;                 // test index 8*lane + slot
+    const int lane = i >> 3, slot = i & 7;
+    d_brief_pattern_f[slot * 32 + lane] = make_float4((float)d_brief_pattern[4 * i], (float)d_brief_pattern[4 * i + 1], (float)d_brief_pattern[4 * i + 2],
+                                                      (float)d_brief_pattern[4 * i + 3]);
+}
+// cvRound for |v| < 2^22: adding 1.5 * 2^23 leaves round-half-even(v) in the low mantissa bits (one FADD + one IADD on the
+// full-rate pipes instead of an F2I on the quarter-rate one)
+__device__ __forceinline__ int cv_round_small(float v)
+{
+    return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000;
 }
 
 constexpr int DS_WARPS = 8;
@@ -140,16 +149,18 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
     // ---- rotated BRIEF (ORBFinder.cpp:89-129)
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     const float rad = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)rad), bb = (float)sin((double)rad);
+    double sn, cs;
+    sincos((double)rad, &sn, &cs);
+    const float a = (float)cs, bb = (float)sn;
     int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
-        const float4 pt = d_brief_pattern_f[lane * 8 + t];
+        const float4 pt = d_brief_pattern_f[t * 32 + lane];
         const float x0 = pt.x, y0 = pt.y, x1 = pt.z, y1 = pt.w;
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, bb), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bb)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bb), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, bb)));
+        const int r0 = cv_round_small(__fadd_rn(__fmul_rn(x0, bb), __fmul_rn(y0, a)));
+        const int c0 = cv_round_small(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bb)));
+        const int r1 = cv_round_small(__fadd_rn(__fmul_rn(x1, bb), __fmul_rn(y1, a)));
+        const int c1 = cv_round_small(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, bb)));
         const int t0 = center[r0 * PP + c0], t1 = center[r1 * PP + c1];
         val |= (t0 < t1) << t;
     }

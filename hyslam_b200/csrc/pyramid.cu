@@ -14,7 +14,10 @@
 
 namespace hyorb {
 
-constexpr int RS_BX = 64, RS_BY = 4, RS_ROWS = 8;
+#ifndef HYORB_RS_ROWS
+#define HYORB_RS_ROWS 8
+#endif
+constexpr int RS_BX = 64, RS_BY = 4, RS_ROWS = HYORB_RS_ROWS;
 
 struct HRow { uint32_t h[4]; };      // horizontal values, already >> 4
 struct RowW { uint32_t A, B; };      // bytes s0 .. s0+7 of a source row
@@ -82,30 +85,20 @@ k_resize(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride
     }
     const unsigned shf = (unsigned)(s0 & 3) * 8;
     const bool full = x4 + 3 < dw;
-    // software pipeline over destination rows: the source words of row y+1 are requested before row y is combined and stored
-    ResizeTab vy = ty[y0];
-    int sy0 = min(max(vy.ofs, 0), sh - 1), sy1 = min(max(vy.ofs + 1, 0), sh - 1);
+    int haveRow = -1;          // source row whose horizontal values sit in hb
     HRow ha, hb;
-    {
-        const RowW wa = load_roww(s + (size_t)sy0 * spitch, s0, sw, spitch, shf);
-        RowW wb = wa;
-        if (sy1 != sy0) wb = load_roww(s + (size_t)sy1 * spitch, s0, sw, spitch, shf);
-        ha = hrow(wa, sel, c01);
-        hb = sy1 != sy0 ? hrow(wb, sel, c01) : ha;
-    }
-    int haveRow = sy1;          // source row whose horizontal values sit in hb
+    hb.h[0] = hb.h[1] = hb.h[2] = hb.h[3] = 0;
     for (int y = y0; y < y1; y++) {
-        const bool more = y + 1 < y1;
-        ResizeTab vn = vy;
-        int ny0 = sy0, ny1 = sy1;
-        RowW na, nb;
-        na.A = na.B = nb.A = nb.B = 0;
-        if (more) {
-            vn = ty[y + 1];
-            ny0 = min(max(vn.ofs, 0), sh - 1); ny1 = min(max(vn.ofs + 1, 0), sh - 1);
-            if (ny0 != haveRow) na = load_roww(s + (size_t)ny0 * spitch, s0, sw, spitch, shf);
-            if (ny1 != ny0) nb = load_roww(s + (size_t)ny1 * spitch, s0, sw, spitch, shf);
-        }
+        const ResizeTab vy = ty[y];
+        const int sy0 = min(max(vy.ofs, 0), sh - 1), sy1 = min(max(vy.ofs + 1, 0), sh - 1);
+        // both source rows are requested before either is consumed
+        RowW wa, wb;
+        wa.A = wa.B = wb.A = wb.B = 0;
+        if (sy0 != haveRow) wa = load_roww(s + (size_t)sy0 * spitch, s0, sw, spitch, shf);
+        if (sy1 != sy0) wb = load_roww(s + (size_t)sy1 * spitch, s0, sw, spitch, shf);
+        ha = sy0 != haveRow ? hrow(wa, sel, c01) : hb;
+        hb = sy1 != sy0 ? hrow(wb, sel, c01) : ha;
+        haveRow = sy1;
         // ((b0 * h0) >> 16) + ((b1 * h1) >> 16): high halves of products with the coefficients pre-shifted by 16 (0 <= b <= 2048)
         const uint32_t b0 = (uint32_t)vy.c0 << 16, b1 = (uint32_t)vy.c1 << 16;
         uint32_t out = 0;
@@ -117,12 +110,6 @@ k_resize(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride
         uint8_t *o = d + (size_t)y * dpitch;
         if (full) *(uint32_t *)o = out;     // pitch and level offsets are multiples of 16
         else for (int j = 0; x4 + j < dw; j++) o[j] = (uint8_t)(out >> (8 * j));
-        if (more) {
-            const HRow nha = ny0 != haveRow ? hrow(na, sel, c01) : hb;
-            hb = ny1 != ny0 ? hrow(nb, sel, c01) : nha;
-            ha = nha;
-            haveRow = ny1; vy = vn; sy0 = ny0; sy1 = ny1;
-        }
     }
 }
 
