@@ -57,7 +57,7 @@ SYMBOLS = [
     "hyorb_match_bruteforce_device", "hyorb_grid_build_host", "hyorb_match_window_host",
     "hyorb_rotation_consistency_host", "hyorb_last_error", "hyorb_version", "hyorb_device_count",
     "hyorb_process_stereo_batch_host", "hyorb_process_stereo_batch_device", "hyorb_extractor_set_profiling",
-    "hyorb_extractor_stage_times",
+    "hyorb_extractor_stage_times", "hyorb_extractor_set_pipelining",
 ]
 N_STAGES = 6
 STAGE_NAMES = ("pyramid", "fast", "quadtree", "blur", "describe", "stereo")
@@ -103,6 +103,7 @@ def lib():
         L.hyorb_process_stereo_batch_device.argtypes = L.hyorb_process_stereo_batch_host.argtypes
         L.hyorb_extractor_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.hyorb_extractor_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hyorb_extractor_set_pipelining.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.hyorb_extractor_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hyorb_extractor_destroy.argtypes = [C.c_void_p]
         L.hyorb_extractor_sync.argtypes = [C.c_void_p]

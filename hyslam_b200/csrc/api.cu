@@ -545,6 +545,21 @@ HYORB_API int hyorb_extractor_set_profiling(hyorb_extractor *h, int enable)
     return HYORB_OK;
 }
 
+HYORB_API int hyorb_extractor_set_pipelining(hyorb_extractor *h, int device_lanes, int host_lanes, int side_blur)
+{
+    if (!h) { set_error("null handle"); return HYORB_EINVAL; }
+    if (device_lanes > hyorb_extractor::MAX_LANES || host_lanes > hyorb_extractor::MAX_LANES || device_lanes == 0 || host_lanes == 0 || side_blur > 2) {
+        set_error("pipelining: lanes must be 1..%d, side_blur 0..2", hyorb_extractor::MAX_LANES);
+        return HYORB_EINVAL;
+    }
+    HY_CUDA(cudaSetDevice(h->device));
+    HY_CUDA(cudaStreamSynchronize(h->stream));
+    if (device_lanes > 0) h->lanes = device_lanes;
+    if (host_lanes > 0) h->host_lanes = host_lanes;
+    if (side_blur >= 0) h->side_blur = side_blur;
+    return HYORB_OK;
+}
+
 HYORB_API int hyorb_extractor_stage_times(hyorb_extractor *h, double *ms, long *calls, int reset)
 {
     if (!h) { set_error("null handle"); return HYORB_EINVAL; }

@@ -136,7 +136,13 @@ __device__ __forceinline__ void corner_test(const uint32_t *__restrict__ pix, in
     }
 }
 
-__global__ void __launch_bounds__(FT_THREADS)
+#ifndef HYORB_FAST_STOP
+#define HYORB_FAST_STOP 0      // timing experiments only: 1..3 leave the tile loop after the test / compaction / scoring phase
+#endif
+#ifndef HYORB_FT_MINB
+#define HYORB_FT_MINB 4
+#endif
+__global__ void __launch_bounds__(FT_THREADS, HYORB_FT_MINB)
 k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0, const CUtensorMap *__restrict__ tmaps, int img0, int nTiles,
        uint32_t *__restrict__ cand, int *__restrict__ candCount, int *__restrict__ status)
 {
@@ -201,6 +207,12 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         default: corner_test<3>(pixw, tid, sx0, sy0, xEnd, yEnd, nflag); break;
         }
     }
+#if HYORB_FAST_STOP == 1
+    { uint32_t acc = 0;
+#pragma unroll
+      for (int k = 0; k < FT_ITEMS; k++) acc |= nflag[k];
+      if (acc == 0x12345678u) atomicOr(status, 128); __syncthreads(); continue; }
+#endif
     // ---- compact the corner flags into the CTA list.  A lane's FT_ITEMS corner counts (<= 4 each) ride in one register,
     // one byte per item: a single packed warp scan (no byte overflows: a warp holds <= 128 corners per item) gives every
     // lane its offsets for all items at once; one shared-memory atomic per warp reserves the chunk.
@@ -239,6 +251,9 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     }
     __syncthreads();
 
+#if HYORB_FAST_STOP == 2
+    __syncthreads(); continue;
+#endif
     // ---- scores of the compacted corners
     const int ncorner = s_n;
     for (int i = tid; i < ncorner; i += FT_THREADS) {
@@ -268,36 +283,29 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     }
     __syncthreads();
 
+#if HYORB_FAST_STOP == 3
+    __syncthreads(); continue;
+#endif
     // ---- cell-local 3x3 NMS over the interior, stage survivors
     for (int i0 = 0; i0 < ncorner; i0 += FT_THREADS) {      // warp-uniform trip count: the ballot below needs all lanes
         const int i = i0 + tid;
         bool kept = false;
         uint32_t packed = 0;
-        do {
-        if (i >= ncorner) break;
-        const int e = s_list[i];
+        // branch-free: the eight neighbour scores are fetched together (independent loads, every address stays inside
+        // s_score for an interior pixel) and neighbours that belong to another cell are replaced by 0
+        const int e = i < ncorner ? (int)s_list[i] : (FT_SW + 1);
         const int r = e / FT_SW, cidx = e - r * FT_SW;
-        if (r < 1 || r > FT_OH || cidx < 1 || cidx > FT_OW) break;      // halo: belongs to the neighbouring tile
-        const int s = s_score[e];
+        const bool inner = i < ncorner && r >= 1 && r <= FT_OH && cidx >= 1 && cidx <= FT_OW;      // else: halo, belongs to the neighbouring tile
+        const uint8_t *q = s_score + (inner ? e : FT_SW + 1);
+        const int s = q[0];
+        const int nl = q[-1], nr = q[1], nu = q[-FT_SW], nul = q[-FT_SW - 1], nur = q[-FT_SW + 1], nd = q[FT_SW], ndl = q[FT_SW - 1], ndr = q[FT_SW + 1];
         const int cf = s_cf[cidx], rf = s_rf[r];
         const bool L_ok = !(cf & 1), R_ok = !(cf & 2), U_ok = !(rf & 1), D_ok = !(rf & 2);
-        const uint8_t *q = s_score + e;
-        bool keep = true;
-        if (L_ok) keep = keep && s > q[-1];
-        if (R_ok) keep = keep && s > q[1];
-        if (U_ok) {
-            keep = keep && s > q[-FT_SW];
-            if (L_ok) keep = keep && s > q[-FT_SW - 1];
-            if (R_ok) keep = keep && s > q[-FT_SW + 1];
-        }
-        if (D_ok) {
-            keep = keep && s > q[FT_SW];
-            if (L_ok) keep = keep && s > q[FT_SW - 1];
-            if (R_ok) keep = keep && s > q[FT_SW + 1];
-        }
-        kept = keep;
+        const int m0 = __vimax3_s32(L_ok ? nl : 0, R_ok ? nr : 0, U_ok ? nu : 0);
+        const int m1 = __vimax3_s32(U_ok && L_ok ? nul : 0, U_ok && R_ok ? nur : 0, D_ok ? nd : 0);
+        const int m2 = __vimax3_s32(D_ok && L_ok ? ndl : 0, D_ok && R_ok ? ndr : 0, m0);
+        kept = inner && s > max(m1, m2);
         packed = pack_cand(sx0 + cidx - LATTICE_MIN, sy0 + r - LATTICE_MIN, s);
-        } while (0);
         const unsigned bal = __ballot_sync(0xffffffffu, kept);
         if (bal) {
             const int lane = tid & 31;
@@ -309,6 +317,10 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         }
     }
     __syncthreads();
+#if HYORB_FAST_STOP == 4
+    if (s_ne == 0x7fffffff) atomicOr(status, 128);
+    continue;
+#endif
     int ne = s_ne;
     if (ne > 0) {       // CTA-uniform
         int *cnt = candCount + b * HYORB_MAX_LEVELS + l;

@@ -122,6 +122,10 @@ class ORBExtractor:
     def set_profiling(self, on=True):
         F.check(F.lib().hyorb_extractor_set_profiling(self._h, int(on)))
 
+    def set_pipelining(self, device_lanes=-1, host_lanes=-1, side_blur=-1):
+        """Sub-batch lanes / side-stream blur of the batch entry points (-1 keeps a setting); lanes=1, side_blur=0 serialises the kernels."""
+        F.check(F.lib().hyorb_extractor_set_pipelining(self._h, int(device_lanes), int(host_lanes), int(side_blur)))
+
     def stage_times(self, reset=True):
         """{stage: accumulated ms} and the number of profiled calls since the last reset (synchronises)."""
         ms = (C.c_double * F.N_STAGES)()
