@@ -35,18 +35,18 @@ constexpr int FAST_T = 20;           // ORBFinder.h:92 + setter bug ORBFinder.cp
 constexpr int LATTICE_MIN = 16;      // minBorderX = EDGE_THRESHOLD-3 (ORBExtractor.cpp:417)
 constexpr int DET_MIN = 19;          // first pixel FAST can report: lattice min + 3
 
-// FAST tile geometry: a CTA scores a 64 x (16*FT_ITEMS) region (one 4-pixel group x one row per work item, FT_ITEMS items
-// per thread) and emits the interior (2 pixels less each way), so the 3x3 NMS never leaves the CTA.  The pixel region
-// (ring radius 3 around the score region) arrives as one TMA box whose left edge is rounded down to a multiple of 16.
-#ifndef HYORB_FT_ITEMS
-#define HYORB_FT_ITEMS 4
-#endif
-constexpr int FT_ITEMS = HYORB_FT_ITEMS;
-constexpr int FT_SW = 64, FT_SH = 16 * FT_ITEMS;       // score region
-constexpr int FT_OW = FT_SW - 2, FT_OH = FT_SH - 2;   // emitted interior
-constexpr int FT_PW = FT_SW + 6, FT_PH = FT_SH + 6;   // pixel region (ring radius 3)
-constexpr int FT_BOXW = (FT_PW + 15 + 15) & ~15;       // TMA box width in bytes: pixel region + up to 15 bytes of left alignment slack
-constexpr int FT_THREADS = 256;
+// FAST tile geometry (fast.cu).  A tile is a 96 x 64 pixel region = 3 bit-plane segments of 32 pixels x 64 rows; region
+// column c holds image column X0 + c, X0 = 15 + FT_OW * tX.  Scores exist for columns [3, 93) and rows [3, 61) of the region
+// (ring radius 3); the tile emits the interior columns [4, 92) and score rows [1, 57), so the 3x3 NMS never leaves the CTA
+// and consecutive tiles abut exactly.  The region arrives as one TMA box whose left edge is X0 rounded down to 16.
+constexpr int FT_NSEG = 3;                              // bit-plane segments per row
+constexpr int FT_SW = 32 * FT_NSEG;                     // score array pitch = region width
+constexpr int FT_PH = 64;                               // region rows
+constexpr int FT_SH = FT_PH - 6;                        // score rows
+constexpr int FT_C0 = 4;                                // first emitted region column
+constexpr int FT_OW = FT_SW - 8, FT_OH = FT_SH - 2;     // emitted interior: 88 x 56
+constexpr int FT_BOXW = FT_SW + 16;                     // TMA box width in bytes: region + up to 15 bytes of left alignment slack
+constexpr int FT_THREADS = 32 * FT_NSEG * (FT_PH / 32); // 192: one transposition unit (row, segment) and at most one test item per thread
 
 constexpr int QT_DMAX = 13;          // quadtree path bits per axis
 constexpr int QT_THREADS = 512;

@@ -11,33 +11,25 @@
 // Output: unordered candidate list per (image, level), packed lattice x | y<<12 | response<<24; the reference's
 // generation order is recovered downstream from cand_order_key().
 //
-// Mapping: persistent CTAs (a few per SM) walk the list of 62x62 output tiles of the whole batch.  The 70x70 pixel
+// Mapping: persistent CTAs (a few per SM) walk the list of 88x56 output tiles of the whole batch.  The 96x64 pixel
 // region of a tile arrives in shared memory as ONE TMA box (cp.async.bulk.tensor; the box starts at the region's left
 // edge rounded down to 16 bytes, as the TMA requires, and the hardware zero-fills past the image edge) into a double
 // buffer: the box of the CTA's next tile is in flight while the current one is processed, so no thread spends
-// instructions or scoreboard stalls on staging.  The corner test runs 4 pixels per thread on packed bytes (SWAR
-// compares, LOP3 arc logic), instantiated for the four byte alignments the region can have inside the box; scores are
-// then computed only for the compacted corner list with 3-input integer min/max (VIMNMX3); cell-local NMS and a
-// CTA-aggregated emit follow.
+// instructions or scoreboard stalls on staging.  Per tile:
+//   T. every thread transposes 32 pixels into 8 bit-plane words (fast_bitslice.cuh);
+//   A. every thread runs the bit-sliced segment test on 32 pixels (one 3-input logic op per bit and ring position,
+//      funnel shifts for the ring's x offsets, 9-of-16 arc logic on 32 pixels per op);
+//   B. corner bits are compacted into the CTA's list (warp scan + one shared-memory atomic per warp);
+//   C. scores are computed only for the listed corners with 3-input integer min/max (VIMNMX3);
+//   D. cell-local 3x3 NMS (branch-free) and a CTA-aggregated emit.
 #include <algorithm>
 #include <atomic>
 
 #include "common.cuh"
 #include "tma.cuh"
+#include "fast_bitslice.cuh"
 
 namespace hyorb {
-
-// 4 bytes starting at byte O (0..11) of w0:w1:w2:w3
-template <int O>
-__device__ __forceinline__ uint32_t pick(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
-{
-    if (O == 0) return w0;
-    if (O < 4) return __funnelshift_r(w0, w1, 8 * O);
-    if (O == 4) return w1;
-    if (O < 8) return __funnelshift_r(w1, w2, 8 * (O & 3));
-    if (O == 8) return w2;
-    return __funnelshift_r(w2, w3, 8 * (O & 3));
-}
 
 // Bresenham circle of radius 3, OpenCV's order (features2d/fast_score.cpp makeOffsets); byte offset inside the staged tile
 __device__ __forceinline__ constexpr int ring_off(int k)
@@ -47,14 +39,16 @@ __device__ __forceinline__ constexpr int ring_off(int k)
     return dy[k] * FT_BOXW + dx[k];
 }
 
-constexpr int EMIT_CAP = 512 * FT_ITEMS;     // NMS survivors of one tile: < (FT_OW/2+1)*(FT_OH/2+1), doubled for cell edges
-constexpr int RW = FT_BOXW / 4;   // shared-memory row stride in words = the TMA box width (dense box, no padding)
-constexpr int PITCHB = FT_BOXW;   // row stride in bytes
-constexpr int FT_BUF_BYTES = (FT_BOXW * FT_PH + 16 + 127) & ~127;   // one pixel buffer (+ one word of read slack), 128-byte aligned for TMA
+constexpr int EMIT_CAP = 2048;                 // NMS survivors of one tile: (FT_OW/2+1)*(FT_OH/2+1) = 1305 plus adjacent pairs across cell edges
+constexpr int PITCHB = FT_BOXW;                // box row stride in bytes
+constexpr int FT_BUF_BYTES = (FT_BOXW * FT_PH + 127) & ~127;   // one pixel buffer, 128-byte aligned for TMA
+constexpr int FT_PLP = 8 * (FT_NSEG + 2) + 4;  // plane row pitch in words: an all-zero segment either side, +4 so that the 128-bit
+                                               // loads of 8 consecutive rows hit disjoint banks
+static_assert(EMIT_CAP * 4 <= FT_PH * FT_PLP * 4, "the emit staging aliases the plane buffer");
 
-struct FastTile { int b, l, sx0, sy0; };      // image, level, score-region origin
+struct FastTile { int b, l, x0, sy0; };      // image, level, image column of region column 0, image row of score row 0
 
-// tile id -> image, level, score-region origin
+// tile id -> image, level, origin
 __device__ __forceinline__ FastTile fast_tile(const PlanDev *__restrict__ plan, int T)
 {
     FastTile t;
@@ -67,78 +61,19 @@ __device__ __forceinline__ FastTile fast_tile(const PlanDev *__restrict__ plan, 
     const int k = ti - L.tileBase;
     const int tY = k / L.tilesX, tX = k - tY * L.tilesX;
     t.l = l;
-    t.sx0 = DET_MIN + tX * FT_OW - 1;     // score region origin = first emitted pixel - 1
-    t.sy0 = DET_MIN + tY * FT_OH - 1;
+    t.x0 = DET_MIN - FT_C0 + tX * FT_OW;      // first emitted column (region column FT_C0) of tile 0 is x = 19
+    t.sy0 = DET_MIN - 1 + tY * FT_OH;         // first emitted row (score row 1) of tile 0 is y = 19
     return t;
 }
 
-// FAST-9/16 corner flags (bit 7 of each byte) of the 4 pixels of one work item.  `row` points at the word that holds the
-// item's leftmost ring column (centre - 3) on the centre row; S = that column's byte position inside the word.
-template <int S>
-__device__ __forceinline__ uint32_t corner_flags(const uint32_t *__restrict__ row)
+// bits [a, b) of a 32-bit word (any integers a, b)
+__device__ __forceinline__ uint32_t bit_range(int a, int b)
 {
-    uint32_t a0, a1, a2, a3 = 0;
-#define LOADROW(dy) { a0 = row[(dy) * RW]; a1 = row[(dy) * RW + 1]; a2 = row[(dy) * RW + 2]; if (S + 6 > 8) a3 = row[(dy) * RW + 3]; }
-    LOADROW(0)
-    const uint32_t c = pick<S + 3>(a0, a1, a2, a3);
-    const uint32_t hi = __vaddus4(c, 0x01010101u * FAST_T), lo = __vsubus4(c, 0x01010101u * FAST_T);
-    uint32_t B[16], D[16];
-    // per byte, bit 7 of ((a & ~b) | (~(a ^ b) & s)) is (a > b) when s = (a & 0x7f) + (~b & 0x7f); the two sums that involve
-    // the ring pixel share its low 7 bits: bright s = r7 + Kb, dark s = Kd - r7 (no carry or borrow crosses a byte)
-    const uint32_t Kb = ~hi & 0x7f7f7f7fu, Kd = (lo & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-#define RING(k, O) { const uint32_t rv = pick<S + O>(a0, a1, a2, a3); const uint32_t r7 = rv & 0x7f7f7f7fu; const uint32_t sb = r7 + Kb, sd = Kd - r7; \
-                     B[k] = (rv & ~hi) | (~(rv ^ hi) & sb); D[k] = (lo & ~rv) | (~(lo ^ rv) & sd); }
-    RING(12, 0) RING(4, 6)              // dy = 0 : dx = -3, +3
-    LOADROW(1) RING(13, 0) RING(3, 6)
-    LOADROW(2) RING(14, 1) RING(2, 5)
-    LOADROW(3) RING(15, 2) RING(0, 3) RING(1, 4)       // dy = +3 : dx = -1, 0, +1
-    LOADROW(-1) RING(11, 0) RING(5, 6)
-    LOADROW(-2) RING(10, 1) RING(6, 5)
-    LOADROW(-3) RING(9, 2) RING(8, 3) RING(7, 4)
-#undef RING
-#undef LOADROW
-    // 9 contiguous: a3[k] = m[k]&m[k+1]&m[k+2]; a9[k] = a3[k]&a3[k+3]&a3[k+6]
-    uint32_t t3[16], t9[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) t3[k] = B[k] & B[(k + 1) & 15] & B[(k + 2) & 15];
-#pragma unroll
-    for (int k = 0; k < 16; k++) t9[k] = t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
-    uint32_t ob = (t9[0] | t9[1] | t9[2]) | (t9[3] | t9[4] | t9[5]) | (t9[6] | t9[7] | t9[8]);
-    ob |= (t9[9] | t9[10] | t9[11]) | (t9[12] | t9[13] | t9[14]) | t9[15];
-#pragma unroll
-    for (int k = 0; k < 16; k++) t3[k] = D[k] & D[(k + 1) & 15] & D[(k + 2) & 15];
-#pragma unroll
-    for (int k = 0; k < 16; k++) t9[k] = t3[k] & t3[(k + 3) & 15] & t3[(k + 6) & 15];
-    uint32_t od = (t9[0] | t9[1] | t9[2]) | (t9[3] | t9[4] | t9[5]) | (t9[6] | t9[7] | t9[8]);
-    od |= (t9[9] | t9[10] | t9[11]) | (t9[12] | t9[13] | t9[14]) | t9[15];
-    return ob | od;
+    const uint32_t hi = b >= 32 ? 0xFFFFFFFFu : (b <= 0 ? 0u : (1u << b) - 1u);
+    const uint32_t lo = a >= 32 ? 0xFFFFFFFFu : (a <= 0 ? 0u : (1u << a) - 1u);
+    return hi & ~lo;
 }
 
-// corner test of a thread's FT_ITEMS work items; pix = word that holds pixel-region column 0 of row 0
-template <int S>
-__device__ __forceinline__ void corner_test(const uint32_t *__restrict__ pix, int tid, int sx0, int sy0, int xEnd, int yEnd, uint32_t (&nflag)[FT_ITEMS])
-{
-#pragma unroll 1
-    for (int it = 0; it < FT_ITEMS; it++) {
-        const int id = tid + it * FT_THREADS;
-        const int g = id & 15, r = id >> 4;
-        const int sy = sy0 + r;
-        uint32_t valid = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int sx = sx0 + 4 * g + j;
-            if (sx >= DET_MIN && sx < xEnd) valid |= 0x80u << (8 * j);
-        }
-        if (sy < DET_MIN || sy >= yEnd) valid = 0;
-        uint32_t f = 0;
-        if (valid) f = corner_flags<S>(pix + (r + 3) * RW + g) & valid;
-        nflag[it] = f;
-    }
-}
-
-#ifndef HYORB_FAST_STOP
-#define HYORB_FAST_STOP 0      // timing experiments only: 1..3 leave the tile loop after the test / compaction / scoring phase
-#endif
 #ifndef HYORB_FT_MINB
 #define HYORB_FT_MINB 4
 #endif
@@ -147,19 +82,20 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
        uint32_t *__restrict__ cand, int *__restrict__ candCount, int *__restrict__ status)
 {
     __shared__ __align__(128) uint8_t s_pixbuf[2][FT_BUF_BYTES];
+    __shared__ __align__(16) uint32_t s_planes[FT_PH * FT_PLP];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ __align__(4) uint8_t s_score[FT_SH * FT_SW];
     __shared__ uint16_t s_list[FT_SH * FT_SW];
-    __shared__ uint32_t s_emit[EMIT_CAP];
-    __shared__ uint8_t s_cf[FT_SW], s_rf[FT_SH];
+    __shared__ uint8_t s_cf[FT_SW], s_rf[64];
     __shared__ int s_n, s_ne, s_base;
+    uint32_t *s_emit = s_planes;            // the planes are dead once the corner test is done
 
     const int tid = threadIdx.x;
     // pixel box of tile T -> buffer `buf`; issued by one thread, completion lands on s_bar[buf]
     auto issue = [&](int T, int buf) {
         const FastTile t = fast_tile(plan, T);
         mbar_arrive_expect_tx(&s_bar[buf], FT_BOXW * FT_PH);
-        tma_load_3d(s_pixbuf[buf], t.l == 0 ? &tm0 : &tmaps[t.l], &s_bar[buf], (t.sx0 - 3) & ~15, t.sy0 - 3, img0 + t.b);
+        tma_load_3d(s_pixbuf[buf], t.l == 0 ? &tm0 : &tmaps[t.l], &s_bar[buf], t.x0 & ~15, t.sy0 - 3, img0 + t.b);
     };
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
@@ -178,88 +114,88 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     const FastTile tile = fast_tile(plan, T);
     const int l = tile.l, b = tile.b;
     const LevelDev &L = plan->lv[l];
-    const int sx0 = tile.sx0, sy0 = tile.sy0;
-    const int off = (sx0 - 3) & 15;                         // byte position of pixel-region column 0 inside the box
-    const uint8_t *pix8 = s_pixbuf[buf] + off;              // pixel region, row pitch PITCHB
+    const int x0 = tile.x0, sy0 = tile.sy0;
+    const int off = x0 & 15;                                // byte position of region column 0 inside the box
+    const uint8_t *pix8 = s_pixbuf[buf] + off;              // region, row pitch PITCHB
 
     if (tid == 0) { s_n = 0; s_ne = 0; }
     for (int i = tid; i < FT_SH * FT_SW / 4; i += FT_THREADS) ((uint32_t *)s_score)[i] = 0;
     if (tid < FT_SW) {
-        const int m = (sx0 + tid - DET_MIN) % L.wCell;      // sx0+tid >= 18; the halo column left of x=19 is never valid
+        const int x = x0 + tid;                              // columns left of x = 19 are never emitted
+        const int m = x >= DET_MIN ? (x - DET_MIN) % L.wCell : 1;
         s_cf[tid] = (uint8_t)((m == 0 ? 1 : 0) | (m == L.wCell - 1 ? 2 : 0));
-    } else if (tid >= 64 && tid < 64 + FT_SH) {      // FT_SH <= 128
-        const int r = tid - 64;
-        const int m = (sy0 + r - DET_MIN) % L.hCell;
+    } else if (tid >= 128 && tid < 128 + FT_SH) {
+        const int r = tid - 128;
+        const int y = sy0 + r;
+        const int m = y >= DET_MIN ? (y - DET_MIN) % L.hCell : 1;
         s_rf[r] = (uint8_t)((m == 0 ? 1 : 0) | (m == L.hCell - 1 ? 2 : 0));
     }
     mbar_wait(&s_bar[buf], (it >> 1) & 1);      // the pixel box has landed
+
+    // ---- T. bit-plane transposition: thread -> (region row, segment)
+    {
+        const int row = tid / FT_NSEG, seg = tid - row * FT_NSEG;
+        const int o = off + 32 * seg;
+        const uint32_t *src = (const uint32_t *)(s_pixbuf[buf] + row * PITCHB) + (o >> 2);
+        const unsigned sh = (unsigned)(o & 3) * 8;
+        uint32_t x[9], w[8], P[8];
+#pragma unroll
+        for (int j = 0; j < 9; j++) x[j] = src[j];
+#pragma unroll
+        for (int j = 0; j < 8; j++) w[j] = __funnelshift_r(x[j], x[j + 1], sh);
+        bs_transpose(w, P);
+        uint4 *dst = (uint4 *)(s_planes + row * FT_PLP + (seg + 1) * 8);
+        dst[0] = make_uint4(P[0], P[1], P[2], P[3]);
+        dst[1] = make_uint4(P[4], P[5], P[6], P[7]);
+        // the zero segments either side of the row (the emit staging of the previous tile may have overwritten them)
+        if (seg == 0) { dst[-2] = make_uint4(0, 0, 0, 0); dst[-1] = make_uint4(0, 0, 0, 0); }
+        if (seg == FT_NSEG - 1) { dst[2] = make_uint4(0, 0, 0, 0); dst[3] = make_uint4(0, 0, 0, 0); }
+    }
     __syncthreads();
 
     const int xEnd = L.maxBX - 3, yEnd = L.maxBY - 3;     // detect range [19, xEnd) x [19, yEnd)
-    // ---- corner test, 4 pixels per item; the byte alignment of the region inside the box is CTA-uniform
-    uint32_t nflag[FT_ITEMS];
-    {
-        const uint32_t *pixw = (const uint32_t *)s_pixbuf[buf] + (off >> 2);
-        switch (off & 3) {
-        case 0: corner_test<0>(pixw, tid, sx0, sy0, xEnd, yEnd, nflag); break;
-        case 1: corner_test<1>(pixw, tid, sx0, sy0, xEnd, yEnd, nflag); break;
-        case 2: corner_test<2>(pixw, tid, sx0, sy0, xEnd, yEnd, nflag); break;
-        default: corner_test<3>(pixw, tid, sx0, sy0, xEnd, yEnd, nflag); break;
-        }
+    // ---- A. corner test: warp -> (segment, block of 32 score rows), lane -> score row
+    uint32_t flags = 0;
+    const int a_seg = (tid >> 5) % FT_NSEG, a_r = ((tid >> 5) / FT_NSEG) * 32 + (tid & 31);
+    if (a_r < FT_SH) {
+        const int sy = sy0 + a_r;
+        // region columns with a full ring [3, 93) that lie in the detect range, restricted to this segment
+        const int cl = max(3, DET_MIN - x0), ch = min(FT_SW - 3, xEnd - x0);
+        uint32_t valid = bit_range(cl - 32 * a_seg, ch - 32 * a_seg);
+        if (sy < DET_MIN || sy >= yEnd) valid = 0;
+        if (valid) flags = bs_corners<FT_PLP>(s_planes + (a_r + 3) * FT_PLP + (a_seg + 1) * 8) & valid;
     }
-#if HYORB_FAST_STOP == 1
-    { uint32_t acc = 0;
-#pragma unroll
-      for (int k = 0; k < FT_ITEMS; k++) acc |= nflag[k];
-      if (acc == 0x12345678u) atomicOr(status, 128); __syncthreads(); continue; }
-#endif
-    // ---- compact the corner flags into the CTA list.  A lane's FT_ITEMS corner counts (<= 4 each) ride in one register,
-    // one byte per item: a single packed warp scan (no byte overflows: a warp holds <= 128 corners per item) gives every
-    // lane its offsets for all items at once; one shared-memory atomic per warp reserves the chunk.
+    // ---- B. compact the corner bits into the CTA list: warp scan of the per-lane counts, one shared-memory atomic per warp
     {
         const int lane = tid & 31;
-        uint32_t cnt = 0;
-#pragma unroll
-        for (int k = 0; k < FT_ITEMS; k++) cnt |= (uint32_t)__popc(nflag[k] & 0x80808080u) << (8 * k);
-        uint32_t inc = cnt;
+        const int cnt = __popc(flags);
+        int inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += t;
         }
-        const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);      // per-item warp totals, one byte each
-        const uint32_t excl = inc - cnt;
-        int total = 0;
-        int ibase[FT_ITEMS];
-#pragma unroll
-        for (int k = 0; k < FT_ITEMS; k++) { ibase[k] = total + (int)((excl >> (8 * k)) & 0xFFu); total += (int)((tot >> (8 * k)) & 0xFFu); }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
         int base = 0;
         if (lane == 0 && total) base = atomicAdd(&s_n, total);
         base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-        for (int k = 0; k < FT_ITEMS; k++) {
-            const uint32_t f = nflag[k];
-            if (f) {
-                const int id = tid + k * FT_THREADS;
-                const int e0 = (id >> 4) * FT_SW + 4 * (id & 15);
-                int pos = base + ibase[k];
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if ((f >> (8 * j + 7)) & 1u) s_list[pos++] = (uint16_t)(e0 + j);
-            }
+        int pos = base + inc - cnt;
+        const int e0 = a_r * FT_SW + 32 * a_seg;
+        uint32_t f = flags;
+        while (f) {
+            const int j = __ffs(f) - 1;
+            f &= f - 1;
+            s_list[pos++] = (uint16_t)(e0 + j);
         }
     }
     __syncthreads();
 
-#if HYORB_FAST_STOP == 2
-    __syncthreads(); continue;
-#endif
-    // ---- scores of the compacted corners
+    // ---- C. scores of the compacted corners
     const int ncorner = s_n;
     for (int i = tid; i < ncorner; i += FT_THREADS) {
         const int e = s_list[i];
         const int r = e / FT_SW, cidx = e - r * FT_SW;
-        const uint8_t *p = pix8 + (r + 3) * PITCHB + (cidx + 3);
+        const uint8_t *p = pix8 + (r + 3) * PITCHB + cidx;
         const int v = p[0];
         // 16-bit lanes: low = centre - ring (dark arcs), high = ring - centre (bright arcs).  With R' = (ring+1)*65535 =
         // (ring << 16 | -(ring+1)) and A' = (-centre << 16 | centre+1), the lane-wise sum A' + R' is exactly that pair.
@@ -283,20 +219,15 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     }
     __syncthreads();
 
-#if HYORB_FAST_STOP == 3
-    __syncthreads(); continue;
-#endif
-    // ---- cell-local 3x3 NMS over the interior, stage survivors
+    // ---- D. cell-local 3x3 NMS over the interior, stage survivors (s_emit aliases the plane buffer)
     for (int i0 = 0; i0 < ncorner; i0 += FT_THREADS) {      // warp-uniform trip count: the ballot below needs all lanes
         const int i = i0 + tid;
-        bool kept = false;
-        uint32_t packed = 0;
         // branch-free: the eight neighbour scores are fetched together (independent loads, every address stays inside
         // s_score for an interior pixel) and neighbours that belong to another cell are replaced by 0
-        const int e = i < ncorner ? (int)s_list[i] : (FT_SW + 1);
+        const int e = i < ncorner ? (int)s_list[i] : (FT_SW + FT_C0);
         const int r = e / FT_SW, cidx = e - r * FT_SW;
-        const bool inner = i < ncorner && r >= 1 && r <= FT_OH && cidx >= 1 && cidx <= FT_OW;      // else: halo, belongs to the neighbouring tile
-        const uint8_t *q = s_score + (inner ? e : FT_SW + 1);
+        const bool inner = i < ncorner && r >= 1 && r <= FT_OH && cidx >= FT_C0 && cidx < FT_C0 + FT_OW;      // else: halo, belongs to the neighbouring tile
+        const uint8_t *q = s_score + (inner ? e : FT_SW + FT_C0);
         const int s = q[0];
         const int nl = q[-1], nr = q[1], nu = q[-FT_SW], nul = q[-FT_SW - 1], nur = q[-FT_SW + 1], nd = q[FT_SW], ndl = q[FT_SW - 1], ndr = q[FT_SW + 1];
         const int cf = s_cf[cidx], rf = s_rf[r];
@@ -304,8 +235,8 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         const int m0 = __vimax3_s32(L_ok ? nl : 0, R_ok ? nr : 0, U_ok ? nu : 0);
         const int m1 = __vimax3_s32(U_ok && L_ok ? nul : 0, U_ok && R_ok ? nur : 0, D_ok ? nd : 0);
         const int m2 = __vimax3_s32(D_ok && L_ok ? ndl : 0, D_ok && R_ok ? ndr : 0, m0);
-        kept = inner && s > max(m1, m2);
-        packed = pack_cand(sx0 + cidx - LATTICE_MIN, sy0 + r - LATTICE_MIN, s);
+        const bool kept = inner && s > max(m1, m2);
+        const uint32_t packed = pack_cand(x0 + cidx - LATTICE_MIN, sy0 + r - LATTICE_MIN, s);
         const unsigned bal = __ballot_sync(0xffffffffu, kept);
         if (bal) {
             const int lane = tid & 31;
@@ -317,10 +248,6 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         }
     }
     __syncthreads();
-#if HYORB_FAST_STOP == 4
-    if (s_ne == 0x7fffffff) atomicOr(status, 128);
-    continue;
-#endif
     int ne = s_ne;
     if (ne > 0) {       // CTA-uniform
         int *cnt = candCount + b * HYORB_MAX_LEVELS + l;
