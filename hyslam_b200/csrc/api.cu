@@ -54,9 +54,9 @@ struct hyorb_extractor {
     // A batch is cut into `lanes` independent sub-batches, each enqueued on its own stream, so that the latency-bound
     // kernels of one sub-batch (quadtree, stereo table) overlap the throughput-bound ones (FAST, blur) of another.
     // Lane 0 runs on `stream`.  Inside a lane the blur runs on a side stream next to FAST + quadtree (it only needs the pyramid).
-    static constexpr int MAX_LANES = 8;
+    static constexpr int MAX_LANES = 16;
     int lanes = 2;           // device-pointer entry points
-    int host_lanes = 4;      // host-buffer entry points: more, smaller lanes so the PCIe copies pipeline against the kernels
+    int host_lanes = 8;      // host-buffer entry points: more, smaller lanes so the PCIe copies pipeline against the kernels
     int side_blur = 2;        // 1: blur on a side stream next to FAST + quadtree; 2: next to the quadtree only (HYORB_SIDE_BLUR)
     cudaStream_t lane_stream[MAX_LANES] = {}, side[MAX_LANES] = {};
     cudaEvent_t ev_start = nullptr, ev_pyr[MAX_LANES] = {}, ev_blur[MAX_LANES] = {}, ev_done[MAX_LANES] = {};

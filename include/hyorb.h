@@ -154,7 +154,7 @@ HYORB_API int hyorb_extractor_set_profiling(hyorb_extractor *h, int enable);
 HYORB_API int hyorb_extractor_stage_times(hyorb_extractor *h, double *ms, long *calls, int reset);
 
 /* How a batch call is pipelined on the device (no counterpart in the reference, which is one frame per call).
- * lanes: the batch is cut into this many independent sub-batches, each on its own stream (1..8), separately for the
+ * lanes: the batch is cut into this many independent sub-batches, each on its own stream (1..16), separately for the
  * device-pointer and the host-buffer entry points; side_blur: 0 = every stage of a lane in stream order, 1 = the blur
  * on a side stream next to FAST + quadtree, 2 = next to the quadtree only (default).  A value < 0 keeps the current
  * setting.  lanes = 1, side_blur = 0 serialises the kernels, which is what makes hyorb_extractor_stage_times() report
