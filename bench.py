@@ -296,6 +296,36 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    # ---- auxiliary line item (config C4, not the headline metric): keyframe-pair brute-force Hamming matching, 8000 x 8000
+    # descriptors, BoW acceptance rule (SearchForTriangulation's scan), device-resident
+    c4 = None
+    try:
+        from hyslam_b200 import synth
+        nq = nt = 8000
+        da = synth.random_descriptors(nq, 7)
+        db = np.roll(da, 17, axis=0) ^ synth.random_descriptors(nt, 8) & 0x11
+        tq, tt = torch.from_numpy(da).to(dev), torch.from_numpy(db).to(dev)
+        obi = torch.empty(nq, dtype=torch.int32, device=dev); ob = torch.empty(nq, dtype=torch.int16, device=dev)
+        osec = torch.empty(nq, dtype=torch.int16, device=dev); oacc = torch.empty(nq, dtype=torch.uint8, device=dev)
+        fm = hb.FeatureMatcher(device=local, stream=stream.cuda_stream)
+        run = lambda: fm.match_bruteforce_device(tq.data_ptr(), nq, tt.data_ptr(), nt, F.RULE_BOW, 50.0, 0.6, obi.data_ptr(), ob.data_ptr(),
+                                                 osec.data_ptr(), oacc.data_ptr())
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        m0.record(stream)
+        for _ in range(reps):
+            run()
+        m1.record(stream)
+        torch.cuda.synchronize()
+        mms = m0.elapsed_time(m1) / reps
+        c4 = {"workload": "C4: 8000 x 8000 descriptors, brute force, best/second-best + ratio test", "ms_per_pair_of_keyframes": mms,
+              "distance_evals_per_s": nq * nt / (mms * 1e-3), "popc32_per_s": 8 * nq * nt / (mms * 1e-3), "accepted": int(oacc.sum().item())}
+    except Exception as e:                      # never let the auxiliary item break the headline line
+        c4 = {"error": str(e)[:200]}
+
     # ---- roofline of the dominant kernel
     peaks = {}
     try:
@@ -365,7 +395,7 @@ def main():
         "kpts_per_sec": value * kp_per_step / P, "keypoints_per_frame": kp_per_step / P, "stereo_matches_per_frame": matched / P,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "hyorb_process_stereo_batch_host (pinned host buffers)"},
-        "gpu_launches": int(launches), "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
+        "gpu_launches": int(launches), "roofline": roofline, "stages": stages, "c4_match": c4, "cpu_baseline": cpu, "clocks": clocks,
     }
     print(json.dumps(line))
     if dist is not None:

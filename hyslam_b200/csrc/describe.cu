@@ -7,6 +7,7 @@
 // x86-64 baseline build: every fp32 operation individually rounded (no FMA contraction), cos/sin in double then
 // narrowed, cvRound = round-half-even.
 #include <float.h>
+#include <mutex>
 #include "common.cuh"
 
 namespace hyorb {
@@ -179,14 +180,19 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
 int launch_describe(const PlanDev &hp, const PlanDev *dp, const uint8_t *blur, const uint32_t *sel, const int *selCount,
                     hyorb_keypoint *kps, uint8_t *desc, int capacity, int *counts, int *status, int B, cudaStream_t st, long *launches)
 {
-    static bool pattern_ready[64] = {};
+    // the float copy of the pattern is filled once per device; call_once blocks concurrent first callers (the reference
+    // runs the left and the right extractor on two threads) until the table is complete
+    static std::once_flag pattern_once[64];
     int dev = 0;
     HY_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && !pattern_ready[dev]) {        // once per device; synchronous so that other handles' streams see the table
+    if (dev < 0 || dev >= 64) { set_error("device ordinal %d not supported", dev); return HYORB_EUNSUPPORTED; }
+    cudaError_t perr = cudaSuccess;
+    std::call_once(pattern_once[dev], [&] {
         k_pattern_to_float<<<1, 256, 0, st>>>();
-        HY_CUDA(cudaStreamSynchronize(st));
-        pattern_ready[dev] = true; ++*launches;
-    }
+        perr = cudaStreamSynchronize(st);
+        ++*launches;
+    });
+    if (perr != cudaSuccess) { set_error("pattern table: %s", cudaGetErrorString(perr)); return HYORB_ECUDA; }
     int slots = hp.selTotalCap < capacity ? hp.selTotalCap : capacity;
     if (slots < 1) slots = 1;
     dim3 grd((slots + DS_WARPS - 1) / DS_WARPS, B);

@@ -1,0 +1,193 @@
+// hyorb_hyslam.hpp -- the C++ host side of the drop-in: hySLAM's own feature interfaces implemented over the C ABI of
+// libhyorb (include/hyorb.h).  Header-only, C++14 like hySLAM; include it from a hySLAM translation unit (its include
+// path supplies FeatureExtractor.h, ORBFactory.h, FeatureViews.h, Camera.h, FeatureMatcher.h and OpenCV).
+//
+//   HYSLAM::CudaORBExtractor   : FeatureExtractor    replaces HYSLAM::ORBExtractor        (src/features/ORBExtractor.h:63-116)
+//   HYSLAM::CudaORBFactory     : ORBFactory          replaces ORBFactory::getExtractor    (src/features/ORBFactory.cpp:32-40)
+//   HYSLAM::CudaStereomatcher                        same public surface as Stereomatcher (src/features/Stereomatcher.h:25-51)
+//   HYSLAM::cuda_marshal::...                        FeatureViews / vector<FeatureDescriptor>  <->  SoA arrays of the ABI
+//
+// The only line of hySLAM that changes is the factory choice in System.cc:77-85 (`new CudaORBFactory(path)` for the
+// YAML key `Features: ORB`); ImageProcessing::ProcessStereoImage (src/main/ImageProcessing.cpp:69-116) keeps its code
+// and swaps `Stereomatcher` for `CudaStereomatcher`.  tests/cpp compiles this header against test doubles of the hySLAM
+// headers and runs ProcessStereoImage's call sequence on a GPU (tests/test_gpu_cpp_shim.py).
+#pragma once
+#include <FeatureExtractor.h>
+#include <FeatureMatcher.h>
+#include <FeatureViews.h>
+#include <ORBFactory.h>
+#include <Camera.h>
+
+#include <cassert>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "hyorb.h"
+
+namespace HYSLAM {
+
+static_assert(sizeof(cv::KeyPoint) == sizeof(hyorb_keypoint), "hyorb_keypoint mirrors the layout of cv::KeyPoint");
+
+namespace cuda_marshal {
+// vector<FeatureDescriptor> (one cloned 1x32 cv::Mat per keypoint, FeatureDescriptor.cpp:14-18) -> n x 32 bytes
+inline std::vector<uint8_t> packDescriptors(const std::vector<FeatureDescriptor> &d)
+{
+    std::vector<uint8_t> out(d.size() * HYORB_DESC_BYTES);
+    for (size_t i = 0; i < d.size(); i++) {
+        const cv::Mat m = d[i].rawDescriptor();
+        assert(m.rows * m.cols == HYORB_DESC_BYTES);
+        std::memcpy(out.data() + i * HYORB_DESC_BYTES, m.data, HYORB_DESC_BYTES);
+    }
+    return out;
+}
+// n x 32 bytes -> vector<FeatureDescriptor>, appended like ORBExtractor::operator() does (ORBExtractor.cpp:558-561)
+inline void appendDescriptors(const uint8_t *rows, int n, const std::shared_ptr<DescriptorDistance> &dist, std::vector<FeatureDescriptor> &out)
+{
+    out.reserve(out.size() + n);
+    for (int i = 0; i < n; i++)
+        out.push_back(FeatureDescriptor(cv::Mat(1, HYORB_DESC_BYTES, CV_8U, const_cast<uint8_t *>(rows) + (size_t)i * HYORB_DESC_BYTES), dist));
+}
+inline const hyorb_keypoint *asAbi(const std::vector<cv::KeyPoint> &k) { return reinterpret_cast<const hyorb_keypoint *>(k.data()); }
+inline void check(int rc) { if (rc != HYORB_OK) throw std::runtime_error(std::string("libhyorb: ") + hyorb_last_error()); }
+}  // namespace cuda_marshal
+
+// ---------------------------------------------------------------------------------------------------------------
+class CudaORBExtractor : public FeatureExtractor {
+public:
+    CudaORBExtractor(std::shared_ptr<DescriptorDistance> dist, FeatureExtractorSettings s, int device = 0)
+        : dist_func(dist), nlevels(s.nLevels), scale(s.fScaleFactor)
+    {
+        hyorb_extractor_params p{s.nFeatures, s.fScaleFactor, s.nLevels, s.N_CELLS, s.init_threshold, s.min_threshold, 0};
+        cuda_marshal::check(hyorb_extractor_create(&p, device, nullptr, &h));
+        sf.resize(nlevels); inv.resize(nlevels); s2.resize(nlevels); is2.resize(nlevels);
+        cuda_marshal::check(hyorb_extractor_get_scales(h, sf.data(), inv.data(), s2.data(), is2.data(), nullptr));
+        cap = 4 * s.nFeatures + 1024;          // the quadtree may return more than nFeatures (ORBExtractor.cpp:309-312)
+        kp.resize(cap); desc.resize((size_t)cap * HYORB_DESC_BYTES);
+    }
+    ~CudaORBExtractor() override { hyorb_extractor_destroy(h); }
+    CudaORBExtractor(const CudaORBExtractor &) = delete;
+    CudaORBExtractor &operator=(const CudaORBExtractor &) = delete;
+
+    // Contract of ORBExtractor::operator() (ORBExtractor.cpp:496-562): the mask is ignored, the image must be CV_8UC1, an
+    // empty image returns silently, `keypoints` is cleared, descriptors are appended.
+    void operator()(cv::InputArray image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint> &keypoints,
+                    std::vector<FeatureDescriptor> &descriptors) override
+    {
+        if (image.empty()) return;
+        const cv::Mat im = image.getMat();
+        assert(im.type() == CV_8UC1);
+        int n = 0;
+        cuda_marshal::check(hyorb_extract_host(h, im.data, im.cols, im.rows, (int)im.step, kp.data(), desc.data(), cap, &n));
+        const cv::KeyPoint *k = reinterpret_cast<const cv::KeyPoint *>(kp.data());
+        keypoints.assign(k, k + n);
+        cuda_marshal::appendDescriptors(desc.data(), n, dist_func, descriptors);
+    }
+    int GetLevels() override { return nlevels; }
+    float GetScaleFactor() override { return scale; }
+    std::vector<float> GetScaleFactors() override { return sf; }
+    std::vector<float> GetInverseScaleFactors() override { return inv; }
+    std::vector<float> GetScaleSigmaSquares() override { return s2; }
+    std::vector<float> GetInverseScaleSigmaSquares() override { return is2; }
+
+private:
+    hyorb_extractor *h = nullptr;
+    std::shared_ptr<DescriptorDistance> dist_func;
+    int nlevels, cap = 0;
+    float scale;
+    std::vector<float> sf, inv, s2, is2;
+    std::vector<hyorb_keypoint> kp;
+    std::vector<uint8_t> desc;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Keeps ORBFactory's settings, vocabulary and distance function; only the extractor objects change.
+class CudaORBFactory : public ORBFactory {
+public:
+    CudaORBFactory() : ORBFactory() {}
+    explicit CudaORBFactory(std::string settings_path, int device_ = 0) : ORBFactory(settings_path), device(device_) {}
+    std::shared_ptr<FeatureExtractor> getExtractor(std::string /*camera type: the reference reads the same YAML block for all*/) override
+    {
+        return getExtractor(getFeatureExtractorSettings());
+    }
+    std::shared_ptr<FeatureExtractor> getExtractor(FeatureExtractorSettings s) override
+    {
+        return std::make_shared<CudaORBExtractor>(getDistanceFunc(), s, device);
+    }
+
+private:
+    int device = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stereomatcher(views, camera, settings); computeStereoMatches(); getData(...) -- Stereomatcher.h:25-51.
+class CudaStereomatcher {
+public:
+    CudaStereomatcher(FeatureViews views, Camera cam_data, FeatureMatcherSettings settings, int device = 0)
+        : mvKeys(views.getKeys()), mvKeysRight(views.getKeysR()), descL(cuda_marshal::packDescriptors(views.getDescriptors())),
+          descR(cuda_marshal::packDescriptors(views.getDescriptorsR())), N((int)mvKeys.size())
+    {
+        const FeatureExtractorSettings orb_params = views.getOrbParams();       // default-constructed at the call site: only size_ref matters
+        sp.mbf = cam_data.mbf; sp.fx = cam_data.fx(); sp.n_rows = (int)cam_data.mnMaxY;
+        sp.th_high = settings.TH_HIGH; sp.th_low = settings.TH_LOW; sp.size_ref = orb_params.size_ref;
+        cuda_marshal::check(hyorb_matcher_create(device, nullptr, &m));
+    }
+    ~CudaStereomatcher() { hyorb_matcher_destroy(m); }
+    CudaStereomatcher(const CudaStereomatcher &) = delete;
+    CudaStereomatcher &operator=(const CudaStereomatcher &) = delete;
+
+    void computeStereoMatches()
+    {
+        mvuRight.assign(N, -1.0f);
+        mvDepth.assign(N, -1.0f);
+        if (N == 0) return;
+        cuda_marshal::check(hyorb_stereo_match_host(m, &sp, cuda_marshal::asAbi(mvKeys), descL.data(), N, cuda_marshal::asAbi(mvKeysRight), descR.data(),
+                                                    (int)mvKeysRight.size(), mvuRight.data(), mvDepth.data(), nullptr, nullptr));
+    }
+    void getData(std::vector<float> &mvuRight_, std::vector<float> &mvDepth_) { mvuRight_ = mvuRight; mvDepth_ = mvDepth; }
+    void getData(FeatureViews &views) { views.setuRs(mvuRight); views.setDepths(mvDepth); }
+
+private:
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight;
+    std::vector<uint8_t> descL, descR;
+    hyorb_stereo_params sp;
+    hyorb_matcher *m = nullptr;
+    std::vector<float> mvuRight, mvDepth;
+    int N;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// The Hamming scans of FeatureMatcher (SearchForTriangulation / SearchByBoW inner loops, FeatureMatcher.cc:281-345, with
+// BestMatchBoWCriterion, MatchCriteria.cpp:601-635) over explicit candidate lists; projection and map bookkeeping stay
+// with hySLAM's FeatureMatcher.
+class CudaDescriptorScan {
+public:
+    explicit CudaDescriptorScan(int device = 0) { cuda_marshal::check(hyorb_matcher_create(device, nullptr, &m)); }
+    ~CudaDescriptorScan() { hyorb_matcher_destroy(m); }
+    CudaDescriptorScan(const CudaDescriptorScan &) = delete;
+    CudaDescriptorScan &operator=(const CudaDescriptorScan &) = delete;
+
+    struct Result { std::vector<int32_t> best_idx; std::vector<uint16_t> best, second; std::vector<uint8_t> accepted; };
+
+    // rule: HYORB_RULE_LANDMARK / HYORB_RULE_BOW / HYORB_RULE_MONOINIT; cand_off/cand_idx = CSR candidate lists (nullptr:
+    // every target in index order)
+    Result scan(const std::vector<FeatureDescriptor> &queries, const std::vector<FeatureDescriptor> &targets, const int32_t *cand_off,
+                const int32_t *cand_idx, int rule, float thr, float ratio)
+    {
+        const std::vector<uint8_t> q = cuda_marshal::packDescriptors(queries), t = cuda_marshal::packDescriptors(targets);
+        const int nq = (int)queries.size(), nt = (int)targets.size();
+        Result r;
+        r.best_idx.assign(nq, -1); r.best.assign(nq, 65535); r.second.assign(nq, 65535); r.accepted.assign(nq, 0);
+        cuda_marshal::check(hyorb_match_csr_host(m, q.data(), nq, t.data(), nt, cand_off, cand_idx, rule, thr, ratio, r.best_idx.data(), r.best.data(),
+                                                 r.second.data(), r.accepted.data()));
+        return r;
+    }
+
+private:
+    hyorb_matcher *m = nullptr;
+};
+
+}  // namespace HYSLAM

@@ -1,0 +1,82 @@
+// Runs the C++ drop-in (include/hyorb_hyslam.hpp) through the call sequence of ImageProcessing::ProcessStereoImage
+// (hySLAM src/main/ImageProcessing.cpp:69-116) and dumps what it produced; tests/test_gpu_cpp_shim.py compares the
+// dump with the CPU oracle.  Compiled against the test doubles in tests/cpp/mock_hyslam (this image has no OpenCV C++).
+//   shim_driver left.raw right.raw W H nFeatures mbf fx out.bin
+#include <hyorb_hyslam.hpp>
+
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
+
+using namespace HYSLAM;
+
+static cv::Mat read_raw(const char *path, int w, int h)
+{
+    cv::Mat m(h, w, CV_8UC1);
+    FILE *f = fopen(path, "rb");
+    if (!f || fread(m.data, 1, (size_t)w * h, f) != (size_t)w * h) { fprintf(stderr, "cannot read %s\n", path); exit(2); }
+    fclose(f);
+    return m;
+}
+static void extractFeatures(FeatureExtractor *ex, cv::Mat &img, std::vector<cv::KeyPoint> &k, std::vector<FeatureDescriptor> &d)
+{
+    (*ex)(img, cv::Mat(), k, d);          // FeatureUtil::extractFeatures, called on a transient thread at ImageProcessing.cpp:82
+}
+template <typename T> static void put(FILE *f, const std::vector<T> &v) { if (!v.empty()) fwrite(v.data(), sizeof(T), v.size(), f); }
+
+int main(int argc, char **argv)
+{
+    if (argc < 9) { fprintf(stderr, "usage: shim_driver left.raw right.raw W H nFeatures mbf fx out.bin\n"); return 2; }
+    const int w = atoi(argv[3]), h = atoi(argv[4]), nf = atoi(argv[5]);
+    const float mbf = (float)atof(argv[6]), fx = (float)atof(argv[7]);
+    try {
+        cv::Mat mImGray = read_raw(argv[1], w, h), imGrayRight = read_raw(argv[2], w, h);
+        CudaORBFactory factory;                                   // System.cc:77-85 would pick this for `Features: ORB`
+        FeatureExtractorSettings s = factory.getFeatureExtractorSettings();
+        s.nFeatures = nf;
+        std::shared_ptr<FeatureExtractor> extractor_left = factory.getExtractor(s), extractor_right = factory.getExtractor(s);
+
+        std::vector<cv::KeyPoint> mvKeys, mvKeysRight;
+        std::vector<FeatureDescriptor> mDescriptors, mDescriptorsRight;
+        std::thread orb_thread(extractFeatures, extractor_left.get(), std::ref(mImGray), std::ref(mvKeys), std::ref(mDescriptors));
+        (*extractor_right)(imGrayRight, cv::Mat(), mvKeysRight, mDescriptorsRight);
+        orb_thread.join();
+        FeatureExtractorSettings orb_params = FeatureExtractorSettings();      // default-constructed, as at ImageProcessing.cpp:85 (only size_ref = 31 is read)
+
+        FeatureViews LMviews(mvKeys, mvKeysRight, mDescriptors, mDescriptorsRight, orb_params);
+        Camera cam;
+        cam.K = cv::Mat(3, 3, CV_32F);
+        for (int i = 0; i < 9; i++) cam.K.ptr<float>()[i] = 0.f;
+        cam.K.at<float>(0, 0) = fx; cam.K.at<float>(1, 1) = fx; cam.K.at<float>(2, 2) = 1.f;
+        cam.mbf = mbf; cam.mnMaxX = (float)w; cam.mnMaxY = (float)h;
+        CudaStereomatcher stereomatch(LMviews, cam, factory.getFeatureMatcherSettings());
+        stereomatch.computeStereoMatches();
+        stereomatch.getData(LMviews);
+
+        // SearchForTriangulation-style scan of the left descriptors against the right ones (all targets, BoW rule)
+        CudaDescriptorScan scan;
+        const FeatureMatcherSettings ms = factory.getFeatureMatcherSettings();
+        CudaDescriptorScan::Result r = scan.scan(mDescriptors, mDescriptorsRight, nullptr, nullptr, HYORB_RULE_BOW, ms.TH_LOW, ms.nnratio);
+
+        FILE *f = fopen(argv[8], "wb");
+        if (!f) { fprintf(stderr, "cannot write %s\n", argv[8]); return 2; }
+        const int32_t hdr[4] = {(int32_t)mvKeys.size(), (int32_t)mvKeysRight.size(), extractor_left->GetLevels(), (int32_t)sizeof(cv::KeyPoint)};
+        fwrite(hdr, sizeof(hdr), 1, f);
+        put(f, mvKeys);
+        put(f, cuda_marshal::packDescriptors(mDescriptors));
+        put(f, mvKeysRight);
+        put(f, cuda_marshal::packDescriptors(mDescriptorsRight));
+        put(f, LMviews.getuRs());
+        put(f, LMviews.getDepths());
+        put(f, r.best_idx); put(f, r.best); put(f, r.second); put(f, r.accepted);
+        put(f, extractor_left->GetScaleFactors());
+        fclose(f);
+        // a FeatureDescriptor built by the shim behaves like the reference's (ORBDistance through the stored functor)
+        if (mDescriptors.size() > 1) printf("distance(desc0, desc1) = %.0f\n", mDescriptors[0].distance(mDescriptors[1]));
+        printf("shim ok: %zu + %zu keypoints\n", mvKeys.size(), mvKeysRight.size());
+    } catch (const std::exception &e) {
+        fprintf(stderr, "shim_driver: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
