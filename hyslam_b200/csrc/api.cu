@@ -848,6 +848,28 @@ HYORB_API int hyorb_rotation_consistency_host(hyorb_matcher *m, const float *ang
     return m_sync(m);
 }
 
+HYORB_API int hyorb_distinctive_descriptor_host(hyorb_matcher *m, const uint8_t *desc, const int32_t *lm_off, int n_landmarks, int32_t *best_idx,
+                                                int32_t *best_median)
+{
+    HY_TRY(m_prepare(m));
+    if (n_landmarks < 0) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (n_landmarks == 0) return HYORB_OK;
+    if (!lm_off || !best_idx || !best_median) { set_error("null argument"); return HYORB_EINVAL; }
+    if (lm_off[0] != 0) { set_error("lm_off must start at 0"); return HYORB_EINVAL; }
+    for (int i = 0; i < n_landmarks; i++)
+        if (lm_off[i + 1] < lm_off[i]) { set_error("lm_off must be non-decreasing"); return HYORB_EINVAL; }
+    const int total = lm_off[n_landmarks];
+    if (total > 0 && !desc) { set_error("null argument"); return HYORB_EINVAL; }
+    HY_TRY(m_upload(m, m->d_a, desc, (size_t)total * 32));
+    HY_TRY(m_upload(m, m->d_g, lm_off, sizeof(int32_t) * ((size_t)n_landmarks + 1)));
+    HY_TRY(m->d_c.ensure(sizeof(int32_t) * (size_t)n_landmarks));
+    HY_TRY(m->d_h.ensure(sizeof(int32_t) * (size_t)n_landmarks));
+    HY_TRY(launch_distinctive(m->d_a.as<uint8_t>(), m->d_g.as<int32_t>(), n_landmarks, m->d_c.as<int32_t>(), m->d_h.as<int32_t>(), m->stream, &m->launches));
+    HY_CUDA(cudaMemcpyAsync(best_idx, m->d_c.p, sizeof(int32_t) * (size_t)n_landmarks, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(best_median, m->d_h.p, sizeof(int32_t) * (size_t)n_landmarks, cudaMemcpyDeviceToHost, m->stream));
+    return m_sync(m);
+}
+
 HYORB_API int hyorb_stereo_match_batch_device(hyorb_matcher *m, const hyorb_stereo_params *sp, int n_pairs, const hyorb_keypoint *d_kps,
                                               const uint8_t *d_desc, const int32_t *d_counts, int capacity, float *d_uR, float *d_depth,
                                               int32_t *d_best_r, int32_t *d_best_dist)

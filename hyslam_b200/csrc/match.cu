@@ -340,6 +340,71 @@ int launch_match_window(const hyorb_keypoint *kps, const uint8_t *tdesc, const f
     return HYORB_OK;
 }
 
+// ---------------- landmark representative descriptor (MapPointDBEntry::_computeDistinctiveDescriptor_, src/core/MapPointDB.cpp:127-171)
+// One warp per landmark.  For every observation i the warp histograms the Hamming distances to all observations (self
+// distance 0) into 257 shared-memory bins and reads the order statistic sorted[(int)(0.5*(N-1))] off a warp scan of the
+// bins -- the reference sorts the row; the first row with the smallest median wins (strict <, :163).
+constexpr int DD_WARPS = 4, DD_BINS = 288;      // 257 bins rounded up to 9 per lane
+
+__global__ void __launch_bounds__(DD_WARPS * 32)
+k_distinctive(const uint4 *__restrict__ desc, const int32_t *__restrict__ off, int n_lm, int32_t *__restrict__ best_idx, int32_t *__restrict__ best_median)
+{
+    __shared__ int s_hist[DD_WARPS][DD_BINS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lm = blockIdx.x * DD_WARPS + w;
+    if (lm >= n_lm) return;
+    const int lo = off[lm], N = off[lm + 1] - lo;
+    if (N <= 0) { if (lane == 0) { best_idx[lm] = -1; best_median[lm] = -1; } return; }
+    const int k = (N - 1) >> 1;                  // (int)(0.5*(N-1))
+    int *hist = s_hist[w];
+    int bestMed = 0x7fffffff, bestI = 0;
+    for (int i = 0; i < N; i++) {
+#pragma unroll
+        for (int t = 0; t < DD_BINS / 32; t++) hist[lane * (DD_BINS / 32) + t] = 0;
+        __syncwarp();
+        const uint4 a0 = desc[2 * (size_t)(lo + i)], a1 = desc[2 * (size_t)(lo + i) + 1];
+        for (int j = lane; j < N; j += 32) {
+            const int d = j == i ? 0 : hamming256(a0, a1, desc[2 * (size_t)(lo + j)], desc[2 * (size_t)(lo + j) + 1]);
+            atomicAdd(&hist[d], 1);
+        }
+        __syncwarp();
+        // lane owns bins [9 lane, 9 lane + 9): chunk sums -> inclusive warp scan -> the chunk where the running count reaches k+1
+        int c = 0;
+#pragma unroll
+        for (int t = 0; t < DD_BINS / 32; t++) c += hist[lane * (DD_BINS / 32) + t];
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const unsigned reach = __ballot_sync(0xffffffffu, inc >= k + 1);
+        const int L = __ffs(reach) - 1;          // exists: the counts sum to N > k
+        int med = 0;
+        if (lane == L) {
+            int run = inc - c;
+#pragma unroll
+            for (int t = 0; t < DD_BINS / 32; t++) {
+                run += hist[lane * (DD_BINS / 32) + t];
+                if (run >= k + 1) { med = lane * (DD_BINS / 32) + t; break; }
+            }
+        }
+        med = __shfl_sync(0xffffffffu, med, L);
+        if (med < bestMed) { bestMed = med; bestI = i; }
+        __syncwarp();
+    }
+    if (lane == 0) { best_idx[lm] = bestI; best_median[lm] = bestMed; }
+}
+
+int launch_distinctive(const uint8_t *desc, const int32_t *off, int n_lm, int32_t *best_idx, int32_t *best_median, cudaStream_t st, long *launches)
+{
+    if (n_lm <= 0) return HYORB_OK;
+    k_distinctive<<<(n_lm + DD_WARPS - 1) / DD_WARPS, DD_WARPS * 32, 0, st>>>((const uint4 *)desc, off, n_lm, best_idx, best_median);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
 int launch_rotation(const float *a_prev, const float *a_curr, int n, uint8_t *keep, int *status, cudaStream_t st, long *launches)
 {
     if (n <= 0) return HYORB_OK;

@@ -120,6 +120,15 @@ class FeatureMatcher(_Handle):
         F.check(F.lib().hyorb_rotation_consistency_host(self._h, F.ptr(a), F.ptr(c), len(a), F.ptr(keep)))
         return keep
 
+    def ComputeDistinctiveDescriptors(self, desc, lm_off):
+        """MapPointDBEntry::_computeDistinctiveDescriptor_ (src/core/MapPointDB.cpp:127-171) for many landmarks at once.
+        desc: [total, 32] observation descriptors, lm_off: CSR offsets.  Returns (best_idx relative to each list, best_median)."""
+        desc = np.ascontiguousarray(desc, np.uint8); lm_off = np.ascontiguousarray(lm_off, np.int32)
+        n = len(lm_off) - 1
+        bi = np.full(n, -1, np.int32); bm = np.full(n, -1, np.int32)
+        F.check(F.lib().hyorb_distinctive_descriptor_host(self._h, F.ptr(desc), F.ptr(lm_off), n, F.ptr(bi), F.ptr(bm)))
+        return bi, bm
+
     def match_bruteforce_device(self, d_q, nq, d_t, nt, rule, thr, ratio, d_best_idx, d_best, d_second, d_accepted):
         F.check(F.lib().hyorb_match_bruteforce_device(self._h, d_q, nq, d_t, nt, int(rule), float(thr), float(ratio),
                                                       d_best_idx, d_best, d_second, d_accepted))

@@ -233,6 +233,14 @@ HYORB_API int hyorb_match_window_host(hyorb_matcher *m, const hyorb_keypoint *t_
 HYORB_API int hyorb_rotation_consistency_host(hyorb_matcher *m, const float *angle_prev, const float *angle_curr,
                                               int n, uint8_t *keep);
 
+/* Representative descriptor of a landmark: MapPointDBEntry::_computeDistinctiveDescriptor_ (src/core/MapPointDB.cpp:127-171).
+ * desc: the observation descriptors of all landmarks back to back (32 bytes each); lm_off[n_landmarks + 1]: CSR offsets
+ * (rows of landmark l = lm_off[l] .. lm_off[l+1]).  Per landmark: all-pairs Hamming distances, per-row order statistic
+ * sorted[(int)(0.5*(N-1))], first row with the smallest one.  best_idx[l] is relative to the landmark's first row (-1
+ * for an empty list: the reference returns without touching the landmark), best_median[l] that row's median. */
+HYORB_API int hyorb_distinctive_descriptor_host(hyorb_matcher *m, const uint8_t *desc, const int32_t *lm_off, int n_landmarks,
+                                                int32_t *best_idx, int32_t *best_median);
+
 /* ----- misc ----- */
 HYORB_API const char *hyorb_last_error(void);
 HYORB_API const char *hyorb_version(void);

@@ -222,6 +222,17 @@ def hamming(a, b):
     return lib().orc_hamming(_p(a), _p(b))
 
 
+def distinctive_descriptor(desc, lm_off):
+    """MapPointDBEntry::_computeDistinctiveDescriptor_ (MapPointDB.cpp:127-171) over CSR landmark lists: (best_idx, best_median)."""
+    desc = np.ascontiguousarray(desc, np.uint8); lm_off = np.ascontiguousarray(lm_off, np.int32)
+    n = len(lm_off) - 1
+    bi = np.empty(n, np.int32); bm = np.empty(n, np.int32)
+    rc = lib().orc_distinctive_descriptor(_p(desc), _p(lm_off), n, _p(bi), _p(bm))
+    if rc != 0:
+        raise RuntimeError(f"orc_distinctive_descriptor rc={rc}")
+    return bi, bm
+
+
 def match_csr(qdesc, tdesc, cand_off=None, cand_idx=None, mode=0, thr=100.0, ratio=0.9):
     qdesc = np.ascontiguousarray(qdesc, np.uint8); tdesc = np.ascontiguousarray(tdesc, np.uint8)
     nq, nt = len(qdesc), len(tdesc)
