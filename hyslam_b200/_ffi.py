@@ -41,6 +41,16 @@ class Bounds(C.Structure):
     _fields_ = [("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
 
 
+LM_DTYPE = np.dtype([("Pw", "<f4", 3), ("size", "<f4"), ("min_dist", "<f4"), ("max_dist", "<f4"), ("assoc_idx", "<i4")])
+assert LM_DTYPE.itemsize == 28
+
+
+class Projection(C.Structure):
+    """hyorb_projection: pose + camera of the frame landmarks are projected into"""
+    _fields_ = [("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3), ("K", C.c_float * 9),
+                ("mbf", C.c_float), ("stereo", C.c_int32), ("bounds", Bounds)]
+
+
 class HyorbError(RuntimeError):
     def __init__(self, rc, msg):
         super().__init__(f"hyorb rc={rc}: {msg}")
@@ -57,7 +67,7 @@ SYMBOLS = [
     "hyorb_match_bruteforce_device", "hyorb_grid_build_host", "hyorb_match_window_host",
     "hyorb_rotation_consistency_host", "hyorb_last_error", "hyorb_version", "hyorb_device_count",
     "hyorb_process_stereo_batch_host", "hyorb_process_stereo_batch_device", "hyorb_extractor_set_profiling",
-    "hyorb_extractor_stage_times", "hyorb_extractor_set_pipelining", "hyorb_distinctive_descriptor_host",
+    "hyorb_extractor_stage_times", "hyorb_extractor_set_pipelining", "hyorb_distinctive_descriptor_host", "hyorb_project_landmarks_host", "hyorb_search_by_projection_host",
 ]
 N_STAGES = 6
 STAGE_NAMES = ("pyramid", "fast", "quadtree", "blur", "describe", "stereo")
@@ -128,6 +138,11 @@ def lib():
                                               C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hyorb_rotation_consistency_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hyorb_distinctive_descriptor_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hyorb_project_landmarks_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                                   C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.hyorb_search_by_projection_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                      C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                                      C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -834,6 +834,70 @@ HYORB_API int hyorb_match_window_host(hyorb_matcher *m, const hyorb_keypoint *t_
     return m_sync(m);
 }
 
+static int m_project(hyorb_matcher *m, const hyorb_projection *pr, const hyorb_landmark *lms, int n, const hyorb_keypoint *t_kps, int nt, float th,
+                     float size_ref, float frac_smaller, float frac_larger)
+{
+    // landmarks -> d_e, target keypoints -> d_a; queries -> d_g, passed -> d_k (read back / consumed by the caller)
+    HY_TRY(m_upload(m, m->d_e, lms, sizeof(hyorb_landmark) * (size_t)n));
+    HY_TRY(m_upload(m, m->d_a, t_kps, sizeof(hyorb_keypoint) * (size_t)nt));
+    HY_TRY(m->d_g.ensure(sizeof(hyorb_window_query) * (size_t)n));
+    HY_TRY(m->d_k.ensure((size_t)n));
+    return launch_project_landmarks(*pr, m->d_e.as<hyorb_landmark>(), n, m->d_a.as<hyorb_keypoint>(), nt, th, size_ref, frac_smaller, frac_larger,
+                                    m->d_g.as<hyorb_window_query>(), m->d_k.as<uint8_t>(), m->d_status.as<int>(), m->stream, &m->launches);
+}
+
+HYORB_API int hyorb_project_landmarks_host(hyorb_matcher *m, const hyorb_projection *pr, const hyorb_landmark *lms, int n, const hyorb_keypoint *t_kps,
+                                           int nt, float th, float size_ref, float frac_smaller, float frac_larger, hyorb_window_query *queries,
+                                           uint8_t *passed)
+{
+    HY_TRY(m_prepare(m));
+    if (n < 0 || nt < 0 || !pr) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (n == 0) return HYORB_OK;
+    if (!lms || !queries || !passed || (nt > 0 && !t_kps)) { set_error("null argument"); return HYORB_EINVAL; }
+    HY_TRY(m_project(m, pr, lms, n, t_kps, nt, th, size_ref, frac_smaller, frac_larger));
+    HY_CUDA(cudaMemcpyAsync(queries, m->d_g.p, sizeof(hyorb_window_query) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(passed, m->d_k.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    return m_sync(m);
+}
+
+HYORB_API int hyorb_search_by_projection_host(hyorb_matcher *m, const hyorb_projection *pr, const hyorb_landmark *lms, const uint8_t *lm_desc, int n,
+                                              const hyorb_keypoint *t_kps, const uint8_t *t_desc, const float *t_uR, const uint8_t *t_matched, int nt,
+                                              float th, float size_ref, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
+                                              uint8_t *accepted, uint8_t *passed)
+{
+    HY_TRY(m_prepare(m));
+    if (n < 0 || nt < 0 || !pr) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (n == 0) return HYORB_OK;
+    if (!lms || !lm_desc || !best_idx || !best || !second || !accepted || (nt > 0 && (!t_kps || !t_desc))) { set_error("null argument"); return HYORB_EINVAL; }
+    if (pr->stereo && !t_uR) { set_error("stereo camera but t_uR is NULL"); return HYORB_EINVAL; }
+    constexpr int NC = HYORB_GRID_COLS * HYORB_GRID_ROWS;
+    HY_TRY(m_project(m, pr, lms, n, t_kps, nt, th, size_ref, 0.5f, 1.5f));     // FeatureSizeCriterion(0.5, 1.5), FeatureMatcher.cc:132
+    HY_TRY(m_upload(m, m->d_b, t_desc, (size_t)nt * 32));
+    if (t_uR) HY_TRY(m_upload(m, m->d_l, t_uR, sizeof(float) * (size_t)nt));
+    if (t_matched) HY_TRY(m_upload(m, m->d_bestd, t_matched, (size_t)nt));
+    HY_TRY(m_upload(m, m->d_h, lm_desc, (size_t)n * 32));
+    HY_TRY(m->d_i.ensure(sizeof(int32_t) * (NC + 1)));
+    HY_TRY(m->d_j.ensure(sizeof(int32_t) * std::max(nt, 1)));
+    HY_TRY(m->d_cellof.ensure(sizeof(int32_t) * std::max(nt, 1)));
+    HY_TRY(m->d_cellcnt.ensure(sizeof(int32_t) * NC));
+    HY_TRY(m->d_c.ensure(sizeof(int32_t) * (size_t)n));
+    HY_TRY(m->d_d.ensure(sizeof(uint16_t) * (size_t)n));
+    HY_TRY(m->d_pkey.ensure(sizeof(uint16_t) * (size_t)n));
+    HY_TRY(m->d_f.ensure((size_t)n));
+    HY_TRY(launch_grid_build(m->d_a.as<hyorb_keypoint>(), nt, pr->bounds, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(), m->d_cellof.as<int32_t>(),
+                             m->d_cellcnt.as<int32_t>(), m->stream, &m->launches));
+    HY_TRY(launch_match_window(m->d_a.as<hyorb_keypoint>(), m->d_b.as<uint8_t>(), t_uR ? m->d_l.as<float>() : nullptr,
+                               t_matched ? m->d_bestd.as<uint8_t>() : nullptr, nt, pr->bounds, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(),
+                               m->d_g.as<hyorb_window_query>(), m->d_h.as<uint8_t>(), n, thr, ratio, m->d_c.as<int32_t>(), m->d_d.as<uint16_t>(),
+                               m->d_pkey.as<uint16_t>(), m->d_f.as<uint8_t>(), m->stream, &m->launches, m->d_k.as<uint8_t>()));
+    HY_CUDA(cudaMemcpyAsync(best_idx, m->d_c.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(best, m->d_d.p, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(second, m->d_pkey.p, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(accepted, m->d_f.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    if (passed) HY_CUDA(cudaMemcpyAsync(passed, m->d_k.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    return m_sync(m);
+}
+
 HYORB_API int hyorb_rotation_consistency_host(hyorb_matcher *m, const float *angle_prev, const float *angle_curr, int n, uint8_t *keep)
 {
     HY_TRY(m_prepare(m));

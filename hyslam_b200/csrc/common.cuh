@@ -144,7 +144,10 @@ int launch_grid_build(const hyorb_keypoint *kps, int n, hyorb_bounds b, int32_t 
                       cudaStream_t st, long *launches);
 int launch_match_window(const hyorb_keypoint *kps, const uint8_t *tdesc, const float *t_uR, const uint8_t *t_matched, int nt, hyorb_bounds b,
                         const int32_t *cell_off, const int32_t *cell_idx, const hyorb_window_query *q, const uint8_t *qdesc, int nq,
-                        float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, cudaStream_t st, long *launches);
+                        float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, cudaStream_t st, long *launches,
+                        const uint8_t *q_active = nullptr);
+int launch_project_landmarks(const hyorb_projection &pr, const hyorb_landmark *lms, int n, const hyorb_keypoint *t_kps, int nt, float th, float size_ref,
+                             float frac_smaller, float frac_larger, hyorb_window_query *queries, uint8_t *passed, int *status, cudaStream_t st, long *launches);
 int launch_rotation(const float *a_prev, const float *a_curr, int n, uint8_t *keep, int *status, cudaStream_t st, long *launches);
 int launch_distinctive(const uint8_t *desc, const int32_t *off, int n_lm, int32_t *best_idx, int32_t *best_median, cudaStream_t st, long *launches);
 size_t stereo_scratch_ints_per_pair(int capacity);

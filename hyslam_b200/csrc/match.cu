@@ -195,11 +195,15 @@ __global__ void __launch_bounds__(256)
 k_match_window(const hyorb_keypoint *__restrict__ kps, const uint4 *__restrict__ tdesc, const float *__restrict__ t_uR,
                const uint8_t *__restrict__ t_matched, int nt, hyorb_bounds b, const int32_t *__restrict__ cell_off,
                const int32_t *__restrict__ cell_idx, const hyorb_window_query *__restrict__ qs, const uint4 *__restrict__ qdesc, int nq,
-               float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *sec, uint8_t *accepted)
+               float thr, float ratio, const uint8_t *__restrict__ q_active, int32_t *best_idx, uint16_t *best, uint16_t *sec, uint8_t *accepted)
 {
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= nq) return;
+    if (q_active && !q_active[qi]) {        // landmark rejected by the landmark criteria: no candidates, no match
+        if (lane == 0) write_result(qi, KEY_NONE, DIST_NONE, -1, HYORB_RULE_LANDMARK, thr, ratio, best_idx, best, sec, accepted);
+        return;
+    }
     const hyorb_window_query Q = qs[qi];
     const uint4 a0 = qdesc[2 * qi], a1 = qdesc[2 * qi + 1];
     // Frame::GetFeaturesInAreaNEW (Frame.cc:416-457)
@@ -330,11 +334,83 @@ int launch_grid_build(const hyorb_keypoint *kps, int n, hyorb_bounds b, int32_t 
 
 int launch_match_window(const hyorb_keypoint *kps, const uint8_t *tdesc, const float *t_uR, const uint8_t *t_matched, int nt, hyorb_bounds b,
                         const int32_t *cell_off, const int32_t *cell_idx, const hyorb_window_query *q, const uint8_t *qdesc, int nq,
-                        float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, cudaStream_t st, long *launches)
+                        float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, cudaStream_t st, long *launches,
+                        const uint8_t *q_active)
 {
     if (nq <= 0) return HYORB_OK;
     k_match_window<<<(nq + 7) / 8, 256, 0, st>>>(kps, (const uint4 *)tdesc, t_uR, t_matched, nt, b, cell_off, cell_idx, q, (const uint4 *)qdesc, nq,
-                                                 thr, ratio, best_idx, best, second, accepted);
+                                                 thr, ratio, q_active, best_idx, best, second, accepted);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+// ---------------- landmark projection: the per-landmark front half of FeatureMatcher::SearchByProjection(Frame&, landmarks, th)
+// (FeatureMatcher.cc:123-143, 57-121).  One thread per landmark: ProjectionCriterion + DistanceCriterion (MatchCriteria.cpp:13-28,
+// 46-77), Frame::ProjectLandMark / Camera::Project (Frame.cc:176-180, Camera.cpp:116-153), Frame::landMarkSizePixels (Frame.cc:296-317)
+// and the window / size / stereo bounds of the view criteria.  fp32 policy of the reference's cv::Mat expressions (pinned on the CPU
+// against cv2.gemm / cv2.norm): 3x3 * 3x1 = OpenCV's small-matrix path, t = (a0*b0 + a1*b1) + a2*b2 in float (no FMA), + C rounded
+// once; cv::norm sums squares in double.
+__device__ __forceinline__ void gemm31(const float *A, const float *b, const float *c, float *out)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float t = __fadd_rn(__fadd_rn(__fmul_rn(A[3 * i], b[0]), __fmul_rn(A[3 * i + 1], b[1])), __fmul_rn(A[3 * i + 2], b[2]));
+        out[i] = c ? __fadd_rn(t, c[i]) : t;      // (float)((double)t + (double)c) == the correctly rounded float sum
+    }
+}
+__device__ __forceinline__ bool project_point(const hyorb_projection &pr, const float *Pw, float *uv)
+{
+    float Pc[3], Pch[3];
+    gemm31(pr.Rcw, Pw, pr.tcw, Pc);
+    const float PcZ = Pc[2];
+    const float invz = __fdiv_rn(1.0f, PcZ);
+    Pch[0] = __fdiv_rn(Pc[0], PcZ); Pch[1] = __fdiv_rn(Pc[1], PcZ); Pch[2] = __fdiv_rn(Pc[2], PcZ);
+    gemm31(pr.K, Pch, nullptr, uv);
+    const float u = uv[0], v = uv[1];
+    uv[2] = pr.stereo ? __fsub_rn(u, __fmul_rn(pr.mbf, invz)) : -1.0f;
+    return PcZ > 0.0f && u >= pr.bounds.min_x && u <= pr.bounds.max_x && v >= pr.bounds.min_y && v <= pr.bounds.max_y;
+}
+
+__global__ void __launch_bounds__(128)
+k_project_landmarks(hyorb_projection pr, const hyorb_landmark *__restrict__ lms, int n, const hyorb_keypoint *__restrict__ t_kps, int nt,
+                    float th, float size_ref, float frac_smaller, float frac_larger, hyorb_window_query *__restrict__ queries,
+                    uint8_t *__restrict__ passed, int *status)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const hyorb_landmark lm = lms[i];
+    float uv[3];
+    const bool valid = project_point(pr, lm.Pw, uv);
+    const float PO[3] = {__fsub_rn(lm.Pw[0], pr.Ow[0]), __fsub_rn(lm.Pw[1], pr.Ow[1]), __fsub_rn(lm.Pw[2], pr.Ow[2])};
+    const double sq = __dadd_rn(__dadd_rn(__dmul_rn((double)PO[0], (double)PO[0]), __dmul_rn((double)PO[1], (double)PO[1])), __dmul_rn((double)PO[2], (double)PO[2]));
+    const float dist = (float)__dsqrt_rn(sq);
+    const bool dist_ok = !(dist < lm.min_dist || dist > lm.max_dist);
+    float size_px;
+    if (lm.assoc_idx >= 0) {
+        if (lm.assoc_idx >= nt) { atomicOr(status, ST_BAD_INDEX); size_px = 0.f; }
+        else size_px = t_kps[lm.assoc_idx].size;
+    } else {
+        const float half = __fdiv_rn(lm.size, 2.0f);
+        const float L[3] = {__fsub_rn(lm.Pw[0], half), lm.Pw[1], lm.Pw[2]}, R[3] = {__fadd_rn(lm.Pw[0], half), lm.Pw[1], lm.Pw[2]};
+        float ul[3], ur[3];
+        project_point(pr, L, ul); project_point(pr, R, ur);
+        size_px = __fsub_rn(ur[0], ul[0]);
+    }
+    const float radius = __fdiv_rn(__fmul_rn(th, size_px), size_ref);
+    hyorb_window_query q;
+    q.u = uv[0]; q.v = uv[1]; q.r = radius;
+    q.size_lo = __fmul_rn(frac_smaller, size_px); q.size_hi = __fmul_rn(frac_larger, size_px);
+    q.ur = uv[2]; q.ur_radius = pr.stereo ? radius : -1.0f;
+    queries[i] = q;
+    passed[i] = (uint8_t)(valid && dist_ok);
+}
+
+int launch_project_landmarks(const hyorb_projection &pr, const hyorb_landmark *lms, int n, const hyorb_keypoint *t_kps, int nt, float th, float size_ref,
+                             float frac_smaller, float frac_larger, hyorb_window_query *queries, uint8_t *passed, int *status, cudaStream_t st, long *launches)
+{
+    if (n <= 0) return HYORB_OK;
+    k_project_landmarks<<<(n + 127) / 128, 128, 0, st>>>(pr, lms, n, t_kps, nt, th, size_ref, frac_smaller, frac_larger, queries, passed, status);
     ++*launches;
     HY_CUDA(cudaGetLastError());
     return HYORB_OK;

@@ -120,6 +120,45 @@ class FeatureMatcher(_Handle):
         F.check(F.lib().hyorb_rotation_consistency_host(self._h, F.ptr(a), F.ptr(c), len(a), F.ptr(keep)))
         return keep
 
+    @staticmethod
+    def make_projection(Rcw, tcw, Ow, K, mbf, stereo, bounds):
+        """hyorb_projection from the frame's pose (Frame::mRcw, mtcw, GetCameraCenter()) and camera (K, mbf, sensor, image bounds)"""
+        pr = F.Projection()
+        pr.Rcw[:] = [float(v) for v in np.asarray(Rcw, np.float32).reshape(9)]
+        pr.tcw[:] = [float(v) for v in np.asarray(tcw, np.float32).reshape(3)]
+        pr.Ow[:] = [float(v) for v in np.asarray(Ow, np.float32).reshape(3)]
+        pr.K[:] = [float(v) for v in np.asarray(K, np.float32).reshape(9)]
+        pr.mbf = float(mbf); pr.stereo = int(stereo)
+        pr.bounds.min_x, pr.bounds.max_x, pr.bounds.min_y, pr.bounds.max_y = [float(v) for v in bounds]
+        return pr
+
+    def ProjectLandMarks(self, pr, landmarks, t_kps, th, size_ref=31.0, frac_smaller=0.5, frac_larger=1.5):
+        """ProjectionCriterion + DistanceCriterion + ProjectLandMark + landMarkSizePixels for every landmark (MatchCriteria.cpp:13-77,
+        Frame.cc:176-180, 296-317): (window queries [WQ_DTYPE], passed flags)."""
+        lms = np.ascontiguousarray(landmarks, F.LM_DTYPE); t_kps = np.ascontiguousarray(t_kps, F.KP_DTYPE)
+        n = len(lms)
+        q = np.zeros(n, F.WQ_DTYPE); passed = np.zeros(n, np.uint8)
+        F.check(F.lib().hyorb_project_landmarks_host(self._h, C.byref(pr), F.ptr(lms), n, F.ptr(t_kps), len(t_kps), float(th), float(size_ref),
+                                                     float(frac_smaller), float(frac_larger), F.ptr(q), F.ptr(passed)))
+        return q, passed
+
+    def SearchByProjectionLandMarks(self, pr, landmarks, lm_desc, t_kps, t_desc, th, t_uR=None, t_matched=None, size_ref=31.0, thr=None, ratio=None):
+        """FeatureMatcher::SearchByProjection(Frame&, landmarks, th) (FeatureMatcher.cc:123-143) up to the association loop, in one
+        device call.  Returns (best_idx, best, second, accepted, passed) per landmark."""
+        lms = np.ascontiguousarray(landmarks, F.LM_DTYPE); lm_desc = np.ascontiguousarray(lm_desc, np.uint8)
+        t_kps = np.ascontiguousarray(t_kps, F.KP_DTYPE); t_desc = np.ascontiguousarray(t_desc, np.uint8)
+        t_uR = None if t_uR is None else np.ascontiguousarray(t_uR, np.float32)
+        t_matched = None if t_matched is None else np.ascontiguousarray(t_matched, np.uint8)
+        thr = float(self.settings.TH_HIGH if thr is None else thr)
+        ratio = float(self.settings.nnratio if ratio is None else ratio)
+        n = len(lms)
+        bi, b, s, acc = self._outs(n)
+        passed = np.zeros(n, np.uint8)
+        F.check(F.lib().hyorb_search_by_projection_host(self._h, C.byref(pr), F.ptr(lms), F.ptr(lm_desc), n, F.ptr(t_kps), F.ptr(t_desc), F.ptr(t_uR),
+                                                        F.ptr(t_matched), len(t_kps), float(th), float(size_ref), thr, ratio, F.ptr(bi), F.ptr(b),
+                                                        F.ptr(s), F.ptr(acc), F.ptr(passed)))
+        return bi, b, s, acc, passed
+
     def ComputeDistinctiveDescriptors(self, desc, lm_off):
         """MapPointDBEntry::_computeDistinctiveDescriptor_ (src/core/MapPointDB.cpp:127-171) for many landmarks at once.
         desc: [total, 32] observation descriptors, lm_off: CSR offsets.  Returns (best_idx relative to each list, best_median)."""

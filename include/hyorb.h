@@ -228,6 +228,43 @@ HYORB_API int hyorb_match_window_host(hyorb_matcher *m, const hyorb_keypoint *t_
                                       float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
                                       uint8_t *accepted);
 
+/* Pose + camera of the frame landmarks are projected into, and one landmark, for the per-landmark front half of
+ * FeatureMatcher::SearchByProjection(Frame&, landmarks, th) (FeatureMatcher.cc:123-143 -> _SearchByProjection_ :57-121). */
+typedef struct hyorb_projection {
+    float Rcw[9], tcw[3];   /* Frame::mRcw, mtcw, row-major */
+    float Ow[3];            /* Frame::GetCameraCenter() */
+    float K[9];             /* Camera::K, row-major */
+    float mbf;              /* Camera::mbf */
+    int32_t stereo;         /* Camera::sensor == 1: ur = u - mbf/z and the stereo consistency test apply */
+    hyorb_bounds bounds;    /* Camera::mnMinX .. mnMaxY */
+} hyorb_projection;
+typedef struct hyorb_landmark {
+    float Pw[3];                /* MapPoint::GetWorldPos() */
+    float size;                 /* MapPoint::getSize(), world units */
+    float min_dist, max_dist;   /* GetMinDistanceInvariance() / GetMaxDistanceInvariance() */
+    int32_t assoc_idx;          /* Frame::hasAssociation(lm): keypoint of this frame already associated with it, or -1 */
+} hyorb_landmark;
+
+/* ProjectionCriterion + DistanceCriterion (MatchCriteria.cpp:13-28, 46-77), Frame::ProjectLandMark / Camera::Project
+ * (Frame.cc:176-180, Camera.cpp:116-153) and Frame::landMarkSizePixels (Frame.cc:296-317) for n landmarks:
+ * queries[i] = the window query _SearchByProjection_ builds (radius = th * size_px / size_ref, FeatureSizeCriterion bounds
+ * frac_smaller/frac_larger * size_px, stereo radius), passed[i] = both landmark criteria hold.  t_kps is only read for
+ * landmarks with assoc_idx >= 0. */
+HYORB_API int hyorb_project_landmarks_host(hyorb_matcher *m, const hyorb_projection *pr, const hyorb_landmark *lms, int n,
+                                           const hyorb_keypoint *t_kps, int nt, float th, float size_ref, float frac_smaller,
+                                           float frac_larger, hyorb_window_query *queries, uint8_t *passed);
+
+/* FeatureMatcher::SearchByProjection(Frame&, landmarks, th) up to (not including) the pointer-ordered associateLandMark loop:
+ * projection and landmark criteria as above, then per passing landmark GetFeaturesInAreaNEW -> PreviouslyMatchedCriterion ->
+ * FeatureSizeCriterion(0.5, 1.5) -> StereoConsistencyCriterion(th) -> BestScoreCriterion(thr = TH_HIGH, ratio), all on the
+ * device in one call.  accepted[i] = landmark i found a keypoint (best_idx[i]); landmarks that fail a landmark criterion
+ * report best_idx = -1.  passed may be NULL. */
+HYORB_API int hyorb_search_by_projection_host(hyorb_matcher *m, const hyorb_projection *pr, const hyorb_landmark *lms,
+                                              const uint8_t *lm_desc, int n, const hyorb_keypoint *t_kps, const uint8_t *t_desc,
+                                              const float *t_uR, const uint8_t *t_matched, int nt, float th, float size_ref,
+                                              float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
+                                              uint8_t *accepted, uint8_t *passed);
+
 /* RotationConsistency + ComputeThreeMaxima (MatchCriteria.cpp:684-767): keep[i] = 1 if match i (angles of the
  * two matched keypoints, pairs in ascending current-index order) falls in one of the 3 dominant rotation bins. */
 HYORB_API int hyorb_rotation_consistency_host(hyorb_matcher *m, const float *angle_prev, const float *angle_curr,

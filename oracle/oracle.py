@@ -41,6 +41,26 @@ WQ_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("r", "<f4"), ("size_lo", "<f4"
                      ("ur", "<f4"), ("ur_radius", "<f4")])
 
 
+LM_DTYPE = np.dtype([("Pw", "<f4", 3), ("size", "<f4"), ("min_dist", "<f4"), ("max_dist", "<f4"), ("assoc_idx", "<i4")])
+
+
+class Projection(C.Structure):
+    """pose + camera of the frame landmarks are projected into (orc_projection)"""
+    _fields_ = [("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3), ("K", C.c_float * 9),
+                ("mbf", C.c_float), ("stereo", C.c_int32), ("bounds", Bounds)]
+
+
+def make_projection(Rcw, tcw, Ow, K, mbf, stereo, bounds, cls=None):
+    pr = (cls or Projection)()
+    pr.Rcw[:] = [float(v) for v in np.asarray(Rcw, np.float32).reshape(9)]
+    pr.tcw[:] = [float(v) for v in np.asarray(tcw, np.float32).reshape(3)]
+    pr.Ow[:] = [float(v) for v in np.asarray(Ow, np.float32).reshape(3)]
+    pr.K[:] = [float(v) for v in np.asarray(K, np.float32).reshape(9)]
+    pr.mbf = float(mbf); pr.stereo = int(stereo)
+    pr.bounds.min_x, pr.bounds.max_x, pr.bounds.min_y, pr.bounds.max_y = [float(v) for v in bounds]
+    return pr
+
+
 def build(force=False):
     """Compile the oracle with gcc (idempotent)."""
     src = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "quadtree_closed_form.c", "Makefile")]
@@ -289,6 +309,18 @@ def match_window(kps, tdesc, t_uR, t_matched, bounds, off, idx, queries, qdesc, 
     if rc != 0:
         raise RuntimeError(f"orc_match_window rc={rc}")
     return bi, b, s, acc
+
+
+def project_landmarks(pr, lms, t_kps, th, size_ref=31.0, frac_smaller=0.5, frac_larger=1.5):
+    """front half of FeatureMatcher::SearchByProjection(Frame&, landmarks, th): (window queries, passed flags)"""
+    lms = np.ascontiguousarray(lms, LM_DTYPE); t_kps = np.ascontiguousarray(t_kps)
+    n = len(lms)
+    q = np.zeros(n, WQ_DTYPE); passed = np.zeros(n, np.uint8)
+    rc = lib().orc_project_landmarks(C.byref(pr), _p(lms), n, _p(t_kps), len(t_kps), C.c_float(th), C.c_float(size_ref),
+                                     C.c_float(frac_smaller), C.c_float(frac_larger), _p(q), _p(passed))
+    if rc != 0:
+        raise RuntimeError(f"orc_project_landmarks rc={rc}")
+    return q, passed
 
 
 def rotation_consistency(angle_prev, angle_curr):

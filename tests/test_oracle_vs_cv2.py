@@ -71,3 +71,68 @@ def test_fast_atan2_matches_cv2():
 
 def test_umax_table():
     assert O.umax().tolist() == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+
+
+def _scene(seed, n=400, stereo=True):
+    """a frame pose, a KITTI-like camera and landmarks in front of / behind / beside it"""
+    rng = np.random.default_rng(seed)
+    a, b, c = rng.normal(0, 0.2, 3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    Rcw = (Rx @ Ry @ Rz).astype(np.float32)
+    tcw = rng.normal(0, 2, 3).astype(np.float32)
+    Ow = (-cv2.gemm(np.ascontiguousarray(Rcw.T), tcw.reshape(3, 1), 1.0, None, 0.0)).reshape(3)      # Frame: mOw = -mRcw.t()*mtcw
+    K = np.array([[718.856, 0, 607.19], [0, 718.856, 185.22], [0, 0, 1]], np.float32)
+    lms = np.zeros(n, O.LM_DTYPE)
+    Pc = np.stack([rng.uniform(-30, 30, n), rng.uniform(-10, 10, n), rng.uniform(-5, 60, n)], 1)
+    lms["Pw"] = ((Pc - tcw) @ Rcw).astype(np.float32)         # Rcw^T (Pc - tcw)
+    lms["size"] = rng.uniform(0.05, 1.5, n).astype(np.float32)
+    lms["min_dist"] = rng.uniform(0.5, 10, n).astype(np.float32)
+    lms["max_dist"] = rng.uniform(20, 80, n).astype(np.float32)
+    lms["assoc_idx"] = -1
+    return Rcw, tcw, Ow.astype(np.float32), K, 386.1448, stereo, (0.0, 1241.0, 0.0, 376.0), lms
+
+
+def _project_cv2(Rcw, tcw, K, mbf, stereo, bounds, P):
+    """Frame::ProjectLandMark + Camera::Project written with the cv2 calls the reference's cv::Mat expressions turn into"""
+    Pc = cv2.gemm(Rcw, P.reshape(3, 1).astype(np.float32), 1.0, tcw.reshape(3, 1), 1.0)
+    PcZ = np.float32(Pc[2, 0])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        invz = np.float32(1.0) / PcZ
+        Pch = np.array([[Pc[0, 0] / PcZ], [Pc[1, 0] / PcZ], [Pc[2, 0] / PcZ]], np.float32)
+        uv = cv2.gemm(K, Pch, 1.0, None, 0.0)
+        u, v = np.float32(uv[0, 0]), np.float32(uv[1, 0])
+        ur = np.float32(u - np.float32(np.float32(mbf) * invz)) if stereo else np.float32(-1.0)
+    valid = bool(PcZ > 0 and bounds[0] <= u <= bounds[1] and bounds[2] <= v <= bounds[3])
+    return u, v, ur, valid
+
+
+@pytest.mark.parametrize("seed,stereo", [(0, True), (1, False), (2, True)])
+def test_landmark_projection_matches_cv2_expressions(seed, stereo):
+    """pins the fp32 policy of orc_project_landmarks (gemm small-matrix path, norm in double) against cv2.gemm / cv2.norm"""
+    Rcw, tcw, Ow, K, mbf, st, bounds, lms = _scene(seed, stereo=stereo)
+    kps = np.zeros(5, O.KP_DTYPE); kps["size"] = [31, 37, 44, 53, 64]
+    lms["assoc_idx"][::9] = np.arange(len(lms[::9])) % 5
+    pr = O.make_projection(Rcw, tcw, Ow, K, mbf, st, bounds)
+    th = 3.0
+    q, passed = O.project_landmarks(pr, lms, kps, th)
+    f = np.float32
+    for i, lm in enumerate(lms):
+        u, v, ur, valid = _project_cv2(Rcw, tcw, K, mbf, st, bounds, lm["Pw"])
+        PO = (lm["Pw"] - Ow).astype(np.float32)
+        dist = f(cv2.norm(PO.reshape(3, 1)))
+        ok = valid and not (dist < lm["min_dist"] or dist > lm["max_dist"])
+        if lm["assoc_idx"] >= 0:
+            size_px = f(kps["size"][lm["assoc_idx"]])
+        else:
+            half = f(lm["size"] / f(2))
+            Lp = lm["Pw"].copy(); Lp[0] = f(Lp[0] - half)
+            Rp = lm["Pw"].copy(); Rp[0] = f(Rp[0] + half)
+            size_px = f(_project_cv2(Rcw, tcw, K, mbf, st, bounds, Rp)[0] - _project_cv2(Rcw, tcw, K, mbf, st, bounds, Lp)[0])
+        radius = f(f(f(th) * size_px) / f(31.0))
+        want = (u, v, radius, f(f(0.5) * size_px), f(f(1.5) * size_px), ur, radius if st else f(-1.0))
+        got = tuple(q[i][k] for k in ("u", "v", "r", "size_lo", "size_hi", "ur", "ur_radius"))
+        same = all((np.isnan(a) and np.isnan(b)) or a == b for a, b in zip(got, want))
+        assert same and bool(passed[i]) == ok, (i, got, want, passed[i], ok)
+    assert 0.1 < passed.mean() < 0.9
