@@ -17,7 +17,7 @@ namespace hyorb {
 #ifndef HYORB_RS_ROWS
 #define HYORB_RS_ROWS 8
 #endif
-constexpr int RS_BX = 64, RS_BY = 4, RS_ROWS = HYORB_RS_ROWS;
+constexpr int RS_THREADS = 256, RS_ROWS = HYORB_RS_ROWS;
 
 struct HRow { uint32_t h[4]; };      // horizontal values, already >> 4
 struct RowW { uint32_t A, B; };      // bytes s0 .. s0+7 of a source row
@@ -50,16 +50,21 @@ __device__ __forceinline__ HRow hrow(const RowW &w, const uint32_t (&sel)[4], co
     return r;
 }
 
-__global__ void __launch_bounds__(RS_BX * RS_BY)
+__global__ void __launch_bounds__(RS_THREADS)
 k_resize(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride, int sw, int sh,
          uint8_t *__restrict__ dst, int dpitch, unsigned long long dstride, int dw, int dh,
-         const ResizeTab *__restrict__ tx, const ResizeTab *__restrict__ ty, int area2x)
+         const ResizeTab *__restrict__ tx, const ResizeTab *__restrict__ ty, int area2x, int nx, int ny, int total)
 {
-    const int x4 = (blockIdx.x * RS_BX + threadIdx.x) * 4;
-    const int y0 = (blockIdx.y * RS_BY + threadIdx.y) * RS_ROWS;
-    if (x4 >= dw || y0 >= dh) return;
-    const uint8_t *s = src + (size_t)blockIdx.z * sstride;
-    uint8_t *d = dst + (size_t)blockIdx.z * dstride + x4;
+    // flat strip index -> (image, strip row, strip column), columns fastest: neighbouring threads read neighbouring words, and no
+    // thread of the grid is idle whatever the level's shape (the narrow upper levels wasted a third of a 2-D grid's threads)
+    const int item = blockIdx.x * RS_THREADS + threadIdx.x;
+    if (item >= total) return;
+    const int per = nx * ny;
+    const int b = item / per, rem = item - b * per;
+    const int syi = rem / nx, sxi = rem - syi * nx;
+    const int x4 = sxi * 4, y0 = syi * RS_ROWS;
+    const uint8_t *s = src + (size_t)b * sstride;
+    uint8_t *d = dst + (size_t)b * dstride + x4;
     const int y1 = min(y0 + RS_ROWS, dh);
     if (area2x) {
         // cv::resize silently takes the INTER_AREA 2x2 mean when the ratio is exactly 2
@@ -120,9 +125,11 @@ int launch_pyramid(const PlanDev &hp, const PlanDev *, Level0 l0, uint8_t *pyr, 
         const uint8_t *src = (l == 1) ? l0.base : pyr + S.off;
         const int spitch = (l == 1) ? l0.pitch : S.pitch;
         const unsigned long long sstride = (l == 1) ? l0.stride : hp.pyrStride;
-        dim3 blk(RS_BX, RS_BY), grd((D.w + 4 * RS_BX - 1) / (4 * RS_BX), (D.h + RS_BY * RS_ROWS - 1) / (RS_BY * RS_ROWS), B);
-        k_resize<<<grd, blk, 0, st>>>(src, spitch, sstride, S.w, S.h, pyr + D.off, D.pitch, hp.pyrStride, D.w, D.h,
-                                      tabs + D.rsX, tabs + D.rsY, D.area2x);
+        const int nx = (D.w + 3) / 4, ny = (D.h + RS_ROWS - 1) / RS_ROWS;
+        const long long total = (long long)nx * ny * B;
+        if (total > 0x7fffffffLL) { set_error("pyramid level too large for one launch"); return HYORB_EUNSUPPORTED; }
+        k_resize<<<(unsigned)((total + RS_THREADS - 1) / RS_THREADS), RS_THREADS, 0, st>>>(src, spitch, sstride, S.w, S.h, pyr + D.off, D.pitch, hp.pyrStride, D.w, D.h,
+                                                                                      tabs + D.rsX, tabs + D.rsY, D.area2x, nx, ny, (int)total);
         ++*launches;
     }
     HY_CUDA(cudaGetLastError());
