@@ -181,18 +181,12 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         base = __shfl_sync(0xffffffffu, base, 0);
         int pos = base + inc - cnt;
         const int e0 = a_r * FT_SW + 32 * a_seg;
-        uint32_t f = flags;
-        while (f) {             // two corners per trip: the trip count of a warp is that of its busiest lane
-            const int j0 = __ffs(f) - 1;
-            f &= f - 1;
-            s_list[pos] = (uint16_t)(e0 + j0);
-            if (f) {
-                const int j1 = __ffs(f) - 1;
-                f &= f - 1;
-                s_list[pos + 1] = (uint16_t)(e0 + j1);
-            }
-            pos += 2;
-        }
+        // branch-free extraction: every lane walks all 32 bit positions with predicated stores (a data-dependent loop runs at the
+        // pace of the warp's busiest lane and costs several times more instructions)
+        uint16_t *dstp = s_list + pos;
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+            if ((flags >> j) & 1u) *dstp++ = (uint16_t)(e0 + j);
     }
     __syncthreads();
 
