@@ -68,6 +68,7 @@ SYMBOLS = [
     "hyorb_rotation_consistency_host", "hyorb_last_error", "hyorb_version", "hyorb_device_count",
     "hyorb_process_stereo_batch_host", "hyorb_process_stereo_batch_device", "hyorb_extractor_set_profiling",
     "hyorb_extractor_stage_times", "hyorb_extractor_set_pipelining", "hyorb_distinctive_descriptor_host", "hyorb_project_landmarks_host", "hyorb_search_by_projection_host",
+    "hyorb_vocabulary_create", "hyorb_vocabulary_destroy", "hyorb_bow_transform_host", "hyorb_search_by_bow_host",
 ]
 N_STAGES = 6
 STAGE_NAMES = ("pyramid", "fast", "quadtree", "blur", "describe", "stereo")
@@ -138,6 +139,11 @@ def lib():
                                               C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hyorb_rotation_consistency_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hyorb_distinctive_descriptor_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hyorb_vocabulary_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hyorb_vocabulary_destroy.argtypes = [C.c_void_p]
+        L.hyorb_bow_transform_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hyorb_search_by_bow_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                               C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hyorb_project_landmarks_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float,
                                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.hyorb_search_by_projection_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -912,6 +912,122 @@ HYORB_API int hyorb_rotation_consistency_host(hyorb_matcher *m, const float *ang
     return m_sync(m);
 }
 
+struct hyorb_vocabulary {
+    int device = 0, n_nodes = 0, L = 0;
+    DevBuf d_off, d_idx, d_desc, d_word, d_weight;
+};
+
+HYORB_API int hyorb_vocabulary_create(int device, int n_nodes, int L, const int32_t *child_off, const int32_t *child_idx, const uint8_t *node_desc,
+                                      const int32_t *word_of, const float *weight_of, hyorb_vocabulary **out)
+{
+    if (!out) { set_error("null argument"); return HYORB_EINVAL; }
+    *out = nullptr;
+    if (n_nodes < 1 || L < 0 || !child_off || !node_desc || !word_of || !weight_of) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (device < 0 || hyorb_device_count() <= device) { set_error("CUDA device %d not available (no CPU fallback exists)", device); return HYORB_ECUDA; }
+    if (child_off[0] != 0) { set_error("child_off must start at 0"); return HYORB_EINVAL; }
+    for (int i = 0; i < n_nodes; i++)
+        if (child_off[i + 1] < child_off[i]) { set_error("child_off must be non-decreasing"); return HYORB_EINVAL; }
+    const int n_edges = child_off[n_nodes];
+    if (n_edges > 0 && !child_idx) { set_error("null argument"); return HYORB_EINVAL; }
+    for (int e = 0; e < n_edges; e++)
+        if (child_idx[e] <= 0 || child_idx[e] >= n_nodes) { set_error("child_idx[%d] = %d outside 1..%d", e, child_idx[e], n_nodes - 1); return HYORB_EINVAL; }
+    for (int i = 0; i < n_nodes; i++)
+        if (child_off[i + 1] - child_off[i] > (1 << 20)) { set_error("node %d has too many children", i); return HYORB_EUNSUPPORTED; }
+    hyorb_vocabulary *v = new (std::nothrow) hyorb_vocabulary();
+    if (!v) return HYORB_ENOMEM;
+    v->device = device; v->n_nodes = n_nodes; v->L = L;
+    int rc = HYORB_OK;
+    auto up = [&](DevBuf &b, const void *src, size_t bytes) {
+        if (rc) return;
+        rc = b.ensure(std::max<size_t>(bytes, 16));
+        if (!rc && bytes && cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("vocabulary upload failed"); rc = HYORB_ECUDA; }
+    };
+    if (cudaSetDevice(device) != cudaSuccess) rc = HYORB_ECUDA;
+    up(v->d_off, child_off, sizeof(int32_t) * ((size_t)n_nodes + 1));
+    up(v->d_idx, child_idx, sizeof(int32_t) * (size_t)n_edges);
+    up(v->d_desc, node_desc, (size_t)n_nodes * 32);
+    up(v->d_word, word_of, sizeof(int32_t) * (size_t)n_nodes);
+    up(v->d_weight, weight_of, sizeof(float) * (size_t)n_nodes);
+    if (rc) { hyorb_vocabulary_destroy(v); return rc; }
+    *out = v;
+    return HYORB_OK;
+}
+
+HYORB_API int hyorb_vocabulary_destroy(hyorb_vocabulary *v)
+{
+    if (!v) return HYORB_OK;
+    cudaSetDevice(v->device);
+    DevBuf *bufs[] = {&v->d_off, &v->d_idx, &v->d_desc, &v->d_word, &v->d_weight};
+    for (DevBuf *b : bufs) b->release();
+    delete v;
+    return HYORB_OK;
+}
+
+static int m_bow_descend(hyorb_matcher *m, const hyorb_vocabulary *v, const uint8_t *d_desc, int n, int levelsup, DevBuf &word, DevBuf &node, DevBuf &weight)
+{
+    HY_TRY(word.ensure(sizeof(int32_t) * std::max(n, 1)));
+    HY_TRY(node.ensure(sizeof(int32_t) * std::max(n, 1)));
+    HY_TRY(weight.ensure(sizeof(float) * std::max(n, 1)));
+    return launch_bow_descend(v->d_off.as<int32_t>(), v->d_idx.as<int32_t>(), v->d_desc.as<uint8_t>(), v->d_word.as<int32_t>(), v->d_weight.as<float>(),
+                              v->L - levelsup, d_desc, n, word.as<int32_t>(), node.as<int32_t>(), weight.as<float>(), m->stream, &m->launches);
+}
+
+HYORB_API int hyorb_bow_transform_host(hyorb_matcher *m, const hyorb_vocabulary *v, const uint8_t *desc, int n, int levelsup, int32_t *word_id,
+                                       int32_t *node_id, float *weight)
+{
+    HY_TRY(m_prepare(m));
+    if (!v || n < 0) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (v->device != m->device) { set_error("vocabulary lives on device %d, matcher on %d", v->device, m->device); return HYORB_EINVAL; }
+    if (n == 0) return HYORB_OK;
+    if (!desc || !word_id || !node_id || !weight) { set_error("null argument"); return HYORB_EINVAL; }
+    HY_TRY(m_upload(m, m->d_a, desc, (size_t)n * 32));
+    HY_TRY(m_bow_descend(m, v, m->d_a.as<uint8_t>(), n, levelsup, m->d_c, m->d_g, m->d_d));
+    HY_CUDA(cudaMemcpyAsync(word_id, m->d_c.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(node_id, m->d_g.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(weight, m->d_d.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    return m_sync(m);
+}
+
+HYORB_API int hyorb_search_by_bow_host(hyorb_matcher *m, const hyorb_vocabulary *v, const uint8_t *desc1, const uint8_t *mask1, int n1,
+                                       const uint8_t *desc2, const uint8_t *mask2, int n2, int levelsup, int rule, float thr, float ratio,
+                                       int32_t *node1, int32_t *node2, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted)
+{
+    HY_TRY(m_prepare(m));
+    if (!v || n1 < 0 || n2 < 0 || rule < 0 || rule > 2) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (v->device != m->device) { set_error("vocabulary lives on device %d, matcher on %d", v->device, m->device); return HYORB_EINVAL; }
+    if (n1 == 0) return HYORB_OK;
+    if (!desc1 || (n2 > 0 && !desc2) || !best_idx || !best || !second || !accepted) { set_error("null argument"); return HYORB_EINVAL; }
+    HY_TRY(m_upload(m, m->d_a, desc1, (size_t)n1 * 32));
+    HY_TRY(m_upload(m, m->d_b, desc2, (size_t)n2 * 32));
+    if (mask1) HY_TRY(m_upload(m, m->d_k, mask1, (size_t)n1));
+    if (mask2) HY_TRY(m_upload(m, m->d_l, mask2, (size_t)n2));
+    // quantise both sets (words / weights are by-products here)
+    HY_TRY(m_bow_descend(m, v, m->d_a.as<uint8_t>(), n1, levelsup, m->d_c, m->d_g, m->d_d));
+    HY_TRY(m_bow_descend(m, v, m->d_b.as<uint8_t>(), n2, levelsup, m->d_e, m->d_h, m->d_f));
+    const size_t tb = bow_sort_temp_bytes(std::max(n2, 1));
+    HY_TRY(m->d_i.ensure(sizeof(int32_t) * std::max(n2, 1)));          // iota
+    HY_TRY(m->d_j.ensure(sizeof(int32_t) * std::max(n2, 1)));          // sorted node ids of set 2
+    HY_TRY(m->d_cellof.ensure(sizeof(int32_t) * std::max(n2, 1)));     // set-2 feature indices in (node, index) order
+    HY_TRY(m->d_rowtab.ensure(std::max<size_t>(tb, 16)));
+    HY_TRY(m->d_cellcnt.ensure(sizeof(int32_t) * (size_t)n1));         // candidate range begin
+    HY_TRY(m->d_bestd.ensure(sizeof(int32_t) * (size_t)n1));           // candidate range end
+    HY_TRY(m->d_pkey.ensure(sizeof(int32_t) * (size_t)n1));            // best_idx
+    HY_TRY(m->d_psecond.ensure(sizeof(uint16_t) * 2 * (size_t)n1 + (size_t)n1));   // best | second | accepted
+    uint16_t *d_best = m->d_psecond.as<uint16_t>(), *d_sec = d_best + n1;
+    uint8_t *d_acc = (uint8_t *)(d_sec + n1);
+    HY_TRY(launch_bow_match(m->d_a.as<uint8_t>(), mask1 ? m->d_k.as<uint8_t>() : nullptr, m->d_g.as<int32_t>(), n1, m->d_b.as<uint8_t>(),
+                            mask2 ? m->d_l.as<uint8_t>() : nullptr, m->d_h.as<int32_t>(), n2, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(),
+                            m->d_cellof.as<int32_t>(), m->d_rowtab.p, tb, m->d_cellcnt.as<int32_t>(), m->d_bestd.as<int32_t>(), rule, thr, ratio,
+                            m->d_pkey.as<int32_t>(), d_best, d_sec, d_acc, m->stream, &m->launches));
+    HY_CUDA(cudaMemcpyAsync(best_idx, m->d_pkey.p, sizeof(int32_t) * (size_t)n1, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(best, d_best, sizeof(uint16_t) * (size_t)n1, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(second, d_sec, sizeof(uint16_t) * (size_t)n1, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(accepted, d_acc, (size_t)n1, cudaMemcpyDeviceToHost, m->stream));
+    if (node1) HY_CUDA(cudaMemcpyAsync(node1, m->d_g.p, sizeof(int32_t) * (size_t)n1, cudaMemcpyDeviceToHost, m->stream));
+    if (node2 && n2 > 0) HY_CUDA(cudaMemcpyAsync(node2, m->d_h.p, sizeof(int32_t) * (size_t)n2, cudaMemcpyDeviceToHost, m->stream));
+    return m_sync(m);
+}
+
 HYORB_API int hyorb_distinctive_descriptor_host(hyorb_matcher *m, const uint8_t *desc, const int32_t *lm_off, int n_landmarks, int32_t *best_idx,
                                                 int32_t *best_median)
 {

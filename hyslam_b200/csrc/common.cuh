@@ -149,6 +149,13 @@ int launch_match_window(const hyorb_keypoint *kps, const uint8_t *tdesc, const f
 int launch_project_landmarks(const hyorb_projection &pr, const hyorb_landmark *lms, int n, const hyorb_keypoint *t_kps, int nt, float th, float size_ref,
                              float frac_smaller, float frac_larger, hyorb_window_query *queries, uint8_t *passed, int *status, cudaStream_t st, long *launches);
 int launch_rotation(const float *a_prev, const float *a_curr, int n, uint8_t *keep, int *status, cudaStream_t st, long *launches);
+int launch_bow_descend(const int32_t *child_off, const int32_t *child_idx, const uint8_t *node_desc, const int32_t *word_of, const float *weight_of,
+                       int nid_level, const uint8_t *desc, int n, int32_t *word_id, int32_t *node_id, float *weight, cudaStream_t st, long *launches);
+size_t bow_sort_temp_bytes(int n);
+int launch_bow_match(const uint8_t *desc1, const uint8_t *mask1, const int32_t *node1, int n1, const uint8_t *desc2, const uint8_t *mask2,
+                     const int32_t *node2, int n2, int32_t *iota, int32_t *sorted_node2, int32_t *sorted_idx2, void *temp, size_t temp_bytes,
+                     int32_t *cbegin, int32_t *cend, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
+                     uint8_t *accepted, cudaStream_t st, long *launches);
 int launch_distinctive(const uint8_t *desc, const int32_t *off, int n_lm, int32_t *best_idx, int32_t *best_median, cudaStream_t st, long *launches);
 size_t stereo_scratch_ints_per_pair(int capacity);
 int launch_stereo(const hyorb_stereo_params &sp, int n_pairs, const hyorb_keypoint *kps, const uint8_t *desc, const int32_t *counts, int capacity,

@@ -13,6 +13,7 @@
 // (distance << 22 | position); second = 2nd order statistic of the distances with multiplicity.  Both merge
 // associatively, so lanes / CTAs scan slices and combine with warp shuffles.
 #include <float.h>
+#include <cub/device/device_radix_sort.cuh>
 #include "common.cuh"
 
 namespace hyorb {
@@ -477,6 +478,121 @@ int launch_distinctive(const uint8_t *desc, const int32_t *off, int n_lm, int32_
     if (n_lm <= 0) return HYORB_OK;
     k_distinctive<<<(n_lm + DD_WARPS - 1) / DD_WARPS, DD_WARPS * 32, 0, st>>>((const uint4 *)desc, off, n_lm, best_idx, best_median);
     ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+// ---------------- bag-of-words quantisation and BoW-gated matching
+// DBoW2::TemplatedVocabulary::transform as called by ORBVocabulary::transform (src/features/low_level/ORBVocabulary.cpp:31-42):
+// one warp per feature descends the vocabulary tree; at every level the lanes take one child each (k <= 32 per pass), Hamming
+// distance to the child's descriptor, warp argmin with the child's list position as tie-break (DBoW2 keeps the first minimum).
+__global__ void __launch_bounds__(256)
+k_bow_descend(const int32_t *__restrict__ child_off, const int32_t *__restrict__ child_idx, const uint4 *__restrict__ node_desc,
+              const int32_t *__restrict__ word_of, const float *__restrict__ weight_of, int nid_level, const uint4 *__restrict__ desc, int n,
+              int32_t *__restrict__ word_id, int32_t *__restrict__ node_id, float *__restrict__ weight)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const uint4 a0 = desc[2 * (size_t)i], a1 = desc[2 * (size_t)i + 1];
+    int node = 0, level = 0, nid = nid_level <= 0 ? 0 : -1;
+    while (true) {
+        const int lo = child_off[node], hi = child_off[node + 1];
+        if (hi <= lo || level > 64) break;
+        ++level;
+        uint32_t key = 0xFFFFFFFFu;
+        for (int c = lo + lane; c < hi; c += 32) {
+            const int id = child_idx[c];
+            const uint32_t d = (uint32_t)hamming256(a0, a1, node_desc[2 * (size_t)id], node_desc[2 * (size_t)id + 1]);
+            key = min(key, (d << 20) | (uint32_t)(c - lo));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+        node = child_idx[lo + (int)(key & 0xFFFFFu)];
+        if (level == nid_level) nid = node;
+    }
+    if (lane == 0) { word_id[i] = word_of[node]; weight[i] = weight_of[node]; node_id[i] = nid >= 0 ? nid : node; }
+}
+
+// candidate ranges of BoW-gated matching: features of keyframe 2 sorted by (node, index) -> for every feature of keyframe 1 the
+// run of keyframe-2 features under the same node (FeatureMatcher::_SearchByBoW_'s merge walk, FeatureMatcher.cc:281-345)
+__global__ void k_bow_ranges(const int32_t *__restrict__ node1, int n1, const int32_t *__restrict__ sorted_node2, int n2,
+                             int32_t *__restrict__ cbegin, int32_t *__restrict__ cend)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const int key = node1[i];
+    int lo = 0, hi = n2;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted_node2[mid] < key) lo = mid + 1; else hi = mid; }
+    const int b = lo;
+    hi = n2;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted_node2[mid] <= key) lo = mid + 1; else hi = mid; }
+    cbegin[i] = b; cend[i] = lo;
+}
+__global__ void k_iota(int32_t *v, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) v[i] = i; }
+
+// one warp per query over the candidate run idx[cbegin[q] .. cend[q]) (shared by all queries under the same node); mask1 / mask2:
+// the BoWIndexCriterion filters (0 = not eligible), may be NULL
+__global__ void __launch_bounds__(256)
+k_match_ranges(const uint4 *__restrict__ q, const uint8_t *__restrict__ mask1, int nq, const uint4 *__restrict__ t, const uint8_t *__restrict__ mask2,
+               const int32_t *__restrict__ cbegin, const int32_t *__restrict__ cend, const int32_t *__restrict__ idx, int rule, float thr,
+               float ratio, int32_t *best_idx, uint16_t *best, uint16_t *sec, uint8_t *accepted)
+{
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    uint32_t bkey = KEY_NONE; int second = DIST_NONE;
+    const int lo = cbegin[qi], hi = (mask1 && !mask1[qi]) ? lo : cend[qi];
+    if (hi > lo) {
+        const uint4 a0 = q[2 * qi], a1 = q[2 * qi + 1];
+        for (int c = lo + lane; c < hi; c += 32) {
+            const int ti = idx[c];
+            if (mask2 && !mask2[ti]) continue;
+            const int d = hamming256(a0, a1, t[2 * (size_t)ti], t[2 * (size_t)ti + 1]);
+            scan_update(bkey, second, d, (uint32_t)(c - lo) & POS_MASK);
+        }
+    }
+    warp_merge(bkey, second);
+    if (lane == 0) {
+        const int bt = bkey != KEY_NONE ? idx[lo + (int)(bkey & POS_MASK)] : -1;
+        write_result(qi, bkey, second, bt, rule, thr, ratio, best_idx, best, sec, accepted);
+    }
+}
+
+int launch_bow_descend(const int32_t *child_off, const int32_t *child_idx, const uint8_t *node_desc, const int32_t *word_of, const float *weight_of,
+                       int nid_level, const uint8_t *desc, int n, int32_t *word_id, int32_t *node_id, float *weight, cudaStream_t st, long *launches)
+{
+    if (n <= 0) return HYORB_OK;
+    k_bow_descend<<<(n + 7) / 8, 256, 0, st>>>(child_off, child_idx, (const uint4 *)node_desc, word_of, weight_of, nid_level, (const uint4 *)desc, n,
+                                               word_id, node_id, weight);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+size_t bow_sort_temp_bytes(int n)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr, (const int32_t *)nullptr, (int32_t *)nullptr, n);
+    return bytes;
+}
+
+// node2 -> (sorted_node2, sorted_idx2) by a stable radix sort (index order inside a node, as FeatureVector::addFeature appends), then ranges + scan
+int launch_bow_match(const uint8_t *desc1, const uint8_t *mask1, const int32_t *node1, int n1, const uint8_t *desc2, const uint8_t *mask2,
+                     const int32_t *node2, int n2, int32_t *iota, int32_t *sorted_node2, int32_t *sorted_idx2, void *temp, size_t temp_bytes,
+                     int32_t *cbegin, int32_t *cend, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
+                     uint8_t *accepted, cudaStream_t st, long *launches)
+{
+    if (n1 <= 0) return HYORB_OK;
+    if (n2 > 0) {
+        k_iota<<<(n2 + 255) / 256, 256, 0, st>>>(iota, n2);
+        HY_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, node2, sorted_node2, iota, sorted_idx2, n2, 0, 32, st));
+        *launches += 2;
+    }
+    k_bow_ranges<<<(n1 + 255) / 256, 256, 0, st>>>(node1, n1, sorted_node2, n2, cbegin, cend);
+    k_match_ranges<<<(n1 + 7) / 8, 256, 0, st>>>((const uint4 *)desc1, mask1, n1, (const uint4 *)desc2, mask2, cbegin, cend, sorted_idx2, rule, thr, ratio,
+                                                 best_idx, best, second, accepted);
+    *launches += 2;
     HY_CUDA(cudaGetLastError());
     return HYORB_OK;
 }

@@ -60,6 +60,52 @@ class Stereomatcher(_Handle):
                                                         d_uR, d_depth, d_best_r, d_best_dist))
 
 
+class Vocabulary:
+    """Device-resident bag-of-words tree (the role of HYSLAM::ORBVocabulary / DBoW2::TemplatedVocabulary,
+    src/features/low_level/ORBVocabulary.cpp).  ``tree``: dict(L, child_off, child_idx, node_desc, word_of, weight_of); node 0 = root."""
+
+    def __init__(self, tree, device=0):
+        self.tree = tree
+        self.L = int(tree["L"])
+        co = np.ascontiguousarray(tree["child_off"], np.int32); ci = np.ascontiguousarray(tree["child_idx"], np.int32)
+        nd = np.ascontiguousarray(tree["node_desc"], np.uint8); wo = np.ascontiguousarray(tree["word_of"], np.int32)
+        wt = np.ascontiguousarray(tree["weight_of"], np.float32)
+        self._h = C.c_void_p()
+        F.check(F.lib().hyorb_vocabulary_create(int(device), len(co) - 1, self.L, F.ptr(co), F.ptr(ci), F.ptr(nd), F.ptr(wo), F.ptr(wt), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            F.lib().hyorb_vocabulary_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    @staticmethod
+    def random_tree(k, L, seed, shrink=0.0):
+        """Stand-in vocabulary (the reference's ORBvoc file is not part of its tree): complete k-ary tree of depth L in breadth-first
+        order with seeded random node descriptors; ``shrink`` removes that fraction of the children lists' tails to exercise
+        ragged trees.  Leaves get consecutive word ids and positive weights."""
+        rng = np.random.default_rng(seed)
+        cnt_list, frontier, n_nodes = [], 1, 1          # breadth-first: cnt_list[i] = number of children of node i
+        for d in range(L):
+            nxt = 0
+            for _ in range(frontier):
+                kk = k if rng.random() >= shrink else max(1, int(rng.integers(1, k + 1)))
+                cnt_list.append(kk); nxt += kk
+            n_nodes += nxt
+            frontier = nxt
+        cnt = np.zeros(n_nodes, np.int32)
+        cnt[: len(cnt_list)] = cnt_list
+        off = np.zeros(n_nodes + 1, np.int32)
+        off[1:] = np.cumsum(cnt)
+        idx = np.arange(1, n_nodes, dtype=np.int32)        # breadth-first numbering: the children of consecutive parents are consecutive
+        node_desc = rng.integers(0, 256, (n_nodes, 32), dtype=np.uint8)
+        leaf = cnt == 0
+        word_of = np.full(n_nodes, -1, np.int32); word_of[leaf] = np.arange(int(leaf.sum()), dtype=np.int32)
+        weight_of = np.zeros(n_nodes, np.float32); weight_of[leaf] = rng.uniform(0.1, 5.0, int(leaf.sum())).astype(np.float32)
+        return dict(L=L, child_off=off, child_idx=idx, node_desc=node_desc, word_of=word_of, weight_of=weight_of)
+
+
 class FeatureMatcher(_Handle):
     """The data-parallel inner loops of HYSLAM::FeatureMatcher: candidate enumeration (grid window / explicit CSR
     lists), Hamming scan, best / second-best, acceptance rule, rotation histogram.  Landmark projection and map
@@ -158,6 +204,52 @@ class FeatureMatcher(_Handle):
                                                         F.ptr(t_matched), len(t_kps), float(th), float(size_ref), thr, ratio, F.ptr(bi), F.ptr(b),
                                                         F.ptr(s), F.ptr(acc), F.ptr(passed)))
         return bi, b, s, acc, passed
+
+    def BowTransform(self, vocab, desc, levelsup=4):
+        """ORBVocabulary::transform (ORBVocabulary.cpp:31-42) per feature: (word_id, node_id at level L - levelsup, weight).
+        ``feature_vector(node_id)`` / ``bow_vector(word_id, weight)`` assemble DBoW2's two containers from them."""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        w = np.full(n, -1, np.int32); nid = np.full(n, -1, np.int32); wt = np.zeros(n, np.float32)
+        F.check(F.lib().hyorb_bow_transform_host(self._h, vocab._h, F.ptr(desc), n, int(levelsup), F.ptr(w), F.ptr(nid), F.ptr(wt)))
+        return w, nid, wt
+
+    @staticmethod
+    def feature_vector(node_id):
+        """DBoW2::FeatureVector as CSR: (sorted unique node ids, offsets, feature indices in index order inside a node)"""
+        order = np.argsort(node_id, kind="stable").astype(np.int32)
+        nodes, start = np.unique(np.asarray(node_id)[order], return_index=True)
+        return nodes, np.append(start, len(order)).astype(np.int32), order
+
+    @staticmethod
+    def bow_vector(word_id, weight):
+        """DBoW2::BowVector for TF_IDF weighting + L1 normalisation (the ORB vocabulary's settings): {word: weight}"""
+        acc = {}
+        for w, x in zip(word_id.tolist(), weight.tolist()):
+            if x > 0:
+                acc[w] = acc.get(w, 0.0) + x
+        if acc:
+            nd = float(len(acc))
+            acc = {w: x / nd for w, x in acc.items()}
+            norm = sum(abs(x) for x in acc.values())
+            if norm > 0:
+                acc = {w: x / norm for w, x in acc.items()}
+        return acc
+
+    def SearchByBoW(self, vocab, desc1, desc2, mask1=None, mask2=None, levelsup=4, rule=F.RULE_BOW, thr=None, ratio=None):
+        """FeatureMatcher::_SearchByBoW_ / SearchForTriangulation (FeatureMatcher.cc:281-345, 373-402) with the DBoW2 gating on the
+        device.  Returns (best_idx, best, second, accepted, node1, node2)."""
+        d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        m1 = None if mask1 is None else np.ascontiguousarray(mask1, np.uint8)
+        m2 = None if mask2 is None else np.ascontiguousarray(mask2, np.uint8)
+        thr = float(self.settings.TH_LOW if thr is None else thr)
+        ratio = float(self.settings.nnratio if ratio is None else ratio)
+        n1, n2 = len(d1), len(d2)
+        bi, b, s, acc = self._outs(n1)
+        node1 = np.full(n1, -1, np.int32); node2 = np.full(max(n2, 1), -1, np.int32)
+        F.check(F.lib().hyorb_search_by_bow_host(self._h, vocab._h, F.ptr(d1), F.ptr(m1), n1, F.ptr(d2), F.ptr(m2), n2, int(levelsup), int(rule),
+                                                 thr, ratio, F.ptr(node1), F.ptr(node2), F.ptr(bi), F.ptr(b), F.ptr(s), F.ptr(acc)))
+        return bi, b, s, acc, node1, node2[:n2]
 
     def ComputeDistinctiveDescriptors(self, desc, lm_off):
         """MapPointDBEntry::_computeDistinctiveDescriptor_ (src/core/MapPointDB.cpp:127-171) for many landmarks at once.

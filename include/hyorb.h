@@ -270,6 +270,32 @@ HYORB_API int hyorb_search_by_projection_host(hyorb_matcher *m, const hyorb_proj
 HYORB_API int hyorb_rotation_consistency_host(hyorb_matcher *m, const float *angle_prev, const float *angle_curr,
                                               int n, uint8_t *keep);
 
+/* Bag-of-words vocabulary tree, resident on the device.  hySLAM reaches it through DBoW2 (ORBVocabulary::transform,
+ * src/features/low_level/ORBVocabulary.cpp:31-42; Frame::ComputeBoW, src/core/Frame.cc:472-479, levelsup = 4); DBoW2 and its
+ * vocabulary file are not part of the reference tree, so the tree is handed over explicitly: node 0 = root, children of node i =
+ * child_idx[child_off[i] .. child_off[i+1]) in DBoW2's child order, node_desc = 32 bytes per node (the root's are ignored),
+ * word_of[i] = word id of a leaf (-1 for inner nodes), weight_of[i] = its weight, L = depth of the leaves. */
+typedef struct hyorb_vocabulary hyorb_vocabulary;
+HYORB_API int hyorb_vocabulary_create(int device, int n_nodes, int L, const int32_t *child_off, const int32_t *child_idx,
+                                      const uint8_t *node_desc, const int32_t *word_of, const float *weight_of, hyorb_vocabulary **out);
+HYORB_API int hyorb_vocabulary_destroy(hyorb_vocabulary *v);
+
+/* DBoW2::TemplatedVocabulary::transform per feature: descend the tree taking the child with the smallest Hamming distance at
+ * every level (first child wins ties), word_id / weight = the leaf reached, node_id = the node passed at level L - levelsup
+ * (the key of DBoW2::FeatureVector; 0 = root when L - levelsup <= 0). */
+HYORB_API int hyorb_bow_transform_host(hyorb_matcher *m, const hyorb_vocabulary *v, const uint8_t *desc, int n, int levelsup,
+                                       int32_t *word_id, int32_t *node_id, float *weight);
+
+/* FeatureMatcher::_SearchByBoW_ / SearchForTriangulation (FeatureMatcher.cc:281-345, 373-402) with the candidate gating on the
+ * device: both descriptor sets are quantised, the features of set 2 are grouped by node (index order inside a node, as
+ * FeatureVector::addFeature appends them), and every feature of set 1 scans the set-2 features under its own node with the
+ * acceptance rule `rule`.  mask1 / mask2 (may be NULL): the BoWIndexCriterion filters, 0 = feature not eligible.
+ * node1 / node2 (may be NULL) return the node ids. */
+HYORB_API int hyorb_search_by_bow_host(hyorb_matcher *m, const hyorb_vocabulary *v, const uint8_t *desc1, const uint8_t *mask1, int n1,
+                                       const uint8_t *desc2, const uint8_t *mask2, int n2, int levelsup, int rule, float thr,
+                                       float ratio, int32_t *node1, int32_t *node2, int32_t *best_idx, uint16_t *best,
+                                       uint16_t *second, uint8_t *accepted);
+
 /* Representative descriptor of a landmark: MapPointDBEntry::_computeDistinctiveDescriptor_ (src/core/MapPointDB.cpp:127-171).
  * desc: the observation descriptors of all landmarks back to back (32 bytes each); lm_off[n_landmarks + 1]: CSR offsets
  * (rows of landmark l = lm_off[l] .. lm_off[l+1]).  Per landmark: all-pairs Hamming distances, per-row order statistic

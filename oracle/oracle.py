@@ -323,6 +323,21 @@ def project_landmarks(pr, lms, t_kps, th, size_ref=31.0, frac_smaller=0.5, frac_
     return q, passed
 
 
+def bow_transform(vocab, desc, levelsup=4):
+    """DBoW2 TemplatedVocabulary::transform per feature (published algorithm; see orb_oracle.c): (word_id, node_id, weight).
+    vocab: dict(L, child_off, child_idx, node_desc, word_of, weight_of)."""
+    desc = np.ascontiguousarray(desc, np.uint8)
+    n = len(desc)
+    co = np.ascontiguousarray(vocab["child_off"], np.int32); ci = np.ascontiguousarray(vocab["child_idx"], np.int32)
+    nd = np.ascontiguousarray(vocab["node_desc"], np.uint8); wo = np.ascontiguousarray(vocab["word_of"], np.int32)
+    wt = np.ascontiguousarray(vocab["weight_of"], np.float32)
+    w = np.empty(n, np.int32); nid = np.empty(n, np.int32); wgt = np.empty(n, np.float32)
+    rc = lib().orc_bow_transform(len(co) - 1, int(vocab["L"]), _p(co), _p(ci), _p(nd), _p(wo), _p(wt), _p(desc), n, int(levelsup), _p(w), _p(nid), _p(wgt))
+    if rc != 0:
+        raise RuntimeError(f"orc_bow_transform rc={rc}")
+    return w, nid, wgt
+
+
 def rotation_consistency(angle_prev, angle_curr):
     a = np.ascontiguousarray(angle_prev, np.float32); b = np.ascontiguousarray(angle_curr, np.float32)
     keep = np.empty(len(a), np.uint8)

@@ -1,0 +1,116 @@
+"""Bag-of-words quantisation and BoW-gated matching.  DBoW2 and its vocabulary are not part of the
+reference tree (un-vendored dependency, missing ORBvoc file): the oracle restates DBoW2's PUBLISHED transform algorithm and
+parity is UNPINNED by the reference for this function; what is checked is oracle == literal Python restatement (CPU) and
+CUDA == oracle on seeded stand-in vocabularies (GPU), including the candidate gating of _SearchByBoW_."""
+import numpy as np
+import pytest
+
+from hyslam_b200 import synth
+from hyslam_b200.matcher import Vocabulary
+from oracle import oracle as O
+
+
+def _features(tree, n, seed):
+    """descriptors near random leaves of the tree (a few flipped bits) plus pure noise"""
+    rng = np.random.default_rng(seed)
+    leaves = np.nonzero(tree["word_of"] >= 0)[0]
+    base = tree["node_desc"][rng.choice(leaves, n)]
+    bits = np.unpackbits(base, axis=1)
+    flips = rng.random(bits.shape) < 0.08
+    out = np.packbits(bits ^ flips, axis=1)
+    out[::9] = rng.integers(0, 256, (len(out[::9]), 32), dtype=np.uint8)
+    return out
+
+
+def _literal_transform(tree, d, levelsup):
+    pop = lambda a, b: int(np.unpackbits(a ^ b).sum())
+    node, level, nid = 0, 0, (0 if tree["L"] - levelsup <= 0 else -1)
+    co, ci = tree["child_off"], tree["child_idx"]
+    while co[node + 1] > co[node]:
+        level += 1
+        kids = ci[co[node]:co[node + 1]]
+        best, best_d = kids[0], pop(d, tree["node_desc"][kids[0]])
+        for k in kids[1:]:
+            dd = pop(d, tree["node_desc"][k])
+            if dd < best_d:
+                best, best_d = k, dd
+        node = int(best)
+        if level == tree["L"] - levelsup:
+            nid = node
+    return int(tree["word_of"][node]), (nid if nid >= 0 else node), float(tree["weight_of"][node])
+
+
+def test_oracle_matches_literal_descent():
+    tree = Vocabulary.random_tree(5, 4, 3, shrink=0.3)
+    f = _features(tree, 60, 1)
+    for levelsup in (0, 2, 4, 7):
+        w, nid, wt = O.bow_transform(tree, f, levelsup)
+        for i in range(len(f)):
+            assert (int(w[i]), int(nid[i]), float(wt[i])) == _literal_transform(tree, f[i], levelsup)
+    # every feature ends in a leaf; nodes at level L - levelsup have that depth
+    assert (w >= 0).all()
+
+
+def _search_reference(tree, d1, d2, m1, m2, levelsup, rule, thr, ratio):
+    """_SearchByBoW_ by composition of oracle pieces: quantise, group set 2 by node (index order), explicit CSR lists"""
+    _, n1, _ = O.bow_transform(tree, d1, levelsup)
+    _, n2, _ = O.bow_transform(tree, d2, levelsup)
+    order = np.argsort(n2, kind="stable")
+    if m2 is not None:
+        order = order[m2[order] != 0]
+    keys = n2[order]
+    off, idx = [0], []
+    for i in range(len(d1)):
+        if m1 is None or m1[i]:
+            lo, hi = np.searchsorted(keys, n1[i], "left"), np.searchsorted(keys, n1[i], "right")
+            idx += order[lo:hi].tolist()
+        off.append(len(idx))
+    return O.match_csr(d1, d2, np.array(off, np.int32), np.array(idx if idx else [0], np.int32), mode=rule, thr=thr, ratio=ratio), n1, n2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,L,shrink,levelsup", [(10, 4, 0.0, 2), (6, 5, 0.4, 4), (40, 2, 0.2, 1), (3, 3, 0.0, 5)])
+def test_gpu_transform_matches_oracle(k, L, shrink, levelsup):
+    import hyslam_b200 as hb
+    tree = Vocabulary.random_tree(k, L, 10 * k + L, shrink=shrink)
+    f = _features(tree, 3000, 2)
+    v = Vocabulary(tree)
+    m = hb.FeatureMatcher()
+    w, nid, wt = m.BowTransform(v, f, levelsup)
+    ow, onid, owt = O.bow_transform(tree, f, levelsup)
+    assert np.array_equal(w, ow) and np.array_equal(nid, onid) and np.array_equal(wt, owt)
+    nodes, off, order = m.feature_vector(nid)
+    assert off[-1] == len(f) and (np.diff(nodes) > 0).all()
+    bv = m.bow_vector(w, wt)
+    assert abs(sum(bv.values()) - 1.0) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,with_masks", [(0, False), (1, True)])
+def test_gpu_search_by_bow_matches_oracle_composition(seed, with_masks):
+    import hyslam_b200 as hb
+    tree = Vocabulary.random_tree(10, 4, 77)
+    rng = np.random.default_rng(seed)
+    d1 = _features(tree, 2500, 3 + seed)
+    d2, _ = synth.perturbed_descriptors(d1, 5 + seed, max_flips=30)
+    m1 = (rng.random(len(d1)) < 0.8).astype(np.uint8) if with_masks else None
+    m2 = (rng.random(len(d2)) < 0.8).astype(np.uint8) if with_masks else None
+    v = Vocabulary(tree)
+    m = hb.FeatureMatcher()
+    bi, b, s, acc, n1, n2 = m.SearchByBoW(v, d1, d2, m1, m2, levelsup=2, rule=1, thr=50.0, ratio=0.6)
+    (obi, ob, osd, oacc), on1, on2 = _search_reference(tree, d1, d2, m1, m2, 2, 1, 50.0, 0.6)
+    assert np.array_equal(n1, on1) and np.array_equal(n2, on2)
+    for g, w_, name in zip((bi, b, s, acc), (obi, ob, osd, oacc), ("best_idx", "best", "second", "accepted")):
+        assert np.array_equal(g, w_), name
+    assert acc.sum() > 200
+
+
+@pytest.mark.gpu
+def test_vocabulary_errors():
+    import hyslam_b200 as hb
+    from hyslam_b200 import _ffi as F
+    tree = Vocabulary.random_tree(3, 2, 1)
+    bad = dict(tree); bad["child_idx"] = tree["child_idx"].copy(); bad["child_idx"][0] = 999
+    with pytest.raises(hb.HyorbError) as e:
+        Vocabulary(bad)
+    assert e.value.rc == F.EINVAL
