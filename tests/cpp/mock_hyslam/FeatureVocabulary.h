@@ -1,3 +1,2 @@
-// TEST DOUBLE: opaque stand-in for hySLAM's FeatureVocabulary (DBoW2-backed, out of scope).
-#pragma once
-namespace HYSLAM { class FeatureVocabulary {}; }
+// forwards to the test doubles (tests/cpp/mock_hyslam/hyslam_test_doubles.hpp); not a hySLAM source file
+#include "hyslam_test_doubles.hpp"
