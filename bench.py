@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--rotate", type=int, default=4, help="distinct device-resident batches cycled so inputs exceed L2")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-workers", type=int, default=2, help="host threads (one extractor handle each) of the end-to-end leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -292,7 +293,7 @@ def main():
     torch.cuda.synchronize()
     dt1 = time.perf_counter() - t0
 
-    n_workers = 2
+    n_workers = max(1, args.e2e_workers)
     workers = [(ex, outs)]
     keep = []
     for _ in range(n_workers - 1):
@@ -309,7 +310,7 @@ def main():
         try:
             torch.cuda.set_device(local)
             start.wait()
-            for i in range(wi, 2 * e2e_steps, n_workers):
+            for i in range(wi, n_workers * e2e_steps, n_workers):
                 exw.process_stereo_batch(pinned[i % len(pinned)].numpy(), cam, capacity=cap, out=ow)
         except Exception as e:                      # surfaced after the join
             errs.append(e)
@@ -331,7 +332,7 @@ def main():
     if dist is not None:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     e2e_single = world * P * e2e_steps / float(tm[0].item())
-    e2e_value = world * P * 2 * e2e_steps / float(tm[1].item())
+    e2e_value = world * P * n_workers * e2e_steps / float(tm[1].item())
     d2h = sum(o.nbytes for o in outs)
 
     if rank != 0:
@@ -436,8 +437,8 @@ def main():
                    "l2": f"{args.rotate} distinct device-resident input batches cycled ({args.rotate * in_bytes / 1e6:.0f} MB of inputs > 126 MB L2); "
                          f"per-step intermediates ({B} pyramids + blurred copies) also exceed L2"},
         "kpts_per_sec": value * kp_per_step / P, "keypoints_per_frame": kp_per_step / P, "stereo_matches_per_frame": matched / P,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h, "steps": 2 * e2e_steps,
-                "api": "hyorb_process_stereo_batch_host (pinned host buffers in and out), 2 host threads with one extractor handle each",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h, "steps": n_workers * e2e_steps,
+                "api": f"hyorb_process_stereo_batch_host (pinned host buffers in and out), {n_workers} host threads with one extractor handle each",
                 "single_handle_value": e2e_single},
         "gpu_launches": int(launches), "roofline": roofline, "stages": stages, "c4_match": c4, "cpu_baseline": cpu, "clocks": clocks,
     }
