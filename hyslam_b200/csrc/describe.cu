@@ -2,8 +2,8 @@
 // Replaces ORBFinder::compute (src/features/low_level/ORBFinder.cpp:70-78): intensityCentroidAngle (:16-43) and
 // computeOrbDescriptor (:89-129), both evaluated on the BLURRED level (ORBExtractor.cpp:536-541), and
 // the tail of ORBExtractor::operator() (:546-561): pt *= scale[level], levels concatenated 0..L-1.
-// One warp per keypoint: lanes 0..30 are the 31 columns of the intensity-centroid disc (integer moments, exact in
-// any order), then lane i evaluates the 8 tests of descriptor byte i.  Floating point follows the reference's
+// One warp per keypoint: lanes 0..30 take one row of the intensity-centroid disc each (integer moments, exact in any
+// order: masked DP4A against the column weights), then lane i evaluates the 8 tests of descriptor byte i.  Floating point follows the reference's
 // x86-64 baseline build: every fp32 operation individually rounded (no FMA contraction), cos/sin in double then
 // narrowed, cvRound = round-half-even.
 #include <float.h>
@@ -62,6 +62,27 @@ constexpr int PT_R = 18;                 // patch radius: |rotated pattern coord
 constexpr int PT_ROWS = 2 * PT_R + 1;    // 37
 constexpr int PT_WORDS = 10;             // 37 columns + up to 3 bytes of alignment slack, as 32-bit words
 
+// byte masks of the disc: row |v| keeps columns |u| <= umax[|v|] (ORBFinder::orientationSetup, ORBFinder.cpp:131-149); word k of a
+// row covers u = -15 + 4k .. -12 + 4k (the 32nd byte, u = 16, is never inside)
+__device__ __forceinline__ uint32_t disc_mask_word(int av, int k)
+{
+    const int umax = av <= 3 ? 15 : av <= 6 ? 14 : av <= 8 ? 13 : av == 9 ? 12 : av == 10 ? 11 : av == 11 ? 10 : av == 12 ? 9 : av == 13 ? 8 : av == 14 ? 6 : 3;
+    uint32_t m = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const int u = -15 + 4 * k + b, au = u < 0 ? -u : u;
+        if (au <= umax) m |= 0xFFu << (8 * b);
+    }
+    return m;
+}
+__device__ __forceinline__ int dp4a_u8_s8(uint32_t a_unsigned, uint32_t b_signed, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_unsigned), "r"(b_signed), "r"(c));
+    return d;
+}
+__host__ __device__ constexpr uint32_t pack_s8(int a, int b, int c, int d) { return (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)b << 8) | ((uint32_t)(uint8_t)c << 16) | ((uint32_t)(uint8_t)d << 24); }
+
 __global__ void __launch_bounds__(DS_WARPS * 32, 5)
 k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, const uint32_t *__restrict__ sel_all,
            const int *__restrict__ selCount, hyorb_keypoint *__restrict__ kps, uint8_t *__restrict__ desc, int capacity,
@@ -70,7 +91,10 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
     // the 37x37 window of the blurred level around the keypoint, one per warp, staged with coalesced 32-bit loads: the
     // 31 disc rows and the 512 rotated-pattern taps then hit shared memory instead of issuing byte gathers to L1
     __shared__ uint32_t s_patch[DS_WARPS][PT_ROWS * PT_WORDS];
+    __shared__ uint32_t s_mask[16][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 128) s_mask[threadIdx.x >> 3][threadIdx.x & 7] = disc_mask_word(threadIdx.x >> 3, threadIdx.x & 7);
+    __syncthreads();
     const int b = blockIdx.y;
     const int k = blockIdx.x * DS_WARPS + warp;
     const int nl = plan->nlevels;
@@ -123,22 +147,26 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
     const uint8_t *center = (const uint8_t *)patch + PT_R * (PT_WORDS * 4) + off + PT_R;
     constexpr int PP = PT_WORDS * 4;      // patch pitch in bytes
 
-    // ---- intensity centroid (ORBFinder.cpp:16-43); umax of ORBFinder::orientationSetup (:131-149)
+    // ---- intensity centroid (ORBFinder.cpp:16-43): lane = disc row v; m10 += sum u*I and m01 += v * sum I over |u| <= umax[|v|]
+    // (ORBFinder::orientationSetup, :131-149) as masked DP4As against the column weights -- integer sums, exact in any order
     int m10 = 0, m01 = 0;
-    const int u = lane - HALF_PATCH;
     if (lane < 31) {
-        const int au = u < 0 ? -u : u;
-        // rows with |v| <= vmax(au) contain column u: umax = {15,15,15,15,14,14,14,13,13,12,11,10,9,8,6,3}
-        const int vmax = au <= 3 ? 15 : au <= 6 ? 14 : au <= 8 ? 13 : au == 9 ? 12 : au == 10 ? 11 : au == 11 ? 10 : au == 12 ? 9 : au == 13 ? 8 : au == 14 ? 6 : 3;
+        const int v = lane - HALF_PATCH, av = v < 0 ? -v : v;
+        const int o = off + PT_R - HALF_PATCH;                        // patch byte of column u = -15 in this row
+        const uint32_t *rowp = patch + (PT_R + v) * PT_WORDS + (o >> 2);
+        const unsigned sh = (unsigned)(o & 3) * 8;
+        uint32_t x[9];
 #pragma unroll
-        for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {
-            const int av = v < 0 ? -v : v;
-            if (av <= vmax) {
-                const int val = center[v * PP + u];
-                m10 += u * val;
-                m01 += v * val;
-            }
+        for (int t = 0; t < 9; t++) x[t] = rowp[t];
+        int su = 0, s1 = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const uint32_t w = __funnelshift_r(x[t], x[t + 1], sh) & s_mask[av][t];
+            su = dp4a_u8_s8(w, pack_s8(-15 + 4 * t, -14 + 4 * t, -13 + 4 * t, -12 + 4 * t), su);
+            s1 = (int)__dp4a(w, 0x01010101u, (unsigned)s1);
         }
+        m10 = su;
+        m01 = v * s1;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
