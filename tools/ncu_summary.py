@@ -19,7 +19,9 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.avg"]
 
 
-def launches(path):
+def launches(path, lo=None, hi=None, label=None):
+    """per-kernel totals of an ncu launch list; lo/hi restrict to a range of the library's own launches (hyorb:: kernels in
+    launch order, setup kernels k_pattern_to_float / k_repack excluded)"""
     rows = list(csv.reader(open(path)))
     for i, r in enumerate(rows):
         if "Kernel Name" in r:
@@ -27,11 +29,14 @@ def launches(path):
             break
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
     agg = collections.OrderedDict()
-    for r in rows[start:]:
-        if len(r) > vi:
-            agg.setdefault(r[ki].split("(")[0], []).append(float(r[vi].replace(",", "")))
+    recs = [(r[ki].split("(")[0], float(r[vi].replace(",", ""))) for r in rows[start:] if len(r) > vi]
+    if lo is not None:
+        own = [x for x in recs if x[0].startswith("hyorb::") and "k_pattern" not in x[0] and "k_repack" not in x[0]]
+        recs = own[lo:hi]
+    for k, v in recs:
+        agg.setdefault(k, []).append(v)
     tot = sum(sum(v) for v in agg.values())
-    print(f"# {path}: gpu__time_duration.sum per kernel (ns), cold-cache serialised replay -- compare SHARES")
+    print(f"# {path}{' ' + label if label else ''}: gpu__time_duration.sum per kernel (ns), cold-cache serialised replay -- compare SHARES")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         print(f"{k[:70]:70s} launches={len(v):4d} total_us={sum(v) / 1e3:10.1f} mean_us={sum(v) / len(v) / 1e3:9.1f} share={sum(v) / tot:.3f}")
 
@@ -49,4 +54,7 @@ def full(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "launches" and len(sys.argv) > 4:
+        launches(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), sys.argv[5] if len(sys.argv) > 5 else None)
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
