@@ -148,3 +148,33 @@ def test_error_behaviour():
     assert e.value.rc == F.EUNSUPPORTED
     with pytest.raises(ValueError):
         ex(img.astype(np.float32), None)
+
+
+@pytest.mark.parametrize("pitched", [False, True])
+def test_device_pointer_entry_matches_host_entry(pitched):
+    """hyorb_extract_batch_device on a dense odd-pitch device batch (repacked on the device to a TMA-addressable layout) and on
+    a pitched one (read in place through TMA) gives what the host entry gives."""
+    torch = pytest.importorskip("torch")
+    imgs = np.stack([synth.noise_image(376, 1241, 70 + i) if i % 2 else synth.blocks_image(376, 1241, 70 + i) for i in range(4)])
+    s = _settings(2000)
+    ex = hb.ORBExtractor(s)
+    kps, desc, counts = ex.extract_batch(imgs)
+    B, H, W = imgs.shape
+    cap = ex.default_capacity()
+    pitch = (W + 15) & ~15 if pitched else W
+    dev = torch.zeros((B, H, pitch), dtype=torch.uint8, device="cuda")
+    dev[:, :, :W] = torch.from_numpy(imgs).cuda()
+    d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    d_counts = torch.zeros(B, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ex.extract_batch_device(dev.data_ptr(), B, W, H, pitch, pitch * H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_counts.data_ptr())
+    ex.sync()
+    torch.cuda.synchronize()
+    c2 = d_counts.cpu().numpy()
+    assert np.array_equal(c2, counts)
+    k2 = d_kps.cpu().numpy().view(np.uint8).reshape(B, cap, 28)
+    for i in range(B):
+        n = counts[i]
+        assert k2[i, :n].tobytes() == kps[i, :n].tobytes()
+        assert np.array_equal(d_desc[i, :n].cpu().numpy(), desc[i, :n])
