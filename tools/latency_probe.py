@@ -1,0 +1,14 @@
+import sys, time, numpy as np
+sys.path.insert(0,'/root/repo')
+import hyslam_b200 as hb
+from hyslam_b200 import synth
+for (h,w,nf) in [(480,752,1000),(376,1241,2000)]:
+    img=synth.noise_image(h,w,1)
+    ex=hb.ORBExtractor(hb.FeatureExtractorSettings(nFeatures=nf))
+    for _ in range(5): ex(img,None)
+    ex.set_profiling(True); ex.stage_times(reset=True)
+    t0=time.perf_counter()
+    for _ in range(50): ex(img,None)
+    dt=(time.perf_counter()-t0)/50
+    st,calls=ex.stage_times(reset=True)
+    print(h,w,"wall ms",round(dt*1e3,3),"stages ms",{k:round(v/calls,3) for k,v in st.items()},"sum",round(sum(st.values())/calls,3))
