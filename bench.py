@@ -283,7 +283,7 @@ def main():
         return tuple(po.numpy().view(x.dtype).reshape(x.shape) for po, x in zip(pin, o)), pin
     outs, _keep0 = make_outs()
     h_in = pinned[0].numpy()
-    e2e_steps = max(4, min(args.steps, 10))
+    e2e_steps = max(4, min(args.steps, 20))
     for _ in range(2):
         ex.process_stereo_batch(h_in, cam, capacity=cap, out=outs)
     barrier()
