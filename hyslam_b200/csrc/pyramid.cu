@@ -50,7 +50,10 @@ __device__ __forceinline__ HRow hrow(const RowW &w, const uint32_t (&sel)[4], co
     return r;
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+#ifndef HYORB_RS_MINB
+#define HYORB_RS_MINB 8      // 32 registers: full occupancy, which this latency-bound kernel needs (measured 0.48 -> 0.44 ms per 256 images)
+#endif
+__global__ void __launch_bounds__(RS_THREADS, HYORB_RS_MINB)
 k_resize(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride, int sw, int sh,
          uint8_t *__restrict__ dst, int dpitch, unsigned long long dstride, int dw, int dh,
          const ResizeTab *__restrict__ tx, const ResizeTab *__restrict__ ty, int area2x, int nx, int ny, int total)
