@@ -18,6 +18,7 @@ OK, EINVAL, ECAPACITY, EUNSUPPORTED, ENOMEM, ECUDA = 0, -1, -2, -3, -4, -5
 MAX_LEVELS = 16
 GRID_COLS, GRID_ROWS = 64, 48
 RULE_LANDMARK, RULE_BOW, RULE_MONOINIT = 0, 1, 2
+SBP_DISTANCE, SBP_STEREO, SBP_ROTATION = 1, 2, 4
 DBG_PYRAMID, DBG_BLURRED, DBG_CANDIDATES, DBG_LEVEL_COUNT = 0, 1, 2, 3
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
@@ -67,7 +68,7 @@ SYMBOLS = [
     "hyorb_match_bruteforce_device", "hyorb_grid_build_host", "hyorb_match_window_host",
     "hyorb_rotation_consistency_host", "hyorb_last_error", "hyorb_version", "hyorb_device_count",
     "hyorb_process_stereo_batch_host", "hyorb_process_stereo_batch_device", "hyorb_extractor_set_profiling",
-    "hyorb_extractor_stage_times", "hyorb_extractor_set_pipelining", "hyorb_distinctive_descriptor_host", "hyorb_project_landmarks_host", "hyorb_search_by_projection_host",
+    "hyorb_extractor_stage_times", "hyorb_extractor_set_pipelining", "hyorb_distinctive_descriptor_host", "hyorb_project_landmarks_host", "hyorb_search_by_projection_host", "hyorb_search_by_projection_ex_host",
     "hyorb_vocabulary_create", "hyorb_vocabulary_destroy", "hyorb_bow_transform_host", "hyorb_search_by_bow_host",
 ]
 N_STAGES = 6
@@ -139,6 +140,9 @@ def lib():
                                               C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hyorb_rotation_consistency_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hyorb_distinctive_descriptor_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hyorb_search_by_projection_ex_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                         C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint,
+                                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hyorb_vocabulary_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hyorb_vocabulary_destroy.argtypes = [C.c_void_p]
         L.hyorb_bow_transform_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]

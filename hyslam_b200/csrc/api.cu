@@ -835,14 +835,14 @@ HYORB_API int hyorb_match_window_host(hyorb_matcher *m, const hyorb_keypoint *t_
 }
 
 static int m_project(hyorb_matcher *m, const hyorb_projection *pr, const hyorb_landmark *lms, int n, const hyorb_keypoint *t_kps, int nt, float th,
-                     float size_ref, float frac_smaller, float frac_larger)
+                     float size_ref, float frac_smaller, float frac_larger, unsigned flags = HYORB_SBP_DISTANCE | HYORB_SBP_STEREO)
 {
     // landmarks -> d_e, target keypoints -> d_a; queries -> d_g, passed -> d_k (read back / consumed by the caller)
     HY_TRY(m_upload(m, m->d_e, lms, sizeof(hyorb_landmark) * (size_t)n));
     HY_TRY(m_upload(m, m->d_a, t_kps, sizeof(hyorb_keypoint) * (size_t)nt));
     HY_TRY(m->d_g.ensure(sizeof(hyorb_window_query) * (size_t)n));
     HY_TRY(m->d_k.ensure((size_t)n));
-    return launch_project_landmarks(*pr, m->d_e.as<hyorb_landmark>(), n, m->d_a.as<hyorb_keypoint>(), nt, th, size_ref, frac_smaller, frac_larger,
+    return launch_project_landmarks(*pr, m->d_e.as<hyorb_landmark>(), n, m->d_a.as<hyorb_keypoint>(), nt, th, size_ref, frac_smaller, frac_larger, flags,
                                     m->d_g.as<hyorb_window_query>(), m->d_k.as<uint8_t>(), m->d_status.as<int>(), m->stream, &m->launches);
 }
 
@@ -865,13 +865,24 @@ HYORB_API int hyorb_search_by_projection_host(hyorb_matcher *m, const hyorb_proj
                                               float th, float size_ref, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
                                               uint8_t *accepted, uint8_t *passed)
 {
+    return hyorb_search_by_projection_ex_host(m, pr, lms, lm_desc, nullptr, n, t_kps, t_desc, t_uR, t_matched, nt, th, size_ref, thr, ratio,
+                                              HYORB_SBP_DISTANCE | HYORB_SBP_STEREO, best_idx, best, second, accepted, passed);
+}
+
+HYORB_API int hyorb_search_by_projection_ex_host(hyorb_matcher *m, const hyorb_projection *pr, const hyorb_landmark *lms, const uint8_t *lm_desc,
+                                                 const float *lm_prev_angle, int n, const hyorb_keypoint *t_kps, const uint8_t *t_desc,
+                                                 const float *t_uR, const uint8_t *t_matched, int nt, float th, float size_ref, float thr, float ratio,
+                                                 unsigned flags, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, uint8_t *passed)
+{
     HY_TRY(m_prepare(m));
-    if (n < 0 || nt < 0 || !pr) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (n < 0 || nt < 0 || !pr || (flags & ~7u)) { set_error("bad argument"); return HYORB_EINVAL; }
+    if ((flags & HYORB_SBP_ROTATION) && n > 0 && !lm_prev_angle) { set_error("HYORB_SBP_ROTATION needs lm_prev_angle"); return HYORB_EINVAL; }
     if (n == 0) return HYORB_OK;
     if (!lms || !lm_desc || !best_idx || !best || !second || !accepted || (nt > 0 && (!t_kps || !t_desc))) { set_error("null argument"); return HYORB_EINVAL; }
-    if (pr->stereo && !t_uR) { set_error("stereo camera but t_uR is NULL"); return HYORB_EINVAL; }
+    const bool use_ur = pr->stereo && (flags & HYORB_SBP_STEREO);
+    if (use_ur && !t_uR) { set_error("stereo consistency requested but t_uR is NULL"); return HYORB_EINVAL; }
     constexpr int NC = HYORB_GRID_COLS * HYORB_GRID_ROWS;
-    HY_TRY(m_project(m, pr, lms, n, t_kps, nt, th, size_ref, 0.5f, 1.5f));     // FeatureSizeCriterion(0.5, 1.5), FeatureMatcher.cc:132
+    HY_TRY(m_project(m, pr, lms, n, t_kps, nt, th, size_ref, 0.5f, 1.5f, flags));     // FeatureSizeCriterion(0.5, 1.5), FeatureMatcher.cc:132
     HY_TRY(m_upload(m, m->d_b, t_desc, (size_t)nt * 32));
     if (t_uR) HY_TRY(m_upload(m, m->d_l, t_uR, sizeof(float) * (size_t)nt));
     if (t_matched) HY_TRY(m_upload(m, m->d_bestd, t_matched, (size_t)nt));
@@ -890,6 +901,12 @@ HYORB_API int hyorb_search_by_projection_host(hyorb_matcher *m, const hyorb_proj
                                t_matched ? m->d_bestd.as<uint8_t>() : nullptr, nt, pr->bounds, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(),
                                m->d_g.as<hyorb_window_query>(), m->d_h.as<uint8_t>(), n, thr, ratio, m->d_c.as<int32_t>(), m->d_d.as<uint16_t>(),
                                m->d_pkey.as<uint16_t>(), m->d_f.as<uint8_t>(), m->stream, &m->launches, m->d_k.as<uint8_t>()));
+    if (flags & HYORB_SBP_ROTATION) {
+        HY_TRY(m_upload(m, m->d_psecond, lm_prev_angle, sizeof(float) * (size_t)n));
+        HY_TRY(m->d_rowtab.ensure(sizeof(int32_t) * std::max(nt, 1)));
+        HY_TRY(launch_projection_rotation(m->d_c.as<int32_t>(), m->d_f.as<uint8_t>(), n, m->d_psecond.as<float>(), m->d_a.as<hyorb_keypoint>(), nt,
+                                          m->d_rowtab.as<int32_t>(), m->d_status.as<int>(), m->stream, &m->launches));
+    }
     HY_CUDA(cudaMemcpyAsync(best_idx, m->d_c.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
     HY_CUDA(cudaMemcpyAsync(best, m->d_d.p, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
     HY_CUDA(cudaMemcpyAsync(second, m->d_pkey.p, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));

@@ -147,7 +147,10 @@ int launch_match_window(const hyorb_keypoint *kps, const uint8_t *tdesc, const f
                         float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, cudaStream_t st, long *launches,
                         const uint8_t *q_active = nullptr);
 int launch_project_landmarks(const hyorb_projection &pr, const hyorb_landmark *lms, int n, const hyorb_keypoint *t_kps, int nt, float th, float size_ref,
-                             float frac_smaller, float frac_larger, hyorb_window_query *queries, uint8_t *passed, int *status, cudaStream_t st, long *launches);
+                             float frac_smaller, float frac_larger, unsigned flags, hyorb_window_query *queries, uint8_t *passed, int *status, cudaStream_t st,
+                             long *launches);
+int launch_projection_rotation(const int32_t *best_idx, uint8_t *accepted, int n, const float *prev_angle, const hyorb_keypoint *t_kps, int nt,
+                               int32_t *owner, int *status, cudaStream_t st, long *launches);
 int launch_rotation(const float *a_prev, const float *a_curr, int n, uint8_t *keep, int *status, cudaStream_t st, long *launches);
 int launch_bow_descend(const int32_t *child_off, const int32_t *child_idx, const uint8_t *node_desc, const int32_t *word_of, const float *weight_of,
                        int nid_level, const uint8_t *desc, int n, int32_t *word_id, int32_t *node_id, float *weight, cudaStream_t st, long *launches);

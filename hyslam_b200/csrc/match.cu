@@ -375,7 +375,7 @@ __device__ __forceinline__ bool project_point(const hyorb_projection &pr, const 
 
 __global__ void __launch_bounds__(128)
 k_project_landmarks(hyorb_projection pr, const hyorb_landmark *__restrict__ lms, int n, const hyorb_keypoint *__restrict__ t_kps, int nt,
-                    float th, float size_ref, float frac_smaller, float frac_larger, hyorb_window_query *__restrict__ queries,
+                    float th, float size_ref, float frac_smaller, float frac_larger, unsigned flags, hyorb_window_query *__restrict__ queries,
                     uint8_t *__restrict__ passed, int *status)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,7 +386,7 @@ k_project_landmarks(hyorb_projection pr, const hyorb_landmark *__restrict__ lms,
     const float PO[3] = {__fsub_rn(lm.Pw[0], pr.Ow[0]), __fsub_rn(lm.Pw[1], pr.Ow[1]), __fsub_rn(lm.Pw[2], pr.Ow[2])};
     const double sq = __dadd_rn(__dadd_rn(__dmul_rn((double)PO[0], (double)PO[0]), __dmul_rn((double)PO[1], (double)PO[1])), __dmul_rn((double)PO[2], (double)PO[2]));
     const float dist = (float)__dsqrt_rn(sq);
-    const bool dist_ok = !(dist < lm.min_dist || dist > lm.max_dist);
+    const bool dist_ok = !(flags & HYORB_SBP_DISTANCE) || !(dist < lm.min_dist || dist > lm.max_dist);
     float size_px;
     if (lm.assoc_idx >= 0) {
         if (lm.assoc_idx >= nt) { atomicOr(status, ST_BAD_INDEX); size_px = 0.f; }
@@ -402,16 +402,78 @@ k_project_landmarks(hyorb_projection pr, const hyorb_landmark *__restrict__ lms,
     hyorb_window_query q;
     q.u = uv[0]; q.v = uv[1]; q.r = radius;
     q.size_lo = __fmul_rn(frac_smaller, size_px); q.size_hi = __fmul_rn(frac_larger, size_px);
-    q.ur = uv[2]; q.ur_radius = pr.stereo ? radius : -1.0f;
+    q.ur = uv[2]; q.ur_radius = (pr.stereo && (flags & HYORB_SBP_STEREO)) ? radius : -1.0f;
     queries[i] = q;
     passed[i] = (uint8_t)(valid && dist_ok);
 }
 
-int launch_project_landmarks(const hyorb_projection &pr, const hyorb_landmark *lms, int n, const hyorb_keypoint *t_kps, int nt, float th, float size_ref,
-                             float frac_smaller, float frac_larger, hyorb_window_query *queries, uint8_t *passed, int *status, cudaStream_t st, long *launches)
+// RotationConsistencyCriterion over the matches of a projection search (MatchCriteria.cpp:363-401, 684-767), single CTA.  The
+// reference re-keys the matches by current keypoint index before the histogram (:382): of several landmarks that matched the
+// same keypoint only the last one in its map order survives -- here: the one listed last by the caller.
+__global__ void __launch_bounds__(256)
+k_projection_rotation(const int32_t *__restrict__ best_idx, uint8_t *__restrict__ accepted, int n, const float *__restrict__ prev_angle,
+                      const hyorb_keypoint *__restrict__ t_kps, int nt, int32_t *__restrict__ owner, int *status)
+{
+    constexpr int HL = 30;
+    __shared__ int hist[HL];
+    __shared__ int ind[3];
+    if (threadIdx.x < HL) hist[threadIdx.x] = 0;
+    for (int k = threadIdx.x; k < nt; k += blockDim.x) owner[k] = -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (accepted[i]) atomicMax(&owner[best_idx[i]], i);
+    __syncthreads();
+    const float factor = 1.0f / HL;
+    auto bin_of = [&](int i) {
+        float rot = __fsub_rn(prev_angle[i], t_kps[best_idx[i]].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, factor));
+        return bin == HL ? 0 : bin;
+    };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!accepted[i] || owner[best_idx[i]] != i) continue;
+        const int bin = bin_of(i);
+        if (bin < 0 || bin >= HL) { atomicOr(status, ST_BAD_INDEX); continue; }   // the reference asserts
+        atomicAdd(&hist[bin], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // ComputeThreeMaxima (:727-767)
+        int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < HL; i++) {
+            const int s = hist[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+            else if (s > max3) { max3 = s; i3 = i; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3 = -1; }
+        ind[0] = i1; ind[1] = i2; ind[2] = i3;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!accepted[i]) continue;
+        if (owner[best_idx[i]] != i) { accepted[i] = 0; continue; }
+        const int bin = bin_of(i);
+        accepted[i] = (uint8_t)(bin == ind[0] || bin == ind[1] || bin == ind[2]);
+    }
+}
+
+int launch_projection_rotation(const int32_t *best_idx, uint8_t *accepted, int n, const float *prev_angle, const hyorb_keypoint *t_kps, int nt,
+                               int32_t *owner, int *status, cudaStream_t st, long *launches)
 {
     if (n <= 0) return HYORB_OK;
-    k_project_landmarks<<<(n + 127) / 128, 128, 0, st>>>(pr, lms, n, t_kps, nt, th, size_ref, frac_smaller, frac_larger, queries, passed, status);
+    k_projection_rotation<<<1, 256, 0, st>>>(best_idx, accepted, n, prev_angle, t_kps, nt, owner, status);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+int launch_project_landmarks(const hyorb_projection &pr, const hyorb_landmark *lms, int n, const hyorb_keypoint *t_kps, int nt, float th, float size_ref,
+                             float frac_smaller, float frac_larger, unsigned flags, hyorb_window_query *queries, uint8_t *passed, int *status, cudaStream_t st,
+                             long *launches)
+{
+    if (n <= 0) return HYORB_OK;
+    k_project_landmarks<<<(n + 127) / 128, 128, 0, st>>>(pr, lms, n, t_kps, nt, th, size_ref, frac_smaller, frac_larger, flags, queries, passed, status);
     ++*launches;
     HY_CUDA(cudaGetLastError());
     return HYORB_OK;

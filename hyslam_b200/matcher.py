@@ -188,9 +188,12 @@ class FeatureMatcher(_Handle):
                                                      float(frac_smaller), float(frac_larger), F.ptr(q), F.ptr(passed)))
         return q, passed
 
-    def SearchByProjectionLandMarks(self, pr, landmarks, lm_desc, t_kps, t_desc, th, t_uR=None, t_matched=None, size_ref=31.0, thr=None, ratio=None):
-        """FeatureMatcher::SearchByProjection(Frame&, landmarks, th) (FeatureMatcher.cc:123-143) up to the association loop, in one
-        device call.  Returns (best_idx, best, second, accepted, passed) per landmark."""
+    def SearchByProjectionLandMarks(self, pr, landmarks, lm_desc, t_kps, t_desc, th, t_uR=None, t_matched=None, size_ref=31.0, thr=None, ratio=None,
+                                    flags=F.SBP_DISTANCE | F.SBP_STEREO, lm_prev_angle=None):
+        """FeatureMatcher::SearchByProjection up to the association loop, in one device call.  ``flags`` picks the variant: local map
+        (FeatureMatcher.cc:123-143) = SBP_DISTANCE | SBP_STEREO (default); motion model (:145-176) = SBP_STEREO | SBP_ROTATION with
+        ``lm_prev_angle``; relocalisation (:180-213) = SBP_DISTANCE | SBP_ROTATION, ratio 1.0.
+        Returns (best_idx, best, second, accepted, passed) per landmark."""
         lms = np.ascontiguousarray(landmarks, F.LM_DTYPE); lm_desc = np.ascontiguousarray(lm_desc, np.uint8)
         t_kps = np.ascontiguousarray(t_kps, F.KP_DTYPE); t_desc = np.ascontiguousarray(t_desc, np.uint8)
         t_uR = None if t_uR is None else np.ascontiguousarray(t_uR, np.float32)
@@ -200,9 +203,10 @@ class FeatureMatcher(_Handle):
         n = len(lms)
         bi, b, s, acc = self._outs(n)
         passed = np.zeros(n, np.uint8)
-        F.check(F.lib().hyorb_search_by_projection_host(self._h, C.byref(pr), F.ptr(lms), F.ptr(lm_desc), n, F.ptr(t_kps), F.ptr(t_desc), F.ptr(t_uR),
-                                                        F.ptr(t_matched), len(t_kps), float(th), float(size_ref), thr, ratio, F.ptr(bi), F.ptr(b),
-                                                        F.ptr(s), F.ptr(acc), F.ptr(passed)))
+        pa = None if lm_prev_angle is None else np.ascontiguousarray(lm_prev_angle, np.float32)
+        F.check(F.lib().hyorb_search_by_projection_ex_host(self._h, C.byref(pr), F.ptr(lms), F.ptr(lm_desc), F.ptr(pa), n, F.ptr(t_kps), F.ptr(t_desc),
+                                                           F.ptr(t_uR), F.ptr(t_matched), len(t_kps), float(th), float(size_ref), thr, ratio,
+                                                           int(flags), F.ptr(bi), F.ptr(b), F.ptr(s), F.ptr(acc), F.ptr(passed)))
         return bi, b, s, acc, passed
 
     def BowTransform(self, vocab, desc, levelsup=4):

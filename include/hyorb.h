@@ -259,6 +259,23 @@ HYORB_API int hyorb_project_landmarks_host(hyorb_matcher *m, const hyorb_project
  * FeatureSizeCriterion(0.5, 1.5) -> StereoConsistencyCriterion(th) -> BestScoreCriterion(thr = TH_HIGH, ratio), all on the
  * device in one call.  accepted[i] = landmark i found a keypoint (best_idx[i]); landmarks that fail a landmark criterion
  * report best_idx = -1.  passed may be NULL. */
+/* Which criteria a projection search applies (the variants of FeatureMatcher::SearchByProjection differ only in these and in
+ * thr / ratio): local map (FeatureMatcher.cc:123-143) = DISTANCE | STEREO; motion model (:145-176) = STEREO | ROTATION;
+ * relocalisation against a keyframe (:180-213) = DISTANCE | ROTATION with ratio 1.0. */
+enum { HYORB_SBP_DISTANCE = 1,   /* DistanceCriterion (MatchCriteria.cpp:46-77) */
+       HYORB_SBP_STEREO = 2,     /* StereoConsistencyCriterion(th) (:149-177); only has an effect for a stereo camera */
+       HYORB_SBP_ROTATION = 4 }; /* RotationConsistencyCriterion (:363-401) against lm_prev_angle */
+
+/* As hyorb_search_by_projection_host with the criteria chosen by `flags`.  HYORB_SBP_ROTATION needs lm_prev_angle[i] = angle of
+ * the keypoint landmark i is associated with in the previous frame, and the landmarks listed in the reference's map order
+ * (ascending MapPoint*): where several landmarks match the same keypoint the reference keeps the last one in that order. */
+HYORB_API int hyorb_search_by_projection_ex_host(hyorb_matcher *m, const hyorb_projection *pr, const hyorb_landmark *lms,
+                                                 const uint8_t *lm_desc, const float *lm_prev_angle, int n,
+                                                 const hyorb_keypoint *t_kps, const uint8_t *t_desc, const float *t_uR,
+                                                 const uint8_t *t_matched, int nt, float th, float size_ref, float thr,
+                                                 float ratio, unsigned flags, int32_t *best_idx, uint16_t *best,
+                                                 uint16_t *second, uint8_t *accepted, uint8_t *passed);
+
 HYORB_API int hyorb_search_by_projection_host(hyorb_matcher *m, const hyorb_projection *pr, const hyorb_landmark *lms,
                                               const uint8_t *lm_desc, int n, const hyorb_keypoint *t_kps, const uint8_t *t_desc,
                                               const float *t_uR, const uint8_t *t_matched, int nt, float th, float size_ref,

@@ -323,6 +323,16 @@ def project_landmarks(pr, lms, t_kps, th, size_ref=31.0, frac_smaller=0.5, frac_
     return q, passed
 
 
+def projection_rotation(best_idx, accepted, prev_angle, t_kps):
+    """RotationConsistencyCriterion over projection matches (MatchCriteria.cpp:363-401): returns the updated accepted flags"""
+    bi = np.ascontiguousarray(best_idx, np.int32); acc = np.ascontiguousarray(accepted, np.uint8).copy()
+    pa = np.ascontiguousarray(prev_angle, np.float32); t_kps = np.ascontiguousarray(t_kps)
+    rc = lib().orc_projection_rotation(_p(bi), _p(acc), len(bi), _p(pa), _p(t_kps), len(t_kps))
+    if rc != 0:
+        raise RuntimeError(f"orc_projection_rotation rc={rc}")
+    return acc
+
+
 def bow_transform(vocab, desc, levelsup=4):
     """DBoW2 TemplatedVocabulary::transform per feature (published algorithm; see orb_oracle.c): (word_id, node_id, weight).
     vocab: dict(L, child_off, child_idx, node_desc, word_of, weight_of)."""

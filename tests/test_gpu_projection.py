@@ -97,3 +97,42 @@ def test_projection_edge_cases():
     lms["assoc_idx"][1] = 7                                  # out of range index is reported
     with pytest.raises(hb.HyorbError):
         m.ProjectLandMarks(pr, lms, kps, 3.0)
+
+
+@pytest.mark.parametrize("seed,stereo", [(3, False), (4, True)])
+def test_motion_model_variant_with_rotation_consistency(seed, stereo):
+    """SearchByProjection(CurrentFrame, LastFrame, th) (FeatureMatcher.cc:145-176): no DistanceCriterion, rotation histogram over the
+    matches, duplicates on one keypoint resolved to the landmark listed last (the reference's map order)"""
+    L, R = synth.stereo_pair(376, 1241, 60 + seed)
+    p = O.default_params(2000)
+    kl, dl = O.extract(L, p)
+    kr, dr = O.extract(R, p)
+    uR, _, _, _ = O.stereo_match(O.StereoParams(386.1448, 718.856, 376, 100.0, 50.0, 31.0), kl, dl, kr, dr)
+    cam, lms, pick = _scene(seed, 2500, stereo, kl, uR if stereo else None)        # 2500 landmarks on 2000 keypoints: duplicates guaranteed
+    rng = np.random.default_rng(200 + seed)
+    lm_desc = dl[pick].copy()
+    prev_angle = (kl["angle"][pick] + rng.choice([0.0, 0.0, 0.0, 25.0, 170.0], len(pick)) + rng.normal(0, 2, len(pick))).astype(np.float32) % np.float32(360)
+    flags = F.SBP_STEREO | F.SBP_ROTATION
+    m = hb.FeatureMatcher()
+    pr = m.make_projection(*cam)
+    bi, b, s, acc, passed = m.SearchByProjectionLandMarks(pr, lms, lm_desc, kl, dl, 7.0, t_uR=uR if stereo else None, thr=100.0, ratio=0.9,
+                                                          flags=flags, lm_prev_angle=prev_angle)
+    # oracle composition: projection without the distance criterion, window scan, then the rotation criterion
+    opr = O.make_projection(*cam)
+    far = lms.copy(); far["min_dist"] = 0; far["max_dist"] = np.float32(3e38)
+    oq, opassed = O.project_landmarks(opr, far, kl, 7.0)
+    if not stereo:
+        pass
+    bounds = O.Bounds(*cam[6])
+    off, idx = O.grid_build(kl, bounds)
+    obi, ob, osd, oacc = O.match_window(kl, dl, uR if stereo else None, None, bounds, off, idx, oq, lm_desc, thr=100.0, ratio=0.9)
+    dead = opassed == 0
+    obi[dead] = -1; ob[dead] = 65535; osd[dead] = 65535; oacc[dead] = 0
+    before = int(oacc.sum())
+    oacc = O.projection_rotation(obi, oacc, prev_angle, kl)
+    assert np.array_equal(passed, opassed)
+    for g, w, name in zip((bi, b, s, acc), (obi, ob, osd, oacc), ("best_idx", "best", "second", "accepted")):
+        assert np.array_equal(g, w), name
+    kept = int(acc.sum())
+    assert 50 < kept < before                              # the histogram and the de-duplication both removed something
+    assert len(np.unique(bi[acc > 0])) == kept             # one landmark per keypoint survives
