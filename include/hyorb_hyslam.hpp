@@ -186,6 +186,43 @@ public:
         return r;
     }
 
+    // FeatureMatcher::SearchByProjection up to its association loop (FeatureMatcher.cc:57-213): the caller fills `pr` from the
+    // frame (mRcw, mtcw, GetCameraCenter(), camera K / mbf / sensor / image bounds) and one hyorb_landmark per candidate MapPoint
+    // (GetWorldPos, getSize, Get{Min,Max}DistanceInvariance, frame.hasAssociation(lm)), in the iteration order of its
+    // std::map<MapPoint*, ...>; `flags` = HYORB_SBP_* picks the variant, lm_prev_angle is needed with HYORB_SBP_ROTATION.
+    // Result::accepted[i] != 0  <=>  the reference would call frame.associateLandMark(best_idx[i], landmark i, true).
+    Result searchByProjection(const hyorb_projection &pr, const std::vector<hyorb_landmark> &landmarks, const std::vector<FeatureDescriptor> &lm_desc,
+                              const std::vector<float> *lm_prev_angle, const FeatureViews &views, const std::vector<uint8_t> *already_matched,
+                              float th, float thr, float ratio, unsigned flags)
+    {
+        const std::vector<cv::KeyPoint> keys = views.getKeys();
+        const std::vector<uint8_t> q = cuda_marshal::packDescriptors(lm_desc), t = cuda_marshal::packDescriptors(views.getDescriptors());
+        const std::vector<float> uR = views.getuRs();
+        const int n = (int)landmarks.size(), nt = (int)keys.size();
+        Result r;
+        r.best_idx.assign(n, -1); r.best.assign(n, 65535); r.second.assign(n, 65535); r.accepted.assign(n, 0);
+        cuda_marshal::check(hyorb_search_by_projection_ex_host(m, &pr, landmarks.data(), q.data(), lm_prev_angle ? lm_prev_angle->data() : nullptr, n,
+                                                               cuda_marshal::asAbi(keys), t.data(), uR.empty() ? nullptr : uR.data(),
+                                                               already_matched ? already_matched->data() : nullptr, nt, th,
+                                                               views.getOrbParams().size_ref, thr, ratio, flags, r.best_idx.data(), r.best.data(),
+                                                               r.second.data(), r.accepted.data(), nullptr));
+        return r;
+    }
+
+    // MapPointDBEntry::_computeDistinctiveDescriptor_ (MapPointDB.cpp:127-171) for many landmarks: observations[l] = descriptors of landmark l
+    std::vector<int32_t> distinctiveDescriptors(const std::vector<std::vector<FeatureDescriptor>> &observations)
+    {
+        std::vector<int32_t> off(1, 0), best(observations.size(), -1), median(observations.size(), -1);
+        std::vector<uint8_t> all;
+        for (const auto &obs : observations) {
+            const std::vector<uint8_t> d = cuda_marshal::packDescriptors(obs);
+            all.insert(all.end(), d.begin(), d.end());
+            off.push_back((int32_t)(all.size() / HYORB_DESC_BYTES));
+        }
+        cuda_marshal::check(hyorb_distinctive_descriptor_host(m, all.data(), off.data(), (int)observations.size(), best.data(), median.data()));
+        return best;
+    }
+
 private:
     hyorb_matcher *m = nullptr;
 };

@@ -58,6 +58,12 @@ int main(int argc, char **argv)
         const FeatureMatcherSettings ms = factory.getFeatureMatcherSettings();
         CudaDescriptorScan::Result r = scan.scan(mDescriptors, mDescriptorsRight, nullptr, nullptr, HYORB_RULE_BOW, ms.TH_LOW, ms.nnratio);
 
+        // representative descriptor of a few synthetic landmarks: landmark l observed by left keypoints 3l, 3l+1, 3l+2 and right keypoint l
+        std::vector<std::vector<FeatureDescriptor>> observations;
+        for (size_t l = 0; 3 * l + 2 < mDescriptors.size() && l < mDescriptorsRight.size() && l < 50; l++)
+            observations.push_back({mDescriptors[3 * l], mDescriptors[3 * l + 1], mDescriptors[3 * l + 2], mDescriptorsRight[l]});
+        const std::vector<int32_t> distinctive = scan.distinctiveDescriptors(observations);
+
         FILE *f = fopen(argv[8], "wb");
         if (!f) { fprintf(stderr, "cannot write %s\n", argv[8]); return 2; }
         const int32_t hdr[4] = {(int32_t)mvKeys.size(), (int32_t)mvKeysRight.size(), extractor_left->GetLevels(), (int32_t)sizeof(cv::KeyPoint)};
@@ -70,6 +76,9 @@ int main(int argc, char **argv)
         put(f, LMviews.getDepths());
         put(f, r.best_idx); put(f, r.best); put(f, r.second); put(f, r.accepted);
         put(f, extractor_left->GetScaleFactors());
+        const int32_t nd = (int32_t)distinctive.size();
+        fwrite(&nd, sizeof(nd), 1, f);
+        put(f, distinctive);
         fclose(f);
         // a FeatureDescriptor built by the shim behaves like the reference's (ORBDistance through the stored functor)
         if (mDescriptors.size() > 1) printf("distance(desc0, desc1) = %.0f\n", mDescriptors[0].distance(mDescriptors[1]));

@@ -45,6 +45,8 @@ def test_process_stereo_image_through_the_cpp_shim(tmp_path, kind, h, w, seed, n
     uR = take(np.float32, nl); depth = take(np.float32, nl)
     bi = take(np.int32, nl); b = take(np.uint16, nl); s = take(np.uint16, nl); acc = take(np.uint8, nl)
     scales = take(np.float32, nlev)
+    nd = int(take(np.int32, 1)[0])
+    distinctive = take(np.int32, nd)
     assert o == len(buf)
 
     p = O.default_params(nf)
@@ -58,4 +60,8 @@ def test_process_stereo_image_through_the_cpp_shim(tmp_path, kind, h, w, seed, n
     for g, wv, name in zip((bi, b, s, acc), want, ("best_idx", "best", "second", "accepted")):
         assert np.array_equal(g, wv), name
     assert np.array_equal(scales, O.scale_tables(p)[0])
+    # CudaDescriptorScan::distinctiveDescriptors: landmark l = left descriptors 3l..3l+2 + right descriptor l
+    obs = np.concatenate([np.concatenate([odl[3 * l:3 * l + 3], odr[l:l + 1]]) for l in range(nd)]) if nd else np.zeros((0, 32), np.uint8)
+    want_idx, _ = O.distinctive_descriptor(obs, np.arange(0, 4 * nd + 1, 4, dtype=np.int32))
+    assert nd > 0 and np.array_equal(distinctive, want_idx)
     assert "shim ok" in r.stdout
