@@ -84,3 +84,12 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert not bad.search(txt), f
+
+
+def test_header_is_plain_c99(tmp_path):
+    """the ABI header is consumable from C (cgo / JNI / N-API style bindings bind exactly these declarations)"""
+    src = tmp_path / "c.c"
+    src.write_text('#include "hyorb.h"\nint main(void){ hyorb_projection p; hyorb_landmark l; hyorb_window_query q; (void)p; (void)l; (void)q; return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
