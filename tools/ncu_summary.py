@@ -31,7 +31,7 @@ def launches(path, lo=None, hi=None, label=None):
     agg = collections.OrderedDict()
     recs = [(r[ki].split("(")[0], float(r[vi].replace(",", ""))) for r in rows[start:] if len(r) > vi]
     if lo is not None:
-        own = [x for x in recs if x[0].startswith("hyorb::") and "k_pattern" not in x[0] and "k_repack" not in x[0]]
+        own = [x for x in recs if "hyorb::" in x[0] and "k_pattern" not in x[0] and "k_repack" not in x[0]]
         recs = own[lo:hi]
     for k, v in recs:
         agg.setdefault(k, []).append(v)
