@@ -20,6 +20,9 @@ struct DevBuf {
         p = nullptr; cap = 0;
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) -> %s", bytes, cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? HYORB_ENOMEM : HYORB_ECUDA; }
+        // fresh buffers are zeroed once: row padding of the image planes is read (and then multiplied by a zero coefficient or
+        // masked) without ever being written, and this keeps those reads initialised
+        if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaGetLastError(); }
         cap = bytes;
         return HYORB_OK;
     }
