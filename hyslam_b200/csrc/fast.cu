@@ -102,6 +102,7 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
         fence_proxy_async();
+        for (int l = 1; l < plan->nlevels; l++) tensormap_acquire(&tmaps[l]);
         if ((int)blockIdx.x < nTiles) issue(blockIdx.x, 0);
     }
     __syncthreads();

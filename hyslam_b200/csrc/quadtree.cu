@@ -103,12 +103,12 @@ __device__ void bitonic_desc(uint32_t *key, uint32_t *val, int n2)
 
 __device__ __forceinline__ int pow2_at_least(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-// warp-aggregated shared-memory counter increment: lanes that hit the same slot elect one leader.  Must be called by
-// all 32 lanes; slot < 0 = this lane has nothing to add.
+// shared-memory counter increment; slot < 0 = nothing to add.  (A warp-aggregated version -- __match_any_sync, one atomic per
+// distinct slot -- measured slower: 0.54 vs 0.47 ms per 256 C2 images; Blackwell's shared-memory atomics absorb the
+// same-address runs of neighbouring candidates.)
 __device__ __forceinline__ void agg_inc(uint32_t *arr, int slot)
 {
-    const unsigned peers = __match_any_sync(0xffffffffu, slot);
-    if (slot >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&arr[slot], (uint32_t)__popc(peers));
+    if (slot >= 0) atomicAdd(&arr[slot], 1u);
 }
 
 template <int QT>

@@ -47,6 +47,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) { }
 }
+// a tensor map that lives in global memory and was (re)written since an earlier kernel used that address: make the
+// TMA unit's descriptor fetch observe the new bytes (handles are created and destroyed, the allocator reuses addresses)
+__device__ __forceinline__ void tensormap_acquire(const CUtensorMap *map)
+{
+    asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(map) : "memory");
+}
 // one box of a 3-D tensor -> shared memory, completion counted in bytes on `bar`
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z)
 {
