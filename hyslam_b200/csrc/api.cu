@@ -22,7 +22,8 @@ struct DevBuf {
         if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) -> %s", bytes, cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? HYORB_ENOMEM : HYORB_ECUDA; }
         // fresh buffers are zeroed once: row padding of the image planes is read (and then multiplied by a zero coefficient or
         // masked) without ever being written, and this keeps those reads initialised
-        if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaGetLastError(); }
+        // (the handles' streams are non-blocking, i.e. not ordered after the legacy stream this memset runs on: wait for it)
+        if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { cudaGetLastError(); }
         cap = bytes;
         return HYORB_OK;
     }

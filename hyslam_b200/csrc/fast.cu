@@ -102,7 +102,9 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
         fence_proxy_async();
+#ifndef HYORB_NO_TMAP_FENCE
         for (int l = 1; l < plan->nlevels; l++) tensormap_acquire(&tmaps[l]);
+#endif
         if ((int)blockIdx.x < nTiles) issue(blockIdx.x, 0);
     }
     __syncthreads();
