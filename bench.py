@@ -24,6 +24,9 @@ import sys
 import threading
 import time
 
+# hardware queues for the lanes' streams: must be in the environment before the CUDA context exists (hyslam_b200/csrc/api.cu)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -32,7 +32,11 @@ class ORBExtractor:
             F.lib().hyorb_extractor_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter teardown: module globals may already be gone
+            pass
 
     # ---- FeatureExtractor interface (src/features/FeatureExtractor.h:25-37)
     def GetLevels(self):

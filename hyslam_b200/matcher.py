@@ -18,7 +18,11 @@ class _Handle:
             F.lib().hyorb_matcher_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter teardown: module globals may already be gone
+            pass
 
     def sync(self):
         F.check(F.lib().hyorb_matcher_sync(self._h))
@@ -78,7 +82,11 @@ class Vocabulary:
             F.lib().hyorb_vocabulary_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter teardown: module globals may already be gone
+            pass
 
     @staticmethod
     def random_tree(k, L, seed, shrink=0.0):
