@@ -975,6 +975,9 @@ HYORB_API int hyorb_vocabulary_create(int device, int n_nodes, int L, const int3
     up(v->d_desc, node_desc, (size_t)n_nodes * 32);
     up(v->d_word, word_of, sizeof(int32_t) * (size_t)n_nodes);
     up(v->d_weight, weight_of, sizeof(float) * (size_t)n_nodes);
+    // a pageable cudaMemcpy may return once the bytes are staged; the matcher's streams are non-blocking (not ordered after the
+    // legacy stream), so wait for the uploads here
+    if (!rc && cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { set_error("vocabulary upload failed"); rc = HYORB_ECUDA; }
     if (rc) { hyorb_vocabulary_destroy(v); return rc; }
     *out = v;
     return HYORB_OK;
