@@ -272,7 +272,8 @@ def main():
         step_device(args.warmup + i)
     stage_ms, stage_calls = ex.stage_times(reset=True)
     ex.set_profiling(False)
-    ex.set_pipelining(device_lanes=int(os.environ.get("HYORB_LANES", "2")), side_blur=int(os.environ.get("HYORB_SIDE_BLUR", "2")))
+    ex.set_pipelining(device_lanes=int(os.environ.get("HYORB_LANES", "2")), side_blur=int(os.environ.get("HYORB_SIDE_BLUR", "2")),
+                      host_lanes=int(os.environ.get("HYORB_HOST_LANES", "-1")))
 
     # ---- end to end through the host-buffer ABI call (pinned host in, host out).  Each call is synchronous (uploads, kernels
     # and downloads of one batch, pipelined over lanes inside the call).  Two numbers: one handle called back to back, and the
@@ -303,6 +304,7 @@ def main():
         o2, k2 = make_outs()
         keep.append(k2)
         workers.append((hb.ORBExtractor(hb.FeatureExtractorSettings(nFeatures=NFEAT), device=local), o2))
+        workers[-1][0].set_pipelining(host_lanes=int(os.environ.get("HYORB_HOST_LANES", "-1")))
     for exw, ow in workers[1:]:
         exw.process_stereo_batch(h_in, cam, capacity=cap, out=ow)          # allocate its workspace outside the timed region
     start = threading.Barrier(n_workers + 1)

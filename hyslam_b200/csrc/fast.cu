@@ -86,7 +86,7 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ __align__(4) uint8_t s_score[FT_SH * FT_SW];
     __shared__ uint16_t s_list[FT_SH * FT_SW];
-    __shared__ uint8_t s_cf[FT_SW], s_rf[64];
+    __shared__ uint8_t s_cl[FT_SW], s_cr[FT_SW], s_ru[64], s_rd[64];   // 1 = the left / right / upper / lower neighbour is in the same cell
     __shared__ int s_n, s_ne, s_base;
     uint32_t *s_emit = s_planes;            // the planes are dead once the corner test is done
 
@@ -126,12 +126,14 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     if (tid < FT_SW) {
         const int x = x0 + tid;                              // columns left of x = 19 are never emitted
         const int m = x >= DET_MIN ? (x - DET_MIN) % L.wCell : 1;
-        s_cf[tid] = (uint8_t)((m == 0 ? 1 : 0) | (m == L.wCell - 1 ? 2 : 0));
+        s_cl[tid] = (uint8_t)(m != 0);
+        s_cr[tid] = (uint8_t)(m != L.wCell - 1);
     } else if (tid >= 128 && tid < 128 + FT_SH) {
         const int r = tid - 128;
         const int y = sy0 + r;
         const int m = y >= DET_MIN ? (y - DET_MIN) % L.hCell : 1;
-        s_rf[r] = (uint8_t)((m == 0 ? 1 : 0) | (m == L.hCell - 1 ? 2 : 0));
+        s_ru[r] = (uint8_t)(m != 0);
+        s_rd[r] = (uint8_t)(m != L.hCell - 1);
     }
     mbar_wait(&s_bar[buf], (it >> 1) & 1);      // the pixel box has landed
 
@@ -200,12 +202,14 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         const int r = e / FT_SW, cidx = e - r * FT_SW;
         const uint8_t *p = pix8 + (r + 3) * PITCHB + cidx;
         const int v = p[0];
-        // 16-bit lanes: low = centre - ring (dark arcs), high = ring - centre (bright arcs).  With R' = (ring+1)*65535 =
-        // (ring << 16 | -(ring+1)) and A' = (-centre << 16 | centre+1), the lane-wise sum A' + R' is exactly that pair.
-        const uint32_t A = ((uint32_t)(v + 1) & 0xFFFFu) | ((uint32_t)(-v) << 16);
+        // 16-bit lanes: low = centre - ring + 0x4000 (dark arcs, biased), high = ring - centre (bright arcs), as ONE multiply-add
+        // per ring pixel (FMA pipe; the ALU pipe is this kernel's bottleneck): (ring - centre) * 65535 + 0x4000 =
+        // (ring - centre) << 16 | (0x4000 + centre - ring) -- the bias keeps the low lane positive, so nothing carries or borrows
+        // across the lanes; min / max are order-preserving under it and it comes off at the end.
+        const uint32_t A = 0x4000u - (uint32_t)v * 65535u;
         uint32_t wv[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) wv[k] = __vadd2(A, ((uint32_t)p[ring_off(k)] + 1u) * 65535u);
+        for (int k = 0; k < 16; k++) wv[k] = (uint32_t)p[ring_off(k)] * 65535u + A;
         uint32_t m3[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) m3[k] = __vimin3_s16x2(wv[k], wv[(k + 1) & 15], wv[(k + 2) & 15]);
@@ -216,7 +220,7 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         mx = __vimax3_s16x2(mx, m9[3], m9[4]); mx = __vimax3_s16x2(mx, m9[5], m9[6]); mx = __vimax3_s16x2(mx, m9[7], m9[8]);
         mx = __vimax3_s16x2(mx, m9[9], m9[10]); mx = __vimax3_s16x2(mx, m9[11], m9[12]); mx = __vimax3_s16x2(mx, m9[13], m9[14]);
         mx = __vimax3_s16x2(mx, m9[15], m9[15]);
-        const int sd = (int)(short)(mx & 0xFFFFu), sb = (int)mx >> 16;
+        const int sd = (int)(mx & 0xFFFFu) - 0x4000, sb = (int)mx >> 16;
         const int sc = __vimax3_s32(sd, sb, FAST_T) - 1;
         s_score[e] = (uint8_t)sc;
     }
@@ -233,11 +237,11 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         const uint8_t *q = s_score + (inner ? e : FT_SW + FT_C0);
         const int s = q[0];
         const int nl = q[-1], nr = q[1], nu = q[-FT_SW], nul = q[-FT_SW - 1], nur = q[-FT_SW + 1], nd = q[FT_SW], ndl = q[FT_SW - 1], ndr = q[FT_SW + 1];
-        const int cf = s_cf[cidx], rf = s_rf[r];
-        const bool L_ok = !(cf & 1), R_ok = !(cf & 2), U_ok = !(rf & 1), D_ok = !(rf & 2);
-        const int m0 = __vimax3_s32(L_ok ? nl : 0, R_ok ? nr : 0, U_ok ? nu : 0);
-        const int m1 = __vimax3_s32(U_ok && L_ok ? nul : 0, U_ok && R_ok ? nur : 0, D_ok ? nd : 0);
-        const int m2 = __vimax3_s32(D_ok && L_ok ? ndl : 0, D_ok && R_ok ? ndr : 0, m0);
+        // masks applied as multiplies by 0 / 1 (FMA pipe) instead of selects (ALU pipe, the bottleneck)
+        const int Lk = s_cl[cidx], Rk = s_cr[cidx], Uk = s_ru[r], Dk = s_rd[r];
+        const int m0 = __vimax3_s32(nl * Lk, nr * Rk, nu * Uk);
+        const int m1 = __vimax3_s32(nul * (Uk * Lk), nur * (Uk * Rk), nd * Dk);
+        const int m2 = __vimax3_s32(ndl * (Dk * Lk), ndr * (Dk * Rk), m0);
         const bool kept = inner && s > max(m1, m2);
         const uint32_t packed = pack_cand(x0 + cidx - LATTICE_MIN, sy0 + r - LATTICE_MIN, s);
         const unsigned bal = __ballot_sync(0xffffffffu, kept);
