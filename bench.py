@@ -414,7 +414,7 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom] * B, "launch_ms": dom_ms,
                 "timing": f"CUDA events on the launching stream, {ksteps} steps with the kernels serialised (1 lane, no side stream)",
-                "note": "integer-logic kernel bound by the ALU pipe (ncu: ALU pipe 58 % busy, DRAM 2 %), reported against the HBM roofline as the contract asks; DESIGN.md section 4"}
+                "note": "integer-logic kernel bound by the ALU pipe (ncu: ALU pipe 57 % busy, DRAM 2 %), reported against the HBM roofline as the contract asks; DESIGN.md section 4"}
 
     # ---- CPU baseline (oracle port, all host threads) on a bounded sample
     cpu = None
