@@ -70,6 +70,7 @@ SYMBOLS = [
     "hyorb_process_stereo_batch_host", "hyorb_process_stereo_batch_device", "hyorb_extractor_set_profiling",
     "hyorb_extractor_stage_times", "hyorb_extractor_set_pipelining", "hyorb_distinctive_descriptor_host", "hyorb_project_landmarks_host", "hyorb_search_by_projection_host", "hyorb_search_by_projection_ex_host",
     "hyorb_vocabulary_create", "hyorb_vocabulary_destroy", "hyorb_bow_transform_host", "hyorb_search_by_bow_host",
+    "hyorb_preprocess_size", "hyorb_preprocess_device", "hyorb_extract_color_host",
 ]
 N_STAGES = 6
 STAGE_NAMES = ("pyramid", "fast", "quadtree", "blur", "describe", "stereo")
@@ -107,6 +108,11 @@ def lib():
         L.hyorb_matcher_launch_count.restype = C.c_long
         L.hyorb_extractor_debug_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.hyorb_extract_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.hyorb_preprocess_size.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.hyorb_preprocess_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_int, C.c_size_t]
+        L.hyorb_extract_color_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hyorb_extract_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t,
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hyorb_extract_batch_device.argtypes = L.hyorb_extract_batch_host.argtypes

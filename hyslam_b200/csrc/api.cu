@@ -514,6 +514,60 @@ HYORB_API int hyorb_extract_host(hyorb_extractor *h, const uint8_t *gray, int wi
     return HYORB_OK;
 }
 
+HYORB_API int hyorb_preprocess_size(int width, int height, int half_scale, int *out_width, int *out_height)
+{
+    if (!out_width || !out_height) { set_error("null argument"); return HYORB_EINVAL; }
+    return preprocess_size(width, height, half_scale, out_width, out_height);
+}
+
+HYORB_API int hyorb_preprocess_device(hyorb_extractor *h, const uint8_t *d_src, int n_images, int width, int height, int stride, size_t image_stride,
+                                      int channels, int rgb_order, int half_scale, uint8_t *d_gray, int gray_stride, size_t gray_image_stride)
+{
+    if (!h || !d_src || !d_gray) { set_error("null argument"); return HYORB_EINVAL; }
+    HY_CUDA(cudaSetDevice(h->device));
+    return launch_preprocess(d_src, stride, image_stride, width, height, channels, rgb_order != 0, half_scale != 0, d_gray, gray_stride, gray_image_stride,
+                             n_images, h->stream, &h->launches);
+}
+
+HYORB_API int hyorb_extract_color_host(hyorb_extractor *h, const uint8_t *image, int width, int height, int stride, int channels, int rgb_order,
+                                       int half_scale, uint8_t *gray_out, int gray_out_stride, hyorb_keypoint *kps, uint8_t *desc, int capacity, int *n)
+{
+    if (!h || !n) { set_error("null argument"); return HYORB_EINVAL; }
+    *n = 0;
+    if (!image || width <= 0 || height <= 0) return HYORB_OK;     // empty image -> silent return, like the gray entry point
+    if (!kps || !desc || capacity < 1 || (channels != 1 && channels != 3 && channels != 4) || stride < width * channels) { set_error("bad argument"); return HYORB_EINVAL; }
+    int gw, gh;
+    HY_TRY(preprocess_size(width, height, half_scale, &gw, &gh));
+    if (gray_out && gray_out_stride < gw) { set_error("bad argument"); return HYORB_EINVAL; }
+    HY_CUDA(cudaSetDevice(h->device));
+    HY_TRY(ex_ensure_plan(h, gw, gh));
+    const PlanDev &P = h->plan.dev;
+    const int pitch = P.lv[0].pitch;
+    const size_t src_bytes = (size_t)stride * (height - 1) + (size_t)width * channels;
+    HY_TRY(h->d_raw.ensure(src_bytes + 16));
+    HY_TRY(h->d_in.ensure((size_t)pitch * gh + 512));
+    HY_TRY(h->d_kps.ensure(sizeof(hyorb_keypoint) * (size_t)capacity));
+    HY_TRY(h->d_desc.ensure((size_t)HYORB_DESC_BYTES * capacity));
+    HY_TRY(h->d_counts.ensure(sizeof(int32_t)));
+    HY_CUDA(cudaMemcpyAsync(h->d_raw.p, image, src_bytes, cudaMemcpyHostToDevice, h->stream));
+    HY_TRY(launch_preprocess(h->d_raw.as<uint8_t>(), stride, 0, width, height, channels, rgb_order != 0, half_scale != 0, h->d_in.as<uint8_t>(), pitch,
+                             (size_t)pitch * gh, 1, h->stream, &h->launches));
+    if (gray_out)       // the reference keeps the gray frame (track_data.image, ImageProcessing.cpp:109)
+        HY_CUDA(cudaMemcpy2DAsync(gray_out, gray_out_stride, h->d_in.p, pitch, gw, gh, cudaMemcpyDeviceToHost, h->stream));
+    Level0 l0{h->d_in.as<uint8_t>(), pitch, (unsigned long long)pitch * gh};
+    HY_TRY(ex_run(h, l0, 1, gw, gh, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), capacity, h->d_counts.as<int32_t>()));
+    int32_t cnt = 0;
+    HY_CUDA(cudaMemcpyAsync(&cnt, h->d_counts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    HY_TRY(ex_sync(h));
+    if (cnt > 0) {
+        HY_CUDA(cudaMemcpyAsync(kps, h->d_kps.p, sizeof(hyorb_keypoint) * (size_t)cnt, cudaMemcpyDeviceToHost, h->stream));
+        HY_CUDA(cudaMemcpyAsync(desc, h->d_desc.p, (size_t)HYORB_DESC_BYTES * cnt, cudaMemcpyDeviceToHost, h->stream));
+        HY_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    *n = cnt;
+    return HYORB_OK;
+}
+
 HYORB_API int hyorb_process_stereo_batch_device(hyorb_extractor *h, const hyorb_stereo_params *sp, const uint8_t *d_images, int n_pairs,
                                                 int width, int height, int stride, size_t image_stride, hyorb_keypoint *d_kps, uint8_t *d_desc,
                                                 int capacity, int32_t *d_counts, float *d_uR, float *d_depth)

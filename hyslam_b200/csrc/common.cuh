@@ -127,6 +127,10 @@ int launch_pyramid(const PlanDev &hp, const PlanDev *dp, Level0 l0, uint8_t *pyr
 // img0 = index of the lane's first image inside the tensors tm0 (level 0) / tmaps[l] (pyramid levels >= 1) describe
 int launch_fast(const PlanDev &hp, const PlanDev *dp, const CUtensorMap &tm0, const CUtensorMap *tmaps, int img0, uint32_t *cand, int *candCount,
                 int *status, int B, int sm_count, cudaStream_t st, long *launches);
+// A.0 camera-image preparation (preprocess.cu): optional 0.5 box scale + RGB|BGR[A] -> gray for B images
+int preprocess_size(int w, int h, int half_scale, int *ow, int *oh);
+int launch_preprocess(const uint8_t *src, int spitch, size_t sstride, int w, int h, int channels, int rgb_order, int half_scale, uint8_t *dst, int dpitch,
+                      size_t dstride, int B, cudaStream_t st, long *launches);
 int launch_repack(const uint8_t *src, int spitch, size_t sstride, uint8_t *dst, int dpitch, size_t dstride, int w, int h, int B, cudaStream_t st, long *launches);
 int launch_quadtree(const PlanDev &hp, const PlanDev *dp, const uint32_t *cand, const int *candCount, const uint32_t *lut,
                     uint32_t *qcode, uint16_t *qnode, uint2 *qleaf, uint32_t *sel, int *selCount, int *status, int B, cudaStream_t st, long *launches);

@@ -79,6 +79,28 @@ class ORBExtractor:
         F.check(F.lib().hyorb_extract_host(self._h, F.ptr(image), W, H, image.strides[0], F.ptr(kps), F.ptr(desc), cap, C.byref(n)))
         return kps[:n.value].copy(), desc[:n.value].copy()
 
+    def extract_color(self, image, rgb=True, half_scale=False, capacity=None):
+        """ImageProcessing::PreProcessImg (ImageProcessing.cpp:118-138: scale 1.0 / 0.5, RGB|BGR[A] -> gray) + operator() on one camera
+        frame (HxW or HxWxC uint8).  Returns (gray, kps, desc); gray is the frame the reference keeps as track_data.image."""
+        if image is None or image.size == 0:
+            return np.zeros((0, 0), np.uint8), np.zeros(0, F.KP_DTYPE), np.zeros((0, 32), np.uint8)
+        if image.dtype != np.uint8 or image.ndim not in (2, 3):
+            raise ValueError("image must be 8-bit with 1, 3 or 4 interleaved channels")
+        cn = 1 if image.ndim == 2 else image.shape[2]
+        if image.strides[-1] != 1 or (image.ndim == 3 and image.strides[1] != cn):
+            image = np.ascontiguousarray(image)
+        H, W = image.shape[:2]
+        gw, gh = C.c_int(), C.c_int()
+        F.check(F.lib().hyorb_preprocess_size(W, H, int(half_scale), C.byref(gw), C.byref(gh)))
+        gray = np.empty((gh.value, gw.value), np.uint8)
+        cap = capacity or self.default_capacity()
+        kps = np.empty(cap, F.KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int(0)
+        F.check(F.lib().hyorb_extract_color_host(self._h, F.ptr(image), W, H, image.strides[0], cn, int(rgb), int(half_scale), F.ptr(gray),
+                                                 gray.strides[0], F.ptr(kps), F.ptr(desc), cap, C.byref(n)))
+        return gray, kps[:n.value].copy(), desc[:n.value].copy()
+
     def extract_batch(self, images, capacity=None):
         """Throughput form over a [B,H,W] uint8 host array.  Returns (kps[B,cap], desc[B,cap,32], counts[B])."""
         images = np.ascontiguousarray(images, np.uint8)

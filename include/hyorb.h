@@ -132,6 +132,22 @@ typedef struct hyorb_stereo_params {
     float size_ref;  /* FeatureExtractorSettings::size_ref = 31 (FeatureExtractorSettings.h:27) */
 } hyorb_stereo_params;
 
+/* ImageProcessing::PreProcessImg (src/main/ImageProcessing.cpp:118-138): cv::resize(img, img, Size(), fscale, fscale)
+ * followed by cvtColor(RGB|BGR[A] -> GRAY), for the scales the reference's camera configurations use: half_scale = 0
+ * (fscale 1.0, copy) or 1 (fscale 0.5 = OpenCV's INTER_AREA 2x2 box path; needs 2*cvRound(src*0.5) <= src, else
+ * HYORB_EUNSUPPORTED).  channels: 1, 3 or 4 interleaved bytes per pixel (alpha ignored); rgb_order: cam_data.RGB (1 = RGB[A],
+ * 0 = BGR[A]).  hyorb_preprocess_size gives the gray frame's size.  hyorb_preprocess_device converts n_images device
+ * frames (asynchronously on the handle's stream, like the other *_device entry points; its output can be fed to them
+ * directly).  hyorb_extract_color_host = PreProcessImg + ORBExtractor::operator() on one HOST camera frame; gray_out
+ * (optional, gray_out_stride bytes per row) receives the gray frame the reference keeps as track_data.image (:109). */
+HYORB_API int hyorb_preprocess_size(int width, int height, int half_scale, int *out_width, int *out_height);
+HYORB_API int hyorb_preprocess_device(hyorb_extractor *h, const uint8_t *d_src, int n_images, int width, int height, int stride,
+                                      size_t image_stride, int channels, int rgb_order, int half_scale, uint8_t *d_gray,
+                                      int gray_stride, size_t gray_image_stride);
+HYORB_API int hyorb_extract_color_host(hyorb_extractor *h, const uint8_t *image, int width, int height, int stride, int channels,
+                                       int rgb_order, int half_scale, uint8_t *gray_out, int gray_out_stride,
+                                       hyorb_keypoint *kps, uint8_t *desc, int capacity, int *n);
+
 /* ImageProcessing::ProcessStereoImage (src/main/ImageProcessing.cpp:69-116) over n_pairs stereo pairs in one call:
  * extractor_left(imL), extractor_right(imR) (:82-83), then Stereomatcher(...).computeStereoMatches() (:101-102).
  * Images are interleaved: image 2p = left, 2p+1 = right of pair p.  kps/desc/counts as hyorb_extract_batch_*

@@ -86,6 +86,24 @@ public:
         keypoints.assign(k, k + n);
         cuda_marshal::appendDescriptors(desc.data(), n, dist_func, descriptors);
     }
+    // ImageProcessing::PreProcessImg (ImageProcessing.cpp:118-138) + operator() in one call: the camera frame (CV_8UC1 / C3 / C4;
+    // mbRGB = cam_data.RGB; fscale = cam_data.scale, 1.0f or 0.5f as in the reference's configurations) is uploaded as it is,
+    // scaled and converted to gray on the device; `gray` receives the frame the reference keeps as track_data.image (:109).
+    void extractFromCameraFrame(const cv::Mat &frame, bool mbRGB, float fscale, cv::Mat &gray, std::vector<cv::KeyPoint> &keypoints,
+                                std::vector<FeatureDescriptor> &descriptors)
+    {
+        if (frame.empty()) return;
+        if (fscale != 1.0f && fscale != 0.5f) throw std::runtime_error("CudaORBExtractor: camera scale must be 1.0 or 0.5");
+        const int half = fscale == 0.5f ? 1 : 0;
+        int gw = 0, gh = 0, n = 0;
+        cuda_marshal::check(hyorb_preprocess_size(frame.cols, frame.rows, half, &gw, &gh));
+        gray.create(gh, gw, CV_8UC1);
+        cuda_marshal::check(hyorb_extract_color_host(h, frame.data, frame.cols, frame.rows, (int)frame.step, frame.channels(), mbRGB ? 1 : 0, half,
+                                                     gray.data, (int)gray.step, kp.data(), desc.data(), cap, &n));
+        const cv::KeyPoint *k = reinterpret_cast<const cv::KeyPoint *>(kp.data());
+        keypoints.assign(k, k + n);
+        cuda_marshal::appendDescriptors(desc.data(), n, dist_func, descriptors);
+    }
     int GetLevels() override { return nlevels; }
     float GetScaleFactor() override { return scale; }
     std::vector<float> GetScaleFactors() override { return sf; }

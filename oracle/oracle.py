@@ -242,6 +242,21 @@ def hamming(a, b):
     return lib().orc_hamming(_p(a), _p(b))
 
 
+def preprocess(img, rgb=True, half_scale=False):
+    """ImageProcessing::PreProcessImg (ImageProcessing.cpp:118-138): scale 1.0 / 0.5 then RGB|BGR[A] -> gray.  img: HxW or HxWxC uint8."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    ow, oh = C.c_int(), C.c_int()
+    if lib().orc_preprocess_size(w, h, int(half_scale), C.byref(ow), C.byref(oh)) != 0:
+        raise ValueError("preprocess: unsupported size for the half-scale box path")
+    out = np.empty((oh.value, ow.value), np.uint8)
+    rc = lib().orc_preprocess(_p(img), w, h, img.strides[0], cn, int(rgb), int(half_scale), _p(out), out.strides[0])
+    if rc != 0:
+        raise RuntimeError(f"orc_preprocess rc={rc}")
+    return out
+
+
 def distinctive_descriptor(desc, lm_off):
     """MapPointDBEntry::_computeDistinctiveDescriptor_ (MapPointDB.cpp:127-171) over CSR landmark lists: (best_idx, best_median)."""
     desc = np.ascontiguousarray(desc, np.uint8); lm_off = np.ascontiguousarray(lm_off, np.int32)

@@ -9,6 +9,8 @@
 #define CV_8U 0
 #define CV_32F 5
 #define CV_8UC1 0
+#define CV_8UC3 16
+#define CV_8UC4 24
 namespace cv {
 struct Point2f { float x = 0, y = 0; };
 struct KeyPoint {            // 28 bytes, same member order as OpenCV's
@@ -22,6 +24,7 @@ public:
     Mat(int r, int c, int type, void *ext, size_t stp = 0) : rows(r), cols(c), data((unsigned char *)ext), type_(type) { step = stp ? stp : (size_t)c * esz(); }
     void create(int r, int c, int type) { rows = r; cols = c; type_ = type; step = (size_t)c * esz(); store_ = std::make_shared<std::vector<unsigned char>>(step * (size_t)r); data = store_->data(); }
     int type() const { return type_; }
+    int channels() const { return (type_ >> 3) + 1; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     bool isContinuous() const { return step == (size_t)cols * esz(); }
     Mat clone() const { Mat m; if (empty()) return m; m.create(rows, cols, type_); for (int r = 0; r < rows; r++) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz()); return m; }
@@ -30,7 +33,7 @@ public:
     template <typename T> T *ptr(int r = 0) { return (T *)(data + (size_t)r * step); }
     template <typename T> const T *ptr(int r = 0) const { return (const T *)(data + (size_t)r * step); }
 private:
-    size_t esz() const { return type_ == CV_32F ? 4 : 1; }
+    size_t esz() const { return ((type_ & 7) == CV_32F ? 4 : 1) * (size_t)channels(); }
     int type_ = CV_8U; std::shared_ptr<std::vector<unsigned char>> store_;
 };
 class _InputArray {           // cv::InputArray = const _InputArray&

@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <thread>
 
 using namespace HYSLAM;
@@ -63,6 +64,25 @@ int main(int argc, char **argv)
         for (size_t l = 0; 3 * l + 2 < mDescriptors.size() && l < mDescriptorsRight.size() && l < 50; l++)
             observations.push_back({mDescriptors[3 * l], mDescriptors[3 * l + 1], mDescriptors[3 * l + 2], mDescriptorsRight[l]});
         const std::vector<int32_t> distinctive = scan.distinctiveDescriptors(observations);
+
+        // PreProcessImg + extraction on a camera frame: a BGR frame with B = G = R = the left gray image converts back to exactly
+        // that image ((g * 32768 + 16384) >> 15 = g), so the result must equal the left extraction above
+        {
+            cv::Mat bgr(h, w, CV_8UC3);
+            for (int y = 0; y < h; y++)
+                for (int x = 0; x < w; x++)
+                    for (int c = 0; c < 3; c++) bgr.ptr<unsigned char>(y)[3 * x + c] = mImGray.at<unsigned char>(y, x);
+            cv::Mat gray2;
+            std::vector<cv::KeyPoint> k2;
+            std::vector<FeatureDescriptor> d2;
+            static_cast<CudaORBExtractor *>(extractor_left.get())->extractFromCameraFrame(bgr, false, 1.0f, gray2, k2, d2);
+            bool same = gray2.rows == h && gray2.cols == w && k2.size() == mvKeys.size();
+            for (int y = 0; same && y < h; y++) same = memcmp(gray2.ptr<unsigned char>(y), mImGray.ptr<unsigned char>(y), (size_t)w) == 0;
+            same = same && (k2.empty() || memcmp(k2.data(), mvKeys.data(), k2.size() * sizeof(cv::KeyPoint)) == 0);
+            same = same && cuda_marshal::packDescriptors(d2) == cuda_marshal::packDescriptors(mDescriptors);
+            if (!same) { fprintf(stderr, "camera-frame path differs from the gray path\n"); return 1; }
+            printf("camera frame ok\n");
+        }
 
         FILE *f = fopen(argv[8], "wb");
         if (!f) { fprintf(stderr, "cannot write %s\n", argv[8]); return 2; }

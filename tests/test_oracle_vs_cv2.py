@@ -136,3 +136,25 @@ def test_landmark_projection_matches_cv2_expressions(seed, stereo):
         same = all((np.isnan(a) and np.isnan(b)) or a == b for a, b in zip(got, want))
         assert same and bool(passed[i]) == ok, (i, got, want, passed[i], ok)
     assert 0.1 < passed.mean() < 0.9
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (36, 52), (376, 1241), (480, 752)])
+@pytest.mark.parametrize("cn", [1, 3, 4])
+def test_preprocess_matches_cv2(shape, cn):
+    """ImageProcessing::PreProcessImg (ImageProcessing.cpp:118-138) restated: cv::resize at fscale 1.0 / 0.5 then cvtColor to gray."""
+    h, w = shape
+    rng = np.random.default_rng(h * 7 + cn)
+    img = rng.integers(0, 256, (h, w, cn), dtype=np.uint8) if cn > 1 else rng.integers(0, 256, (h, w), dtype=np.uint8)
+    for rgb in (True, False):
+        for half in (False, True):
+            ref = cv2.resize(img, None, fx=0.5, fy=0.5) if half else img
+            if cn == 3:
+                ref = cv2.cvtColor(ref, cv2.COLOR_RGB2GRAY if rgb else cv2.COLOR_BGR2GRAY)
+            elif cn == 4:
+                ref = cv2.cvtColor(ref, cv2.COLOR_RGBA2GRAY if rgb else cv2.COLOR_BGRA2GRAY)
+            assert np.array_equal(O.preprocess(img, rgb, half), ref), (shape, cn, rgb, half)
+
+
+def test_preprocess_rejects_sizes_outside_the_box_path():
+    with pytest.raises(ValueError):
+        O.preprocess(np.zeros((35, 51, 3), np.uint8), True, True)       # cvRound(17.5) = 18, 2*18 > 35
