@@ -715,7 +715,7 @@ struct hyorb_matcher {
     bool own_stream = false;
     long launches = 0;
     DevBuf d_status, d_a, d_b, d_c, d_d, d_e, d_f, d_g, d_h, d_i, d_j, d_k, d_l;   // generic staging slots
-    DevBuf d_pkey, d_psecond, d_rowtab, d_bestd, d_cellof, d_cellcnt;
+    DevBuf d_pkey, d_psecond, d_rowtab, d_bestd, d_cellof, d_cellcnt, d_kp1, d_kp2;
 };
 
 static int m_prepare(hyorb_matcher *m)
@@ -777,7 +777,7 @@ HYORB_API int hyorb_matcher_destroy(hyorb_matcher *m)
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
     DevBuf *bufs[] = {&m->d_status, &m->d_a, &m->d_b, &m->d_c, &m->d_d, &m->d_e, &m->d_f, &m->d_g, &m->d_h, &m->d_i, &m->d_j, &m->d_k, &m->d_l,
-                      &m->d_pkey, &m->d_psecond, &m->d_rowtab, &m->d_bestd, &m->d_cellof, &m->d_cellcnt};
+                      &m->d_pkey, &m->d_psecond, &m->d_rowtab, &m->d_bestd, &m->d_cellof, &m->d_cellcnt, &m->d_kp1, &m->d_kp2};
     for (DevBuf *b : bufs) b->release();
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -800,9 +800,22 @@ HYORB_API int hyorb_match_bruteforce_device(hyorb_matcher *m, const uint8_t *d_q
                                    m->d_psecond.as<uint16_t>(), ns, m->stream, &m->launches);
 }
 
-HYORB_API int hyorb_match_csr_host(hyorb_matcher *m, const uint8_t *q_desc, int nq, const uint8_t *t_desc, int nt, const int32_t *cand_off,
-                                   const int32_t *cand_idx, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best,
-                                   uint16_t *second, uint8_t *accepted)
+struct EpipolarHost { const hyorb_keypoint *kps1, *kps2; const float *F12; float sigma_ref, size_ref; };
+static int m_epipolar_upload(hyorb_matcher *m, const EpipolarHost *eh, int n1, int n2, EpipolarDev *epi)
+{
+    *epi = EpipolarDev{};
+    if (!eh) return HYORB_OK;
+    HY_TRY(m_upload(m, m->d_kp1, eh->kps1, sizeof(hyorb_keypoint) * (size_t)n1));
+    HY_TRY(m_upload(m, m->d_kp2, eh->kps2, sizeof(hyorb_keypoint) * (size_t)n2));
+    epi->kps1 = m->d_kp1.as<hyorb_keypoint>(); epi->kps2 = m->d_kp2.as<hyorb_keypoint>();
+    for (int i = 0; i < 9; i++) epi->F[i] = eh->F12[i];
+    epi->sigma_ref = eh->sigma_ref; epi->size_ref = eh->size_ref;
+    return HYORB_OK;
+}
+
+static int m_match_csr(hyorb_matcher *m, const uint8_t *q_desc, int nq, const uint8_t *t_desc, int nt, const int32_t *cand_off,
+                       const int32_t *cand_idx, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best,
+                       uint16_t *second, uint8_t *accepted, const EpipolarHost *eh)
 {
     HY_TRY(m_prepare(m));
     if (nq < 0 || nt < 0 || rule < 0 || rule > 2 || (cand_off == nullptr) != (cand_idx == nullptr)) { set_error("bad argument"); return HYORB_EINVAL; }
@@ -823,10 +836,13 @@ HYORB_API int hyorb_match_csr_host(hyorb_matcher *m, const uint8_t *q_desc, int 
         }
         HY_TRY(m_upload(m, m->d_g, cand_off, sizeof(int32_t) * ((size_t)nq + 1)));
         HY_TRY(m_upload(m, m->d_h, cand_idx, sizeof(int32_t) * (size_t)total));
+        EpipolarDev epi;
+        HY_TRY(m_epipolar_upload(m, eh, nq, nt, &epi));
         HY_TRY(launch_match_csr(m->d_a.as<uint8_t>(), nq, m->d_b.as<uint8_t>(), nt, m->d_g.as<int32_t>(), m->d_h.as<int32_t>(), rule, thr, ratio,
                                 m->d_c.as<int32_t>(), m->d_d.as<uint16_t>(), m->d_e.as<uint16_t>(), m->d_f.as<uint8_t>(), m->d_status.as<int>(),
-                                m->stream, &m->launches));
+                                epi, m->stream, &m->launches));
     } else {
+        if (eh) { set_error("the epipolar criterion needs candidate lists"); return HYORB_EINVAL; }
         HY_TRY(hyorb_match_bruteforce_device(m, m->d_a.as<uint8_t>(), nq, m->d_b.as<uint8_t>(), nt, rule, thr, ratio, m->d_c.as<int32_t>(),
                                              m->d_d.as<uint16_t>(), m->d_e.as<uint16_t>(), m->d_f.as<uint8_t>()));
     }
@@ -835,6 +851,24 @@ HYORB_API int hyorb_match_csr_host(hyorb_matcher *m, const uint8_t *q_desc, int 
     HY_CUDA(cudaMemcpyAsync(second, m->d_e.p, sizeof(uint16_t) * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
     HY_CUDA(cudaMemcpyAsync(accepted, m->d_f.p, (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
     return m_sync(m);
+}
+
+HYORB_API int hyorb_match_csr_host(hyorb_matcher *m, const uint8_t *q_desc, int nq, const uint8_t *t_desc, int nt, const int32_t *cand_off,
+                                   const int32_t *cand_idx, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best,
+                                   uint16_t *second, uint8_t *accepted)
+{
+    return m_match_csr(m, q_desc, nq, t_desc, nt, cand_off, cand_idx, rule, thr, ratio, best_idx, best, second, accepted, nullptr);
+}
+
+HYORB_API int hyorb_match_csr_epipolar_host(hyorb_matcher *m, const hyorb_keypoint *q_kps, const uint8_t *q_desc, int nq, const hyorb_keypoint *t_kps,
+                                            const uint8_t *t_desc, int nt, const int32_t *cand_off, const int32_t *cand_idx, const float *F12,
+                                            float sigma_ref, float size_ref, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best,
+                                            uint16_t *second, uint8_t *accepted)
+{
+    if (!F12 || !cand_off || !cand_idx || (nq > 0 && !q_kps) || (nt > 0 && !t_kps)) { set_error("null argument"); return HYORB_EINVAL; }
+    if (!(size_ref > 0.f)) { set_error("size_ref must be positive"); return HYORB_EINVAL; }
+    const EpipolarHost eh{q_kps, t_kps, F12, sigma_ref, size_ref};
+    return m_match_csr(m, q_desc, nq, t_desc, nt, cand_off, cand_idx, rule, thr, ratio, best_idx, best, second, accepted, &eh);
 }
 
 HYORB_API int hyorb_grid_build_host(hyorb_matcher *m, const hyorb_keypoint *kps, int n, const hyorb_bounds *b, int32_t *cell_off, int32_t *cell_idx)
@@ -1072,9 +1106,10 @@ HYORB_API int hyorb_bow_transform_host(hyorb_matcher *m, const hyorb_vocabulary 
     return m_sync(m);
 }
 
-HYORB_API int hyorb_search_by_bow_host(hyorb_matcher *m, const hyorb_vocabulary *v, const uint8_t *desc1, const uint8_t *mask1, int n1,
-                                       const uint8_t *desc2, const uint8_t *mask2, int n2, int levelsup, int rule, float thr, float ratio,
-                                       int32_t *node1, int32_t *node2, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted)
+static int m_search_by_bow(hyorb_matcher *m, const hyorb_vocabulary *v, const uint8_t *desc1, const uint8_t *mask1, int n1,
+                           const uint8_t *desc2, const uint8_t *mask2, int n2, int levelsup, int rule, float thr, float ratio,
+                           int32_t *node1, int32_t *node2, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted,
+                           const EpipolarHost *eh)
 {
     HY_TRY(m_prepare(m));
     if (!v || n1 < 0 || n2 < 0 || rule < 0 || rule > 2) { set_error("bad argument"); return HYORB_EINVAL; }
@@ -1099,10 +1134,12 @@ HYORB_API int hyorb_search_by_bow_host(hyorb_matcher *m, const hyorb_vocabulary 
     HY_TRY(m->d_psecond.ensure(sizeof(uint16_t) * 2 * (size_t)n1 + (size_t)n1));   // best | second | accepted
     uint16_t *d_best = m->d_psecond.as<uint16_t>(), *d_sec = d_best + n1;
     uint8_t *d_acc = (uint8_t *)(d_sec + n1);
+    EpipolarDev epi;
+    HY_TRY(m_epipolar_upload(m, eh, n1, n2, &epi));
     HY_TRY(launch_bow_match(m->d_a.as<uint8_t>(), mask1 ? m->d_k.as<uint8_t>() : nullptr, m->d_g.as<int32_t>(), n1, m->d_b.as<uint8_t>(),
                             mask2 ? m->d_l.as<uint8_t>() : nullptr, m->d_h.as<int32_t>(), n2, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(),
                             m->d_cellof.as<int32_t>(), m->d_rowtab.p, tb, m->d_cellcnt.as<int32_t>(), m->d_bestd.as<int32_t>(), rule, thr, ratio,
-                            m->d_pkey.as<int32_t>(), d_best, d_sec, d_acc, m->stream, &m->launches));
+                            m->d_pkey.as<int32_t>(), d_best, d_sec, d_acc, epi, m->stream, &m->launches));
     HY_CUDA(cudaMemcpyAsync(best_idx, m->d_pkey.p, sizeof(int32_t) * (size_t)n1, cudaMemcpyDeviceToHost, m->stream));
     HY_CUDA(cudaMemcpyAsync(best, d_best, sizeof(uint16_t) * (size_t)n1, cudaMemcpyDeviceToHost, m->stream));
     HY_CUDA(cudaMemcpyAsync(second, d_sec, sizeof(uint16_t) * (size_t)n1, cudaMemcpyDeviceToHost, m->stream));
@@ -1110,6 +1147,26 @@ HYORB_API int hyorb_search_by_bow_host(hyorb_matcher *m, const hyorb_vocabulary 
     if (node1) HY_CUDA(cudaMemcpyAsync(node1, m->d_g.p, sizeof(int32_t) * (size_t)n1, cudaMemcpyDeviceToHost, m->stream));
     if (node2 && n2 > 0) HY_CUDA(cudaMemcpyAsync(node2, m->d_h.p, sizeof(int32_t) * (size_t)n2, cudaMemcpyDeviceToHost, m->stream));
     return m_sync(m);
+}
+
+HYORB_API int hyorb_search_by_bow_host(hyorb_matcher *m, const hyorb_vocabulary *v, const uint8_t *desc1, const uint8_t *mask1, int n1,
+                                       const uint8_t *desc2, const uint8_t *mask2, int n2, int levelsup, int rule, float thr, float ratio,
+                                       int32_t *node1, int32_t *node2, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted)
+{
+    return m_search_by_bow(m, v, desc1, mask1, n1, desc2, mask2, n2, levelsup, rule, thr, ratio, node1, node2, best_idx, best, second, accepted, nullptr);
+}
+
+HYORB_API int hyorb_search_for_triangulation_host(hyorb_matcher *m, const hyorb_vocabulary *v, const hyorb_keypoint *kps1, const uint8_t *desc1,
+                                                  const uint8_t *mask1, int n1, const hyorb_keypoint *kps2, const uint8_t *desc2,
+                                                  const uint8_t *mask2, int n2, int levelsup, const float *F12, float sigma_ref, float size_ref,
+                                                  float thr, float ratio, int32_t *node1, int32_t *node2, int32_t *best_idx, uint16_t *best,
+                                                  uint16_t *second, uint8_t *accepted)
+{
+    if (!F12 || (n1 > 0 && !kps1) || (n2 > 0 && !kps2)) { set_error("null argument"); return HYORB_EINVAL; }
+    if (!(size_ref > 0.f)) { set_error("size_ref must be positive"); return HYORB_EINVAL; }
+    const EpipolarHost eh{kps1, kps2, F12, sigma_ref, size_ref};
+    return m_search_by_bow(m, v, desc1, mask1, n1, desc2, mask2, n2, levelsup, HYORB_RULE_BOW, thr, ratio, node1, node2, best_idx, best, second,
+                           accepted, &eh);
 }
 
 HYORB_API int hyorb_distinctive_descriptor_host(hyorb_matcher *m, const uint8_t *desc, const int32_t *lm_off, int n_landmarks, int32_t *best_idx,

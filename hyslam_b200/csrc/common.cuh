@@ -142,8 +142,12 @@ int launch_describe(const PlanDev &hp, const PlanDev *dp, const uint8_t *blur, c
 int launch_match_bruteforce(const uint8_t *q, int nq, const uint8_t *t, int nt, int rule, float thr, float ratio,
                             int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted,
                             uint32_t *pkey, uint16_t *psecond, int nsplit, cudaStream_t st, long *launches);
+// EpipolarConsistencyBoWCriterion (MatchCriteria.cpp:641-676) as a candidate filter of the candidate-list scans: device keypoints of
+// both sets, F12 row-major, FeatureExtractorSettings::sigma_ref / size_ref.  kps1 == nullptr = no epipolar criterion.
+struct EpipolarDev { const hyorb_keypoint *kps1, *kps2; float F[9]; float sigma_ref, size_ref; };
 int launch_match_csr(const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *off, const int32_t *idx, int rule, float thr,
-                     float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, int *status, cudaStream_t st, long *launches);
+                     float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, int *status, const EpipolarDev &epi,
+                     cudaStream_t st, long *launches);
 int launch_grid_build(const hyorb_keypoint *kps, int n, hyorb_bounds b, int32_t *cell_off, int32_t *cell_idx, int32_t *cell_of, int32_t *cell_cnt,
                       cudaStream_t st, long *launches);
 int launch_match_window(const hyorb_keypoint *kps, const uint8_t *tdesc, const float *t_uR, const uint8_t *t_matched, int nt, hyorb_bounds b,
@@ -162,7 +166,7 @@ size_t bow_sort_temp_bytes(int n);
 int launch_bow_match(const uint8_t *desc1, const uint8_t *mask1, const int32_t *node1, int n1, const uint8_t *desc2, const uint8_t *mask2,
                      const int32_t *node2, int n2, int32_t *iota, int32_t *sorted_node2, int32_t *sorted_idx2, void *temp, size_t temp_bytes,
                      int32_t *cbegin, int32_t *cend, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
-                     uint8_t *accepted, cudaStream_t st, long *launches);
+                     uint8_t *accepted, const EpipolarDev &epi, cudaStream_t st, long *launches);
 int launch_distinctive(const uint8_t *desc, const int32_t *off, int n_lm, int32_t *best_idx, int32_t *best_median, cudaStream_t st, long *launches);
 size_t stereo_scratch_ints_per_pair(int capacity);
 int launch_stereo(const hyorb_stereo_params &sp, int n_pairs, const hyorb_keypoint *kps, const uint8_t *desc, const int32_t *counts, int capacity,

@@ -105,11 +105,34 @@ __global__ void k_bf_finalize(const uint32_t *__restrict__ pkey, const uint16_t 
     write_result(qi, bkey, second, (int)(bkey & POS_MASK), rule, thr, ratio, best_idx, best, sec, accepted);
 }
 
+// ---------------- EpipolarConsistencyBoWCriterion::CheckDistEpipolarLine (MatchCriteria.cpp:659-676), plain fp32, left to right, unfused
+struct EpiLine { float a, b, c, den; };
+__device__ __forceinline__ EpiLine epi_line(const EpipolarDev &epi, int qi)       // l = x1' F12 = [a b c]
+{
+    const float x1 = epi.kps1[qi].x, y1 = epi.kps1[qi].y;
+    EpiLine l;
+    l.a = x1 * epi.F[0] + y1 * epi.F[3] + epi.F[6];
+    l.b = x1 * epi.F[1] + y1 * epi.F[4] + epi.F[7];
+    l.c = x1 * epi.F[2] + y1 * epi.F[5] + epi.F[8];
+    l.den = l.a * l.a + l.b * l.b;
+    return l;
+}
+__device__ __forceinline__ bool epi_pass(const EpipolarDev &epi, const EpiLine &l, int ti)
+{
+    const hyorb_keypoint k2 = epi.kps2[ti];
+    const float sf = k2.size / epi.size_ref;                    // FeatureExtractorSettings::determineSigma2 (FeatureExtractorSettings.cpp:5-8)
+    const float sigma2 = epi.sigma_ref * (sf * sf);
+    const float num = l.a * k2.x + l.b * k2.y + l.c;
+    if (l.den == 0.f) return false;
+    const float dsqr = num * num / l.den;
+    return (double)dsqr < 3.84 * (double)sigma2;                // `dsqr < 3.84*sigma2`: the literal is a double
+}
+
 // ---------------- candidate lists (CSR): one warp per query, lanes stride over the list
 __global__ void __launch_bounds__(256)
 k_match_csr(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, const int32_t *__restrict__ off,
             const int32_t *__restrict__ idx, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *sec,
-            uint8_t *accepted, int *status)
+            uint8_t *accepted, int *status, const EpipolarDev epi)
 {
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -117,9 +140,12 @@ k_match_csr(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, in
     const uint4 a0 = q[2 * qi], a1 = q[2 * qi + 1];
     const int lo = off[qi], hi = off[qi + 1];
     uint32_t bkey = KEY_NONE; int second = DIST_NONE;
+    EpiLine el{0.f, 0.f, 0.f, 0.f};
+    if (epi.kps1) el = epi_line(epi, qi);
     for (int c = lo + lane; c < hi; c += 32) {
         const int ti = idx[c];
         if (ti < 0 || ti >= nt) { atomicOr(status, ST_BAD_INDEX); continue; }
+        if (epi.kps1 && !epi_pass(epi, el, ti)) continue;
         const int d = hamming256(a0, a1, t[2 * (size_t)ti], t[2 * (size_t)ti + 1]);
         scan_update(bkey, second, d, (uint32_t)(c - lo) & POS_MASK);
     }
@@ -313,10 +339,11 @@ int launch_match_bruteforce(const uint8_t *q, int nq, const uint8_t *t, int nt, 
 }
 
 int launch_match_csr(const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *off, const int32_t *idx, int rule, float thr,
-                     float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, int *status, cudaStream_t st, long *launches)
+                     float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, int *status, const EpipolarDev &epi,
+                     cudaStream_t st, long *launches)
 {
     if (nq <= 0) return HYORB_OK;
-    k_match_csr<<<(nq + 7) / 8, 256, 0, st>>>((const uint4 *)q, nq, (const uint4 *)t, nt, off, idx, rule, thr, ratio, best_idx, best, second, accepted, status);
+    k_match_csr<<<(nq + 7) / 8, 256, 0, st>>>((const uint4 *)q, nq, (const uint4 *)t, nt, off, idx, rule, thr, ratio, best_idx, best, second, accepted, status, epi);
     ++*launches;
     HY_CUDA(cudaGetLastError());
     return HYORB_OK;
@@ -598,7 +625,7 @@ __global__ void k_iota(int32_t *v, int n) { const int i = blockIdx.x * blockDim.
 __global__ void __launch_bounds__(256)
 k_match_ranges(const uint4 *__restrict__ q, const uint8_t *__restrict__ mask1, int nq, const uint4 *__restrict__ t, const uint8_t *__restrict__ mask2,
                const int32_t *__restrict__ cbegin, const int32_t *__restrict__ cend, const int32_t *__restrict__ idx, int rule, float thr,
-               float ratio, int32_t *best_idx, uint16_t *best, uint16_t *sec, uint8_t *accepted)
+               float ratio, int32_t *best_idx, uint16_t *best, uint16_t *sec, uint8_t *accepted, const EpipolarDev epi)
 {
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -607,9 +634,12 @@ k_match_ranges(const uint4 *__restrict__ q, const uint8_t *__restrict__ mask1, i
     const int lo = cbegin[qi], hi = (mask1 && !mask1[qi]) ? lo : cend[qi];
     if (hi > lo) {
         const uint4 a0 = q[2 * qi], a1 = q[2 * qi + 1];
+        EpiLine el{0.f, 0.f, 0.f, 0.f};
+        if (epi.kps1) el = epi_line(epi, qi);
         for (int c = lo + lane; c < hi; c += 32) {
             const int ti = idx[c];
             if (mask2 && !mask2[ti]) continue;
+            if (epi.kps1 && !epi_pass(epi, el, ti)) continue;
             const int d = hamming256(a0, a1, t[2 * (size_t)ti], t[2 * (size_t)ti + 1]);
             scan_update(bkey, second, d, (uint32_t)(c - lo) & POS_MASK);
         }
@@ -643,7 +673,7 @@ size_t bow_sort_temp_bytes(int n)
 int launch_bow_match(const uint8_t *desc1, const uint8_t *mask1, const int32_t *node1, int n1, const uint8_t *desc2, const uint8_t *mask2,
                      const int32_t *node2, int n2, int32_t *iota, int32_t *sorted_node2, int32_t *sorted_idx2, void *temp, size_t temp_bytes,
                      int32_t *cbegin, int32_t *cend, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
-                     uint8_t *accepted, cudaStream_t st, long *launches)
+                     uint8_t *accepted, const EpipolarDev &epi, cudaStream_t st, long *launches)
 {
     if (n1 <= 0) return HYORB_OK;
     if (n2 > 0) {
@@ -653,7 +683,7 @@ int launch_bow_match(const uint8_t *desc1, const uint8_t *mask1, const int32_t *
     }
     k_bow_ranges<<<(n1 + 255) / 256, 256, 0, st>>>(node1, n1, sorted_node2, n2, cbegin, cend);
     k_match_ranges<<<(n1 + 7) / 8, 256, 0, st>>>((const uint4 *)desc1, mask1, n1, (const uint4 *)desc2, mask2, cbegin, cend, sorted_idx2, rule, thr, ratio,
-                                                 best_idx, best, second, accepted);
+                                                 best_idx, best, second, accepted, epi);
     *launches += 2;
     HY_CUDA(cudaGetLastError());
     return HYORB_OK;

@@ -263,6 +263,39 @@ class FeatureMatcher(_Handle):
                                                  thr, ratio, F.ptr(node1), F.ptr(node2), F.ptr(bi), F.ptr(b), F.ptr(s), F.ptr(acc)))
         return bi, b, s, acc, node1, node2[:n2]
 
+    def match_csr_epipolar(self, kps1, desc1, kps2, desc2, cand_off, cand_idx, F12, rule=F.RULE_BOW, thr=None, ratio=1.0, sigma_ref=1.0, size_ref=31.0):
+        """Candidate-list scan behind EpipolarConsistencyBoWCriterion (MatchCriteria.cpp:641-676): the form SearchForTriangulation takes
+        when the DBoW2 FeatureVectors already exist on the host.  Returns (best_idx, best, second, accepted)."""
+        k1 = np.ascontiguousarray(kps1, F.KP_DTYPE); k2 = np.ascontiguousarray(kps2, F.KP_DTYPE)
+        d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        off = np.ascontiguousarray(cand_off, np.int32); idx = np.ascontiguousarray(cand_idx, np.int32)
+        Fm = np.ascontiguousarray(F12, np.float32).reshape(9)
+        thr = float(self.settings.TH_LOW if thr is None else thr)
+        bi, b, s, acc = self._outs(len(d1))
+        F.check(F.lib().hyorb_match_csr_epipolar_host(self._h, F.ptr(k1), F.ptr(d1), len(d1), F.ptr(k2), F.ptr(d2), len(d2), F.ptr(off), F.ptr(idx),
+                                                      F.ptr(Fm), float(sigma_ref), float(size_ref), int(rule), thr, float(ratio), F.ptr(bi), F.ptr(b),
+                                                      F.ptr(s), F.ptr(acc)))
+        return bi, b, s, acc
+
+    def SearchForTriangulation(self, vocab, kps1, desc1, kps2, desc2, F12, mask1=None, mask2=None, levelsup=4, sigma_ref=1.0, size_ref=31.0,
+                               thr=None, ratio=1.0):
+        """FeatureMatcher::SearchForTriangulation (FeatureMatcher.cc:373-402) up to the rotation histogram: BoW-gated scan with
+        EpipolarConsistencyBoWCriterion(F12) (MatchCriteria.cpp:641-676) in front of BestMatchBoWCriterion(TH_LOW, 1.0).  mask1 / mask2 =
+        the index criteria (unmatched features; stereo features when bOnlyStereo).  Returns (best_idx, best, second, accepted, node1, node2)."""
+        k1 = np.ascontiguousarray(kps1, F.KP_DTYPE); k2 = np.ascontiguousarray(kps2, F.KP_DTYPE)
+        d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+        m1 = None if mask1 is None else np.ascontiguousarray(mask1, np.uint8)
+        m2 = None if mask2 is None else np.ascontiguousarray(mask2, np.uint8)
+        Fm = np.ascontiguousarray(F12, np.float32).reshape(9)
+        thr = float(self.settings.TH_LOW if thr is None else thr)
+        n1, n2 = len(d1), len(d2)
+        bi, b, s, acc = self._outs(n1)
+        node1 = np.full(n1, -1, np.int32); node2 = np.full(max(n2, 1), -1, np.int32)
+        F.check(F.lib().hyorb_search_for_triangulation_host(self._h, vocab._h, F.ptr(k1), F.ptr(d1), F.ptr(m1), n1, F.ptr(k2), F.ptr(d2), F.ptr(m2), n2,
+                                                            int(levelsup), F.ptr(Fm), float(sigma_ref), float(size_ref), thr, float(ratio),
+                                                            F.ptr(node1), F.ptr(node2), F.ptr(bi), F.ptr(b), F.ptr(s), F.ptr(acc)))
+        return bi, b, s, acc, node1, node2[:n2]
+
     def ComputeDistinctiveDescriptors(self, desc, lm_off):
         """MapPointDBEntry::_computeDistinctiveDescriptor_ (src/core/MapPointDB.cpp:127-171) for many landmarks at once.
         desc: [total, 32] observation descriptors, lm_off: CSR offsets.  Returns (best_idx relative to each list, best_median)."""

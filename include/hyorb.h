@@ -329,6 +329,27 @@ HYORB_API int hyorb_search_by_bow_host(hyorb_matcher *m, const hyorb_vocabulary 
                                        float ratio, int32_t *node1, int32_t *node2, int32_t *best_idx, uint16_t *best,
                                        uint16_t *second, uint8_t *accepted);
 
+/* FeatureMatcher::SearchForTriangulation (FeatureMatcher.cc:373-402) up to the rotation histogram: _SearchByBoW_ with
+ * EpipolarConsistencyBoWCriterion(F12) (MatchCriteria.cpp:641-676: the candidate must lie within 3.84 * sigma2(kp2.size) of the
+ * epipolar line x1' F12, sigma2 = FeatureExtractorSettings::determineSigma2 = sigma_ref * (size / size_ref)^2) in front of
+ * BestMatchBoWCriterion(thr = TH_LOW, ratio = 1.0).  F12: 9 floats, row-major.  mask1 / mask2 carry the index criteria
+ * (PreviouslyMatchedIndexCriterion(false), StereoIndexCriterion for bOnlyStereo).  RotationConsistencyBoW follows through
+ * hyorb_rotation_consistency_host. */
+HYORB_API int hyorb_search_for_triangulation_host(hyorb_matcher *m, const hyorb_vocabulary *v, const hyorb_keypoint *kps1,
+                                                  const uint8_t *desc1, const uint8_t *mask1, int n1, const hyorb_keypoint *kps2,
+                                                  const uint8_t *desc2, const uint8_t *mask2, int n2, int levelsup, const float *F12,
+                                                  float sigma_ref, float size_ref, float thr, float ratio, int32_t *node1,
+                                                  int32_t *node2, int32_t *best_idx, uint16_t *best, uint16_t *second,
+                                                  uint8_t *accepted);
+
+/* The same epipolar gate in front of an explicit candidate-list scan (hyorb_match_csr_host): for a hySLAM build that already
+ * holds DBoW2 FeatureVectors, the node lists go in as CSR and nothing is re-quantised. */
+HYORB_API int hyorb_match_csr_epipolar_host(hyorb_matcher *m, const hyorb_keypoint *q_kps, const uint8_t *q_desc, int nq,
+                                            const hyorb_keypoint *t_kps, const uint8_t *t_desc, int nt, const int32_t *cand_off,
+                                            const int32_t *cand_idx, const float *F12, float sigma_ref, float size_ref, int rule,
+                                            float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
+                                            uint8_t *accepted);
+
 /* Representative descriptor of a landmark: MapPointDBEntry::_computeDistinctiveDescriptor_ (src/core/MapPointDB.cpp:127-171).
  * desc: the observation descriptors of all landmarks back to back (32 bytes each); lm_off[n_landmarks + 1]: CSR offsets
  * (rows of landmark l = lm_off[l] .. lm_off[l+1]).  Per landmark: all-pairs Hamming distances, per-row order statistic

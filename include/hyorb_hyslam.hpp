@@ -227,6 +227,28 @@ public:
         return r;
     }
 
+    // FeatureMatcher::SearchForTriangulation (FeatureMatcher.cc:373-402) up to RotationConsistencyBoW: cand_off / cand_idx = for every
+    // eligible feature of pKF1 (index criteria applied by the caller) the features of pKF2 under the same vocabulary node, in
+    // FeatureVector order; F12 = the 3x3 CV_32F fundamental matrix; EpipolarConsistencyBoWCriterion + BestMatchBoWCriterion(TH_LOW, 1.0)
+    // run on the device.  accepted[i] != 0  <=>  matches_internal gets (i, best_idx[i]).
+    Result searchForTriangulation(const FeatureViews &views1, const FeatureViews &views2, const int32_t *cand_off, const int32_t *cand_idx,
+                                  const cv::Mat &F12, float TH_LOW)
+    {
+        const std::vector<cv::KeyPoint> k1 = views1.getKeys(), k2 = views2.getKeys();
+        const std::vector<uint8_t> q = cuda_marshal::packDescriptors(views1.getDescriptors()), t = cuda_marshal::packDescriptors(views2.getDescriptors());
+        float F[9];
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) F[3 * r + c] = F12.at<float>(r, c);
+        FeatureExtractorSettings orb_params = views2.getOrbParams();
+        const int nq = (int)k1.size(), nt = (int)k2.size();
+        Result r;
+        r.best_idx.assign(nq, -1); r.best.assign(nq, 65535); r.second.assign(nq, 65535); r.accepted.assign(nq, 0);
+        cuda_marshal::check(hyorb_match_csr_epipolar_host(m, cuda_marshal::asAbi(k1), q.data(), nq, cuda_marshal::asAbi(k2), t.data(), nt, cand_off, cand_idx,
+                                                          F, orb_params.sigma_ref, orb_params.size_ref, HYORB_RULE_BOW, TH_LOW, 1.0f, r.best_idx.data(),
+                                                          r.best.data(), r.second.data(), r.accepted.data()));
+        return r;
+    }
+
     // MapPointDBEntry::_computeDistinctiveDescriptor_ (MapPointDB.cpp:127-171) for many landmarks: observations[l] = descriptors of landmark l
     std::vector<int32_t> distinctiveDescriptors(const std::vector<std::vector<FeatureDescriptor>> &observations)
     {

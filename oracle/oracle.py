@@ -242,6 +242,16 @@ def hamming(a, b):
     return lib().orc_hamming(_p(a), _p(b))
 
 
+def epipolar_check(kps1, kps2, i1, i2, F12, sigma_ref=1.0, size_ref=31.0):
+    """EpipolarConsistencyBoWCriterion::CheckDistEpipolarLine (MatchCriteria.cpp:659-676) for candidate pairs (i1[c], i2[c])."""
+    k1 = np.ascontiguousarray(kps1, KP_DTYPE); k2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    i1 = np.ascontiguousarray(i1, np.int32); i2 = np.ascontiguousarray(i2, np.int32)
+    Fm = np.ascontiguousarray(F12, np.float32).reshape(9)
+    ok = np.zeros(len(i1), np.uint8)
+    lib().orc_epipolar_check(_p(k1), _p(k2), _p(i1), _p(i2), len(i1), _p(Fm), C.c_float(sigma_ref), C.c_float(size_ref), _p(ok))
+    return ok
+
+
 def preprocess(img, rgb=True, half_scale=False):
     """ImageProcessing::PreProcessImg (ImageProcessing.cpp:118-138): scale 1.0 / 0.5 then RGB|BGR[A] -> gray.  img: HxW or HxWxC uint8."""
     img = np.ascontiguousarray(img, np.uint8)

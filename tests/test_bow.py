@@ -114,3 +114,85 @@ def test_vocabulary_errors():
     with pytest.raises(hb.HyorbError) as e:
         Vocabulary(bad)
     assert e.value.rc == F.EINVAL
+
+
+def _epipolar_scene(tree, n, seed, general):
+    """Two keypoint sets whose descriptors match (perturbed copies) and whose positions lie near each other's epipolar lines
+    (noise of a few pixels, so that the 3.84 * sigma2(size) gate accepts some candidates and rejects others)."""
+    from hyslam_b200 import _ffi as F
+    rng = np.random.default_rng(seed)
+    d1 = _features(tree, n, 11 + seed)
+    d2, perm = synth.perturbed_descriptors(d1, 13 + seed, max_flips=30)
+    if general:
+        Fm = (rng.normal(size=(3, 3)) * np.array([[1e-6, 1e-5, 1e-3], [1e-5, 1e-6, 1e-2], [1e-3, 1e-2, 1.0]])).astype(np.float32)
+    else:
+        Fm = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)          # rectified pair: the line of (x1, y1) is y2 = y1
+    k1 = np.zeros(n, F.KP_DTYPE); k2 = np.zeros(n, F.KP_DTYPE)
+    k1["x"] = rng.uniform(20, 1200, n).astype(np.float32); k1["y"] = rng.uniform(20, 350, n).astype(np.float32)
+    octv = rng.integers(0, 8, n)
+    k1["size"] = (31 * 1.2 ** octv).astype(np.float32); k1["octave"] = octv
+    a = k1["x"].astype(np.float64) * Fm[0, 0] + k1["y"] * Fm[1, 0] + Fm[2, 0]
+    b = k1["x"].astype(np.float64) * Fm[0, 1] + k1["y"] * Fm[1, 1] + Fm[2, 1]
+    c = k1["x"].astype(np.float64) * Fm[0, 2] + k1["y"] * Fm[1, 2] + Fm[2, 2]
+    # set-2 feature j is a perturbed copy of set-1 feature src[j]: put it near that feature's line
+    src = np.empty(n, np.int64)
+    src[:] = -1
+    if perm is not None and len(perm) == n:
+        src = np.asarray(perm)
+    x2 = rng.uniform(20, 1200, n)
+    y2 = rng.uniform(20, 350, n)
+    ok = (src >= 0) & (np.abs(b[np.clip(src, 0, n - 1)]) > 1e-9)
+    s = np.clip(src, 0, n - 1)
+    y2[ok] = (-(a[s] * x2 + c[s]) / b[s])[ok] + rng.normal(0, 2.0, n)[ok]
+    k2["x"] = x2.astype(np.float32); k2["y"] = y2.astype(np.float32)
+    o2 = rng.integers(0, 8, n)
+    k2["size"] = (31 * 1.2 ** o2).astype(np.float32); k2["octave"] = o2
+    return k1, d1, k2, d2, Fm
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,general,with_masks", [(0, False, False), (1, True, True), (2, True, False)])
+def test_gpu_search_for_triangulation_matches_oracle_composition(seed, general, with_masks):
+    """FeatureMatcher::SearchForTriangulation (FeatureMatcher.cc:373-402): BoW gating + EpipolarConsistencyBoWCriterion +
+    BestMatchBoWCriterion(TH_LOW, 1.0), against the same chain composed from oracle pieces."""
+    import hyslam_b200 as hb
+    tree = Vocabulary.random_tree(10, 4, 78)
+    k1, d1, k2, d2, Fm = _epipolar_scene(tree, 2500, seed, general)
+    rng = np.random.default_rng(100 + seed)
+    m1 = (rng.random(len(d1)) < 0.8).astype(np.uint8) if with_masks else None
+    m2 = (rng.random(len(d2)) < 0.8).astype(np.uint8) if with_masks else None
+    v = Vocabulary(tree)
+    m = hb.FeatureMatcher()
+    bi, b, s, acc, n1, n2 = m.SearchForTriangulation(v, k1, d1, k2, d2, Fm, m1, m2, levelsup=2, thr=50.0, ratio=1.0)
+    # reference chain: node lists (index order) -> epipolar filter -> best match
+    _, on1, _ = O.bow_transform(tree, d1, 2)
+    _, on2, _ = O.bow_transform(tree, d2, 2)
+    order = np.argsort(on2, kind="stable")
+    if m2 is not None:
+        order = order[m2[order] != 0]
+    keys = on2[order]
+    pi1, pi2, rows = [], [], []
+    for i in range(len(d1)):
+        if m1 is None or m1[i]:
+            lo, hi = np.searchsorted(keys, on1[i], "left"), np.searchsorted(keys, on1[i], "right")
+            c = order[lo:hi]
+            pi1 += [i] * len(c); pi2 += c.tolist()
+        rows.append(len(pi2))
+    ok = O.epipolar_check(k1, k2, pi1, pi2, Fm).astype(bool)
+    pi2 = np.array(pi2, np.int64)
+    off, idx, prev = [0], [], 0
+    for i in range(len(d1)):
+        seg = slice(prev, rows[i])
+        idx += pi2[seg][ok[seg]].tolist()
+        off.append(len(idx)); prev = rows[i]
+    obi, ob, osd, oacc = O.match_csr(d1, d2, np.array(off, np.int32), np.array(idx if idx else [0], np.int32), mode=1, thr=50.0, ratio=1.0)
+    assert np.array_equal(n1, on1) and np.array_equal(n2, on2)
+    for g, w_, name in zip((bi, b, s, acc), (obi, ob, osd, oacc), ("best_idx", "best", "second", "accepted")):
+        assert np.array_equal(g, w_), name
+    assert ok.sum() > 500 and (~ok).sum() > 500, "the gate must both accept and reject"
+    # the same gate in front of explicit candidate lists (the unfiltered node lists as CSR)
+    uoff = np.array([0] + rows, np.int32)
+    cbi, cb, cs, cacc = m.match_csr_epipolar(k1, d1, k2, d2, uoff, pi2.astype(np.int32) if len(pi2) else np.zeros(1, np.int32), Fm, rule=1, thr=50.0, ratio=1.0)
+    for g, w_, name in zip((cbi, cb, cs, cacc), (obi, ob, osd, oacc), ("best_idx", "best", "second", "accepted")):
+        assert np.array_equal(g, w_), "csr " + name
+    assert acc.sum() > 100
