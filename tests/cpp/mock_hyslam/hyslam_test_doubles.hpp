@@ -134,6 +134,8 @@ namespace HYSLAM {
 class FeatureViews {
 public:
     FeatureViews() {}
+    FeatureViews(std::vector<cv::KeyPoint> k, std::vector<FeatureDescriptor> d, FeatureExtractorSettings p)      // mono constructor (FeatureViews.h:24)
+        : is_stereo(false), is_empty(false), N((int)k.size()), mvKeys(k), mDescriptors(d), orb_params(p) {}
     FeatureViews(std::vector<cv::KeyPoint> k, std::vector<cv::KeyPoint> kr, std::vector<FeatureDescriptor> d, std::vector<FeatureDescriptor> dr, FeatureExtractorSettings p)
         : is_stereo(true), is_empty(false), N((int)k.size()), mvKeys(k), mvKeysRight(kr), mDescriptors(d), mDescriptorsRight(dr), orb_params(p) {}
     bool empty() const { return is_empty; }

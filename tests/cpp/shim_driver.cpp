@@ -5,6 +5,7 @@
 #include <hyorb_hyslam.hpp>
 
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -84,6 +85,21 @@ int main(int argc, char **argv)
             printf("camera frame ok\n");
         }
 
+        // SearchForTriangulation-style scan: the first (up to) 300 left keypoints against ALL right keypoints as one "node", behind the
+        // epipolar gate of a rectified pair (F12 = [0 0 0; 0 0 -1; 0 1 0]: the line of (x1, y1) is y2 = y1)
+        const int n_tri = (int)std::min<size_t>(300, mvKeys.size());
+        std::vector<int32_t> tri_off(mvKeys.size() + 1, 0), tri_idx;
+        for (size_t i = 0; i < mvKeys.size(); i++) {
+            if ((int)i < n_tri) for (size_t j = 0; j < mvKeysRight.size(); j++) tri_idx.push_back((int32_t)j);
+            tri_off[i + 1] = (int32_t)tri_idx.size();
+        }
+        if (tri_idx.empty()) tri_idx.push_back(0);
+        cv::Mat F12(3, 3, CV_32F);
+        for (int i = 0; i < 9; i++) F12.ptr<float>()[i] = 0.f;
+        F12.at<float>(1, 2) = -1.f; F12.at<float>(2, 1) = 1.f;
+        FeatureViews viewsL(mvKeys, mDescriptors, orb_params), viewsR(mvKeysRight, mDescriptorsRight, orb_params);
+        CudaDescriptorScan::Result tri = scan.searchForTriangulation(viewsL, viewsR, tri_off.data(), tri_idx.data(), F12, ms.TH_LOW);
+
         FILE *f = fopen(argv[8], "wb");
         if (!f) { fprintf(stderr, "cannot write %s\n", argv[8]); return 2; }
         const int32_t hdr[4] = {(int32_t)mvKeys.size(), (int32_t)mvKeysRight.size(), extractor_left->GetLevels(), (int32_t)sizeof(cv::KeyPoint)};
@@ -99,6 +115,9 @@ int main(int argc, char **argv)
         const int32_t nd = (int32_t)distinctive.size();
         fwrite(&nd, sizeof(nd), 1, f);
         put(f, distinctive);
+        const int32_t ntri = n_tri;
+        fwrite(&ntri, sizeof(ntri), 1, f);
+        put(f, tri.best_idx); put(f, tri.best); put(f, tri.second); put(f, tri.accepted);
         fclose(f);
         // a FeatureDescriptor built by the shim behaves like the reference's (ORBDistance through the stored functor)
         if (mDescriptors.size() > 1) printf("distance(desc0, desc1) = %.0f\n", mDescriptors[0].distance(mDescriptors[1]));

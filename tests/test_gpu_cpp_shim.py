@@ -48,6 +48,8 @@ def test_process_stereo_image_through_the_cpp_shim(tmp_path, kind, h, w, seed, n
     scales = take(np.float32, nlev)
     nd = int(take(np.int32, 1)[0])
     distinctive = take(np.int32, nd)
+    ntri = int(take(np.int32, 1)[0])
+    tbi = take(np.int32, nl); tb = take(np.uint16, nl); ts = take(np.uint16, nl); tacc = take(np.uint8, nl)
     assert o == len(buf)
 
     p = O.default_params(nf)
@@ -65,4 +67,17 @@ def test_process_stereo_image_through_the_cpp_shim(tmp_path, kind, h, w, seed, n
     obs = np.concatenate([np.concatenate([odl[3 * l:3 * l + 3], odr[l:l + 1]]) for l in range(nd)]) if nd else np.zeros((0, 32), np.uint8)
     want_idx, _ = O.distinctive_descriptor(obs, np.arange(0, 4 * nd + 1, 4, dtype=np.int32))
     assert nd > 0 and np.array_equal(distinctive, want_idx)
+    # CudaDescriptorScan::searchForTriangulation: first ntri left keypoints x all right keypoints behind the rectified-pair epipolar gate
+    F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)
+    i1 = np.repeat(np.arange(ntri, dtype=np.int32), nr); i2 = np.tile(np.arange(nr, dtype=np.int32), ntri)
+    ok = O.epipolar_check(okl, okr, i1, i2, F12).astype(bool).reshape(ntri, nr)
+    off, idx = [0], []
+    for i in range(nl):
+        if i < ntri:
+            idx += np.nonzero(ok[i])[0].tolist()
+        off.append(len(idx))
+    want = O.match_csr(odl, odr, np.array(off, np.int32), np.array(idx if idx else [0], np.int32), mode=1, thr=50.0, ratio=1.0)
+    for g, wv, name in zip((tbi, tb, ts, tacc), want, ("best_idx", "best", "second", "accepted")):
+        assert np.array_equal(g, wv), "triangulation " + name
+    assert ntri > 0 and ok.any() and not ok.all()
     assert "shim ok" in r.stdout
