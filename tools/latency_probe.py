@@ -1,5 +1,6 @@
-import sys, time, numpy as np
-sys.path.insert(0,'/root/repo')
+"""Per-frame latency of the single-image entry point (the drop-in's use inside hySLAM): wall time per call and per-stage CUDA-event times."""
+import os, sys, time, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hyslam_b200 as hb
 from hyslam_b200 import synth
 for (h,w,nf) in [(480,752,1000),(376,1241,2000)]:
