@@ -383,7 +383,13 @@ HYORB_API int hyorb_extractor_create(const hyorb_extractor_params *params, int d
     if (const char *v = getenv("HYORB_LANES")) h->lanes = atoi(v);
     if (const char *v = getenv("HYORB_HOST_LANES")) h->host_lanes = atoi(v);
     if (const char *v = getenv("HYORB_SIDE_BLUR")) h->side_blur = atoi(v);
-    if (e != cudaSuccess) { set_error("CUDA init: %s", cudaGetErrorString(e)); delete h; return HYORB_ECUDA; }
+    if (e != cudaSuccess) {
+        set_error("CUDA init: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        if (!h->own_stream) h->stream = nullptr;
+        hyorb_extractor_destroy(h);          // releases the streams / events created so far
+        return HYORB_ECUDA;
+    }
     *out = h;
     return HYORB_OK;
 }
