@@ -178,6 +178,60 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// ImageProcessing::ProcessStereoImage (ImageProcessing.cpp:69-116) as ONE device call: extractor_left(imL), extractor_right(imR)
+// and Stereomatcher(...).computeStereoMatches() run back to back on the GPU (hyorb_process_stereo_batch_host with one pair), so
+// the keypoints and descriptors are not downloaded, repacked and uploaded again between extraction and association and no
+// second host thread is needed.  Returns the FeatureViews the reference builds at :98-103 (keys, right keys, descriptors, uR,
+// depth); results are identical to the three-object path above.
+class CudaStereoFrontEnd {
+public:
+    CudaStereoFrontEnd(std::shared_ptr<DescriptorDistance> dist, FeatureExtractorSettings s, int device = 0) : dist_func(dist)
+    {
+        hyorb_extractor_params p{s.nFeatures, s.fScaleFactor, s.nLevels, s.N_CELLS, s.init_threshold, s.min_threshold, 0};
+        cuda_marshal::check(hyorb_extractor_create(&p, device, nullptr, &h));
+        cap = 4 * s.nFeatures + 1024;
+        kp.resize((size_t)2 * cap); desc.resize((size_t)2 * cap * HYORB_DESC_BYTES); uR.resize(cap); depth.resize(cap);
+    }
+    ~CudaStereoFrontEnd() { hyorb_extractor_destroy(h); }
+    CudaStereoFrontEnd(const CudaStereoFrontEnd &) = delete;
+    CudaStereoFrontEnd &operator=(const CudaStereoFrontEnd &) = delete;
+
+    FeatureViews processStereoImage(const cv::Mat &imGrayLeft, const cv::Mat &imGrayRight, const Camera &cam_data, const FeatureMatcherSettings &settings,
+                                    FeatureExtractorSettings orb_params = FeatureExtractorSettings())
+    {
+        assert(imGrayLeft.type() == CV_8UC1 && imGrayRight.type() == CV_8UC1 && imGrayLeft.rows == imGrayRight.rows && imGrayLeft.cols == imGrayRight.cols);
+        const int w = imGrayLeft.cols, hgt = imGrayLeft.rows;
+        pair.resize((size_t)2 * w * hgt);            // left | right, dense rows: the ABI takes one base pointer and an image stride
+        for (int y = 0; y < hgt; y++) {
+            std::memcpy(pair.data() + (size_t)y * w, imGrayLeft.ptr<unsigned char>(y), (size_t)w);
+            std::memcpy(pair.data() + (size_t)(hgt + y) * w, imGrayRight.ptr<unsigned char>(y), (size_t)w);
+        }
+        hyorb_stereo_params sp;
+        sp.mbf = cam_data.mbf; sp.fx = cam_data.fx(); sp.n_rows = (int)cam_data.mnMaxY;
+        sp.th_high = settings.TH_HIGH; sp.th_low = settings.TH_LOW; sp.size_ref = orb_params.size_ref;
+        int32_t counts[2] = {0, 0};
+        cuda_marshal::check(hyorb_process_stereo_batch_host(h, &sp, pair.data(), 1, w, hgt, w, (size_t)w * hgt, kp.data(), desc.data(), cap, counts,
+                                                            uR.data(), depth.data()));
+        const cv::KeyPoint *kl = reinterpret_cast<const cv::KeyPoint *>(kp.data()), *kr = kl + cap;
+        std::vector<FeatureDescriptor> dl, dr;
+        cuda_marshal::appendDescriptors(desc.data(), counts[0], dist_func, dl);
+        cuda_marshal::appendDescriptors(desc.data() + (size_t)cap * HYORB_DESC_BYTES, counts[1], dist_func, dr);
+        FeatureViews views(std::vector<cv::KeyPoint>(kl, kl + counts[0]), std::vector<cv::KeyPoint>(kr, kr + counts[1]), dl, dr, orb_params);
+        views.setuRs(std::vector<float>(uR.begin(), uR.begin() + counts[0]));
+        views.setDepths(std::vector<float>(depth.begin(), depth.begin() + counts[0]));
+        return views;
+    }
+
+private:
+    hyorb_extractor *h = nullptr;
+    std::shared_ptr<DescriptorDistance> dist_func;
+    int cap = 0;
+    std::vector<hyorb_keypoint> kp;
+    std::vector<uint8_t> desc, pair;
+    std::vector<float> uR, depth;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // The Hamming scans of FeatureMatcher (SearchForTriangulation / SearchByBoW inner loops, FeatureMatcher.cc:281-345, with
 // BestMatchBoWCriterion, MatchCriteria.cpp:601-635) over explicit candidate lists; projection and map bookkeeping stay
 // with hySLAM's FeatureMatcher.

@@ -85,6 +85,23 @@ int main(int argc, char **argv)
             printf("camera frame ok\n");
         }
 
+        // the whole of ProcessStereoImage as one device call must give what the three-object path above gave
+        {
+            CudaStereoFrontEnd front(factory.getDistanceFunc(), s);
+            FeatureViews fused = front.processStereoImage(mImGray, imGrayRight, cam, factory.getFeatureMatcherSettings(), orb_params);
+            const std::vector<cv::KeyPoint> fk = fused.getKeys(), fkr = fused.getKeysR();
+            bool same = fk.size() == mvKeys.size() && fkr.size() == mvKeysRight.size();
+            same = same && (fk.empty() || memcmp(fk.data(), mvKeys.data(), fk.size() * sizeof(cv::KeyPoint)) == 0);
+            same = same && (fkr.empty() || memcmp(fkr.data(), mvKeysRight.data(), fkr.size() * sizeof(cv::KeyPoint)) == 0);
+            same = same && cuda_marshal::packDescriptors(fused.getDescriptors()) == cuda_marshal::packDescriptors(mDescriptors);
+            same = same && cuda_marshal::packDescriptors(fused.getDescriptorsR()) == cuda_marshal::packDescriptors(mDescriptorsRight);
+            const std::vector<float> fu = fused.getuRs(), fd = fused.getDepths(), u0 = LMviews.getuRs(), d0 = LMviews.getDepths();
+            same = same && fu.size() == u0.size() && fd.size() == d0.size();
+            same = same && (fu.empty() || (memcmp(fu.data(), u0.data(), fu.size() * sizeof(float)) == 0 && memcmp(fd.data(), d0.data(), fd.size() * sizeof(float)) == 0));
+            if (!same) { fprintf(stderr, "fused stereo front end differs from the three-object path\n"); return 1; }
+            printf("fused stereo ok\n");
+        }
+
         // SearchForTriangulation-style scan: the first (up to) 300 left keypoints against ALL right keypoints as one "node", behind the
         // epipolar gate of a rectified pair (F12 = [0 0 0; 0 0 -1; 0 1 0]: the line of (x1, y1) is y2 = y1)
         const int n_tri = (int)std::min<size_t>(300, mvKeys.size());
