@@ -174,7 +174,9 @@ static int ex_event(hyorb_extractor *h, cudaStream_t st, std::vector<cudaEvent_t
 struct HostIO {
     const uint8_t *images; int stride; size_t image_stride;     // source images (host)
     hyorb_keypoint *kps; uint8_t *desc; int32_t *counts; float *uR; float *depth;   // destinations (host), uR/depth optional
+    bool defer_results = false;     // small batches: the caller downloads exactly what was produced (ex_download_small) instead of capacity-sized blocks
 };
+constexpr int SMALL_BATCH = 8;      // images; below this a call is latency-bound and the extra round trip for the counts pays
 
 // the whole extraction pipeline (+ optional stereo association over consecutive image pairs) for B images
 static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_keypoint *d_kps, uint8_t *d_desc, int capacity, int32_t *d_counts,
@@ -301,7 +303,7 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
                     HY_CUDA(cudaEventRecord(e, st));
                     evs[k][6] = e;
                 }
-                if (io) {       // download this lane's results
+                if (io && !io->defer_results) {       // download this lane's results
                     HY_CUDA(cudaMemcpyAsync(io->counts + i0, d_counts + i0, sizeof(int32_t) * Bk, cudaMemcpyDeviceToHost, st));
                     HY_CUDA(cudaMemcpyAsync(io->kps + (size_t)i0 * capacity, d_kps + (size_t)i0 * capacity, sizeof(hyorb_keypoint) * (size_t)capacity * Bk,
                                             cudaMemcpyDeviceToHost, st));
@@ -325,6 +327,29 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
     }
     if (h->profile) { for (int k = 0; k < nl; k++) h->ev_pending.push_back(evs[k]); h->stage_calls++; }
     h->last_B = B; h->last_l0 = l0;
+    return HYORB_OK;
+}
+
+static int ex_sync(hyorb_extractor *h);
+// results of a small host batch: counts first, then only the keypoints / descriptors / stereo values each image produced
+static int ex_download_small(hyorb_extractor *h, const HostIO &io, int B, int capacity, const hyorb_keypoint *d_kps, const uint8_t *d_desc,
+                             const int32_t *d_counts, const float *d_uR, const float *d_depth)
+{
+    HY_CUDA(cudaMemcpyAsync(io.counts, d_counts, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, h->stream));
+    HY_TRY(ex_sync(h));
+    for (int i = 0; i < B; i++) {
+        const int n = io.counts[i] < capacity ? io.counts[i] : capacity;
+        if (n <= 0) continue;
+        HY_CUDA(cudaMemcpyAsync(io.kps + (size_t)i * capacity, d_kps + (size_t)i * capacity, sizeof(hyorb_keypoint) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        HY_CUDA(cudaMemcpyAsync(io.desc + (size_t)i * capacity * HYORB_DESC_BYTES, d_desc + (size_t)i * capacity * HYORB_DESC_BYTES, (size_t)HYORB_DESC_BYTES * n,
+                                cudaMemcpyDeviceToHost, h->stream));
+        if (d_uR && io.uR && io.depth && (i & 1) == 0) {
+            const int p = i / 2;
+            HY_CUDA(cudaMemcpyAsync(io.uR + (size_t)p * capacity, d_uR + (size_t)p * capacity, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+            HY_CUDA(cudaMemcpyAsync(io.depth + (size_t)p * capacity, d_depth + (size_t)p * capacity, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    HY_CUDA(cudaStreamSynchronize(h->stream));
     return HYORB_OK;
 }
 
@@ -485,8 +510,11 @@ HYORB_API int hyorb_extract_batch_host(hyorb_extractor *h, const uint8_t *images
     HY_TRY(h->d_desc.ensure((size_t)HYORB_DESC_BYTES * capacity * n_images));
     HY_TRY(h->d_counts.ensure(sizeof(int32_t) * n_images));
     HostIO io{images, stride, image_stride, kps, desc, counts, nullptr, nullptr};
+    io.defer_results = n_images <= SMALL_BATCH;
     HY_TRY(ex_run(h, l0, n_images, width, height, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), capacity, h->d_counts.as<int32_t>(),
                   nullptr, nullptr, nullptr, &io));
+    if (io.defer_results)
+        return ex_download_small(h, io, n_images, capacity, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), h->d_counts.as<int32_t>(), nullptr, nullptr);
     return ex_sync(h);
 }
 
@@ -603,8 +631,12 @@ HYORB_API int hyorb_process_stereo_batch_host(hyorb_extractor *h, const hyorb_st
     HY_TRY(h->d_uR.ensure(sizeof(float) * (size_t)capacity * n_pairs));
     HY_TRY(h->d_depth.ensure(sizeof(float) * (size_t)capacity * n_pairs));
     HostIO io{images, stride, image_stride, kps, desc, counts, uR, depth};
+    io.defer_results = n_images <= SMALL_BATCH;
     HY_TRY(ex_run(h, l0, n_images, width, height, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), capacity, h->d_counts.as<int32_t>(), sp,
                   h->d_uR.as<float>(), h->d_depth.as<float>(), &io));
+    if (io.defer_results)
+        return ex_download_small(h, io, n_images, capacity, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), h->d_counts.as<int32_t>(),
+                                 h->d_uR.as<float>(), h->d_depth.as<float>());
     return ex_sync(h);
 }
 
