@@ -525,26 +525,12 @@ HYORB_API int hyorb_extract_host(hyorb_extractor *h, const uint8_t *gray, int wi
     *n = 0;
     if (!gray || width <= 0 || height <= 0) return HYORB_OK;     // ORBExtractor.cpp:499-500: empty image -> silent return
     if (!kps || !desc || capacity < 1 || stride < width) { set_error("bad argument"); return HYORB_EINVAL; }
-    HY_CUDA(cudaSetDevice(h->device));
-    HY_TRY(ex_ensure_plan(h, width, height));
-    const PlanDev &P = h->plan.dev;
-    const int pitch = P.lv[0].pitch;
-    HY_TRY(h->d_in.ensure((size_t)pitch * height + 512));
-    HY_TRY(h->d_kps.ensure(sizeof(hyorb_keypoint) * (size_t)capacity));
-    HY_TRY(h->d_desc.ensure((size_t)HYORB_DESC_BYTES * capacity));
-    HY_TRY(h->d_counts.ensure(sizeof(int32_t)));
-    HY_CUDA(cudaMemcpy2DAsync(h->d_in.p, pitch, gray, stride, width, height, cudaMemcpyHostToDevice, h->stream));
-    Level0 l0{h->d_in.as<uint8_t>(), pitch, (unsigned long long)pitch * height};
-    HY_TRY(ex_run(h, l0, 1, width, height, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), capacity, h->d_counts.as<int32_t>()));
+    // a batch of one: one flat upload of the rows (repacked on the device when the pitch is not TMA-addressable) and a download of
+    // exactly what was produced.  A narrow view of a much wider image is uploaded row by row instead (scattered layout).
+    const size_t istride = (size_t)stride * height + ((size_t)stride > 2 * (size_t)width ? 8192 : 0);
     int32_t cnt = 0;
-    HY_CUDA(cudaMemcpyAsync(&cnt, h->d_counts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    HY_TRY(ex_sync(h));
-    if (cnt > 0) {
-        HY_CUDA(cudaMemcpyAsync(kps, h->d_kps.p, sizeof(hyorb_keypoint) * (size_t)cnt, cudaMemcpyDeviceToHost, h->stream));
-        HY_CUDA(cudaMemcpyAsync(desc, h->d_desc.p, (size_t)HYORB_DESC_BYTES * cnt, cudaMemcpyDeviceToHost, h->stream));
-        HY_CUDA(cudaStreamSynchronize(h->stream));
-    }
-    *n = cnt;
+    HY_TRY(hyorb_extract_batch_host(h, gray, 1, width, height, stride, istride, kps, desc, capacity, &cnt));
+    *n = cnt < capacity ? cnt : capacity;
     return HYORB_OK;
 }
 

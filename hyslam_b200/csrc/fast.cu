@@ -90,6 +90,7 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     __shared__ int s_n, s_ne, s_base;
     uint32_t *s_emit = s_planes;            // the planes are dead once the corner test is done
 
+    grid_dependency_wait();      // launch_dependent (common.cuh): follows the last pyramid level
     const int tid = threadIdx.x;
     // pixel box of tile T -> buffer `buf`; issued by one thread, completion lands on s_bar[buf]
     auto issue = [&](int T, int buf) {
@@ -290,7 +291,7 @@ int launch_fast(const PlanDev &hp, const PlanDev *dp, const CUtensorMap &tm0, co
     const long long nTiles = (long long)hp.tilesPerImage * B;
     if (nTiles > 0x7fffffffLL) { set_error("too many FAST tiles in one batch"); return HYORB_EUNSUPPORTED; }
     const int grid = (int)std::min<long long>(nTiles, (long long)sms * per);
-    k_fast<<<grid, FT_THREADS, 0, st>>>(dp, tm0, tmaps, img0, (int)nTiles, cand, candCount, status);
+    HY_CUDA(launch_dependent(k_fast, dim3(grid), dim3(FT_THREADS), 0, st, dp, tm0, tmaps, img0, (int)nTiles, cand, candCount, status));
     ++*launches;
     HY_CUDA(cudaGetLastError());
     return HYORB_OK;

@@ -60,6 +60,7 @@ k_resize(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride
 {
     // flat strip index -> (image, strip row, strip column), columns fastest: neighbouring threads read neighbouring words, and no
     // thread of the grid is idle whatever the level's shape (the narrow upper levels wasted a third of a 2-D grid's threads)
+    grid_dependency_wait();      // launch_dependent (common.cuh): nothing of the source level is read before the previous launch is complete
     const int item = blockIdx.x * RS_THREADS + threadIdx.x;
     if (item >= total) return;
     const int per = nx * ny;
@@ -131,8 +132,14 @@ int launch_pyramid(const PlanDev &hp, const PlanDev *, Level0 l0, uint8_t *pyr, 
         const int nx = (D.w + 3) / 4, ny = (D.h + RS_ROWS - 1) / RS_ROWS;
         const long long total = (long long)nx * ny * B;
         if (total > 0x7fffffffLL) { set_error("pyramid level too large for one launch"); return HYORB_EUNSUPPORTED; }
-        k_resize<<<(unsigned)((total + RS_THREADS - 1) / RS_THREADS), RS_THREADS, 0, st>>>(src, spitch, sstride, S.w, S.h, pyr + D.off, D.pitch, hp.pyrStride, D.w, D.h,
-                                                                                      tabs + D.rsX, tabs + D.rsY, D.area2x, nx, ny, (int)total);
+        // levels 2.. depend only on the launch before them (level 1 follows the caller's copies)
+        const dim3 grd((unsigned)((total + RS_THREADS - 1) / RS_THREADS));
+        if (l > 1)
+            HY_CUDA(launch_dependent(k_resize, grd, dim3(RS_THREADS), 0, st, src, spitch, sstride, S.w, S.h, pyr + D.off, D.pitch, hp.pyrStride, D.w, D.h,
+                                     tabs + D.rsX, tabs + D.rsY, D.area2x, nx, ny, (int)total));
+        else
+            k_resize<<<grd, RS_THREADS, 0, st>>>(src, spitch, sstride, S.w, S.h, pyr + D.off, D.pitch, hp.pyrStride, D.w, D.h, tabs + D.rsX, tabs + D.rsY, D.area2x,
+                                                 nx, ny, (int)total);
         ++*launches;
     }
     HY_CUDA(cudaGetLastError());

@@ -120,6 +120,7 @@ k_quadtree(const PlanDev *__restrict__ plan, const uint32_t *__restrict__ cand_a
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ QtShared S;
 
+    grid_dependency_wait();      // launch_dependent (common.cuh): follows k_fast
     const int l = blockIdx.x, b = blockIdx.y;
     const LevelDev &L = plan->lv[l];
     const int maxN = L.qtMaxN;
@@ -352,8 +353,8 @@ int launch_quadtree(const PlanDev &hp, const PlanDev *dp, const uint32_t *cand, 
     dim3 grd(hp.nlevels, B);
     // a handful of images cannot fill the machine anyway: give each (image, level) CTA twice the threads (measured on one C2
     // frame: 0.166 -> 0.112 ms); large batches keep 512 threads per CTA for occupancy
-    if (B * hp.nlevels <= 148) k_quadtree<QT_LAT><<<grd, QT_LAT, smem, st>>>(dp, cand, candCount, lut, qcode, qnode, qleaf, sel, selCount, status);
-    else k_quadtree<QT_THREADS><<<grd, QT_THREADS, smem, st>>>(dp, cand, candCount, lut, qcode, qnode, qleaf, sel, selCount, status);
+    if (B * hp.nlevels <= 148) HY_CUDA(launch_dependent(k_quadtree<QT_LAT>, grd, dim3(QT_LAT), smem, st, dp, cand, candCount, lut, qcode, qnode, qleaf, sel, selCount, status));
+    else HY_CUDA(launch_dependent(k_quadtree<QT_THREADS>, grd, dim3(QT_THREADS), smem, st, dp, cand, candCount, lut, qcode, qnode, qleaf, sel, selCount, status));
     ++*launches;
     HY_CUDA(cudaGetLastError());
     return HYORB_OK;

@@ -40,6 +40,7 @@ __device__ __forceinline__ bool right_band(const hyorb_keypoint &k, float size_r
 __global__ void __launch_bounds__(ST_THREADS)
 k_stereo_table(StereoArgs A)
 {
+    grid_dependency_wait();      // launch_dependent (common.cuh)
     __shared__ int s_off[ST_MAX_ROWS + 1];
     __shared__ int s_fill[ST_MAX_ROWS];
     __shared__ int s_part[ST_THREADS];
@@ -90,6 +91,7 @@ k_stereo_table(StereoArgs A)
 __global__ void __launch_bounds__(ST_THREADS)
 k_stereo_search(StereoArgs A)
 {
+    grid_dependency_wait();      // launch_dependent (common.cuh)
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.y;
     const int iL = blockIdx.x * (ST_THREADS / 32) + (threadIdx.x >> 5);
@@ -152,6 +154,7 @@ k_stereo_search(StereoArgs A)
 __global__ void __launch_bounds__(ST_THREADS)
 k_stereo_cut(StereoArgs A)
 {
+    grid_dependency_wait();      // launch_dependent (common.cuh)
     __shared__ float s_th;
     const int tid = threadIdx.x, p = blockIdx.x;
     const int nl = min(A.counts[2 * p], A.capacity);
@@ -199,10 +202,10 @@ int launch_stereo(const hyorb_stereo_params &sp, int n_pairs, const hyorb_keypoi
     A.rowoff = scratch + (size_t)A.tabCap * n_pairs;
     A.hist = A.rowoff + (size_t)(ST_MAX_ROWS + 1) * n_pairs;
     A.uR = uR; A.depth = depth; A.best_r = best_r; A.best_d = best_d; A.status = status;
-    k_stereo_table<<<n_pairs, ST_THREADS, 0, st>>>(A);
+    HY_CUDA(launch_dependent(k_stereo_table, dim3(n_pairs), dim3(ST_THREADS), 0, st, A));
     dim3 grd((capacity + ST_THREADS / 32 - 1) / (ST_THREADS / 32), n_pairs);
-    k_stereo_search<<<grd, ST_THREADS, 0, st>>>(A);
-    k_stereo_cut<<<n_pairs, ST_THREADS, 0, st>>>(A);
+    HY_CUDA(launch_dependent(k_stereo_search, grd, dim3(ST_THREADS), 0, st, A));
+    HY_CUDA(launch_dependent(k_stereo_cut, dim3(n_pairs), dim3(ST_THREADS), 0, st, A));
     *launches += 3;
     HY_CUDA(cudaGetLastError());
     return HYORB_OK;
