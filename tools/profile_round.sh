@@ -1,8 +1,8 @@
 #!/bin/bash
 # Everything profiles/ needs from one GPU box, in one gpurun call:
-#   gpurun --timeout 1500 -- 'bash tools/profile_round.sh r1d'      then, back here:   bash tools/refresh_profiles.sh r1d
+#   gpurun --timeout 1500 -- 'bash tools/profile_round.sh r1e'      then, back here:   bash tools/refresh_profiles.sh r1e
 # (numbers come from the plain runs; the ncu passes only produce the launch list and the per-kernel captures)
-tag=${1:-r1d}
+tag=${1:-r1e}
 mkdir -p gpurun_out
 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2>> gpurun_out/${tag}_bench.err

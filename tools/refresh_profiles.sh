@@ -1,8 +1,8 @@
 #!/bin/bash
 # Turns the artefacts of one profile run (gpurun_out/<tag>_*) into the tracked summaries under profiles/.
-#   bash tools/refresh_profiles.sh r1d
+#   bash tools/refresh_profiles.sh r1e
 set -e
-tag=${1:-r1d}
+tag=${1:-r1e}
 cp gpurun_out/${tag}_bench.json profiles/${tag}_bench.json
 cp gpurun_out/${tag}_bench_reference.json profiles/
 cp gpurun_out/${tag}_launches.csv profiles/
