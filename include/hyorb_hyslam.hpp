@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -53,6 +54,34 @@ inline void appendDescriptors(const uint8_t *rows, int n, const std::shared_ptr<
 }
 inline const hyorb_keypoint *asAbi(const std::vector<cv::KeyPoint> &k) { return reinterpret_cast<const hyorb_keypoint *>(k.data()); }
 inline void check(int rc) { if (rc != HYORB_OK) throw std::runtime_error(std::string("libhyorb: ") + hyorb_last_error()); }
+
+// hySLAM constructs a Stereomatcher (and criteria objects) per frame; a matcher handle owns a stream and device buffers whose
+// creation costs several hundred microseconds, so the per-frame objects of this header borrow handles from a process-wide
+// free list instead of creating them (handles are returned on destruction and live until the process exits).
+class MatcherPool {
+public:
+    static hyorb_matcher *acquire(int device)
+    {
+        {
+            std::lock_guard<std::mutex> lock(mutex());
+            auto &f = free_list();
+            for (size_t i = 0; i < f.size(); i++)
+                if (f[i].first == device) { hyorb_matcher *m = f[i].second; f.erase(f.begin() + (long)i); return m; }
+        }
+        hyorb_matcher *m = nullptr;
+        check(hyorb_matcher_create(device, nullptr, &m));
+        return m;
+    }
+    static void release(int device, hyorb_matcher *m)
+    {
+        if (!m) return;
+        std::lock_guard<std::mutex> lock(mutex());
+        free_list().push_back(std::make_pair(device, m));
+    }
+private:
+    static std::mutex &mutex() { static std::mutex mu; return mu; }
+    static std::vector<std::pair<int, hyorb_matcher *>> &free_list() { static std::vector<std::pair<int, hyorb_matcher *>> f; return f; }
+};
 }  // namespace cuda_marshal
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -151,9 +180,10 @@ public:
         const FeatureExtractorSettings orb_params = views.getOrbParams();       // default-constructed at the call site: only size_ref matters
         sp.mbf = cam_data.mbf; sp.fx = cam_data.fx(); sp.n_rows = (int)cam_data.mnMaxY;
         sp.th_high = settings.TH_HIGH; sp.th_low = settings.TH_LOW; sp.size_ref = orb_params.size_ref;
-        cuda_marshal::check(hyorb_matcher_create(device, nullptr, &m));
+        dev = device;
+        m = cuda_marshal::MatcherPool::acquire(device);
     }
-    ~CudaStereomatcher() { hyorb_matcher_destroy(m); }
+    ~CudaStereomatcher() { cuda_marshal::MatcherPool::release(dev, m); }
     CudaStereomatcher(const CudaStereomatcher &) = delete;
     CudaStereomatcher &operator=(const CudaStereomatcher &) = delete;
 
@@ -174,7 +204,7 @@ private:
     hyorb_stereo_params sp;
     hyorb_matcher *m = nullptr;
     std::vector<float> mvuRight, mvDepth;
-    int N;
+    int N, dev = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -237,8 +267,8 @@ private:
 // with hySLAM's FeatureMatcher.
 class CudaDescriptorScan {
 public:
-    explicit CudaDescriptorScan(int device = 0) { cuda_marshal::check(hyorb_matcher_create(device, nullptr, &m)); }
-    ~CudaDescriptorScan() { hyorb_matcher_destroy(m); }
+    explicit CudaDescriptorScan(int device = 0) : dev(device) { m = cuda_marshal::MatcherPool::acquire(device); }
+    ~CudaDescriptorScan() { cuda_marshal::MatcherPool::release(dev, m); }
     CudaDescriptorScan(const CudaDescriptorScan &) = delete;
     CudaDescriptorScan &operator=(const CudaDescriptorScan &) = delete;
 
@@ -319,6 +349,7 @@ public:
 
 private:
     hyorb_matcher *m = nullptr;
+    int dev = 0;
 };
 
 }  // namespace HYSLAM

@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -100,6 +101,25 @@ int main(int argc, char **argv)
             same = same && (fu.empty() || (memcmp(fu.data(), u0.data(), fu.size() * sizeof(float)) == 0 && memcmp(fd.data(), d0.data(), fd.size() * sizeof(float)) == 0));
             if (!same) { fprintf(stderr, "fused stereo front end differs from the three-object path\n"); return 1; }
             printf("fused stereo ok\n");
+            // per-pair latency of both forms as hySLAM would drive them (informational)
+            const int reps = 20;
+            auto t0 = std::chrono::steady_clock::now();
+            for (int r = 0; r < reps; r++) {
+                std::vector<cv::KeyPoint> k1, k2;
+                std::vector<FeatureDescriptor> d1, d2;
+                std::thread th(extractFeatures, extractor_left.get(), std::ref(mImGray), std::ref(k1), std::ref(d1));
+                (*extractor_right)(imGrayRight, cv::Mat(), k2, d2);
+                th.join();
+                FeatureViews v(k1, k2, d1, d2, orb_params);
+                CudaStereomatcher sm(v, cam, factory.getFeatureMatcherSettings());
+                sm.computeStereoMatches();
+                sm.getData(v);
+            }
+            auto t1 = std::chrono::steady_clock::now();
+            for (int r = 0; r < reps; r++) (void)front.processStereoImage(mImGray, imGrayRight, cam, factory.getFeatureMatcherSettings(), orb_params);
+            auto t2 = std::chrono::steady_clock::now();
+            printf("latency per pair: three objects %.3f ms, fused %.3f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count() / reps,
+                   std::chrono::duration<double, std::milli>(t2 - t1).count() / reps);
         }
 
         // SearchForTriangulation-style scan: the first (up to) 300 left keypoints against ALL right keypoints as one "node", behind the

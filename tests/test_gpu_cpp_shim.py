@@ -30,6 +30,7 @@ def test_process_stereo_image_through_the_cpp_shim(tmp_path, kind, h, w, seed, n
     mbf, fx = 386.1448, 718.856
     r = subprocess.run([_driver(), lp, rp, str(w), str(h), str(nf), repr(mbf), repr(fx), op], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+    print(r.stdout)
     assert "fused stereo ok" in r.stdout          # CudaStereoFrontEnd (one device call) == extractor x 2 + CudaStereomatcher
     assert "camera frame ok" in r.stdout          # PreProcessImg + extraction through the shim == the gray path
     buf = open(op, "rb").read()
