@@ -196,3 +196,33 @@ def test_gpu_search_for_triangulation_matches_oracle_composition(seed, general, 
     for g, w_, name in zip((cbi, cb, cs, cacc), (obi, ob, osd, oacc), ("best_idx", "best", "second", "accepted")):
         assert np.array_equal(g, w_), "csr " + name
     assert acc.sum() > 100
+
+
+@pytest.mark.gpu
+def test_epipolar_gate_edge_cases():
+    """den == 0 (a degenerate F12 maps every keypoint to the zero line) rejects every candidate (MatchCriteria.cpp:670-671); empty
+    candidate lists and an empty query set are handled; the gate needs candidate lists."""
+    import hyslam_b200 as hb
+    from hyslam_b200 import _ffi as F
+    tree = Vocabulary.random_tree(6, 3, 5)
+    k1, d1, k2, d2, Fm = _epipolar_scene(tree, 300, 7, False)
+    m = hb.FeatureMatcher()
+    n = len(d1)
+    off = np.arange(0, n + 1, dtype=np.int32) * 4
+    idx = np.random.default_rng(0).integers(0, n, 4 * n).astype(np.int32)
+    bi, b, s, acc = m.match_csr_epipolar(k1, d1, k2, d2, off, idx, np.zeros((3, 3), np.float32), thr=256.0)
+    assert (bi == -1).all() and not acc.any()
+    ok = O.epipolar_check(k1, k2, np.repeat(np.arange(n, dtype=np.int32), 4), idx, np.zeros(9, np.float32))
+    assert not ok.any()
+    # empty lists for every query
+    bi, b, s, acc = m.match_csr_epipolar(k1, d1, k2, d2, np.zeros(n + 1, np.int32), np.zeros(1, np.int32), Fm, thr=256.0)
+    assert (bi == -1).all() and not acc.any()
+    # no queries at all
+    bi, b, s, acc = m.match_csr_epipolar(k1[:0], d1[:0], k2, d2, np.zeros(1, np.int32), np.zeros(1, np.int32), Fm)
+    assert len(bi) == 0
+    v = Vocabulary(tree)
+    out = m.SearchForTriangulation(v, k1[:0], d1[:0], k2, d2, Fm)
+    assert len(out[0]) == 0
+    with pytest.raises(hb.HyorbError):
+        F.check(F.lib().hyorb_match_csr_epipolar_host(m._h, F.ptr(k1), F.ptr(d1), n, F.ptr(k2), F.ptr(d2), n, None, None, F.ptr(Fm.reshape(9)),
+                                                      1.0, 31.0, 1, 50.0, 1.0, F.ptr(bi), F.ptr(b), F.ptr(s), F.ptr(acc)))
