@@ -97,7 +97,9 @@ public:
         cap = 4 * s.nFeatures + 1024;          // the quadtree may return more than nFeatures (ORBExtractor.cpp:309-312)
         kp.resize(cap); desc.resize((size_t)cap * HYORB_DESC_BYTES);
     }
-    ~CudaORBExtractor() override { hyorb_extractor_destroy(h); }
+    // FeatureExtractor (FeatureExtractor.h:25-37) declares no virtual destructor: own these objects through the
+    // std::shared_ptr the factory returns (make_shared remembers the concrete type), as hySLAM does everywhere.
+    ~CudaORBExtractor() { hyorb_extractor_destroy(h); }
     CudaORBExtractor(const CudaORBExtractor &) = delete;
     CudaORBExtractor &operator=(const CudaORBExtractor &) = delete;
 
@@ -156,10 +158,11 @@ class CudaORBFactory : public ORBFactory {
 public:
     CudaORBFactory() : ORBFactory() {}
     explicit CudaORBFactory(std::string settings_path, int device_ = 0) : ORBFactory(settings_path), device(device_) {}
-    std::shared_ptr<FeatureExtractor> getExtractor(std::string /*camera type: the reference reads the same YAML block for all*/) override
-    {
-        return getExtractor(getFeatureExtractorSettings());
-    }
+    // getExtractor(std::string camera_type) is NOT overridden: ORBFactory's own version (ORBFactory.cpp:32-35) re-reads the
+    // ORB.<camera_type>.Extractor / Matcher block of the settings file (SLAM and Imaging cameras differ: 1000 features / 1.2
+    // vs 3000 / 1.4 in config/slam_feature_config.yaml), updates the settings ImageProcessing.cpp:34-36 reads back through
+    // getFeatureExtractorSettings(), and then dispatches virtually to the overload below.
+    using ORBFactory::getExtractor;
     std::shared_ptr<FeatureExtractor> getExtractor(FeatureExtractorSettings s) override
     {
         return std::make_shared<CudaORBExtractor>(getDistanceFunc(), s, device);

@@ -5,15 +5,16 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as the
  * checker and CPU baseline.  Nothing under hyslam_b200/ may call into this file.
  *
- * PARITY STATUS: *unpinned by the reference* -- the reference has no tests, golden vectors or
- * fixtures on this path and cannot be compiled here (needs OpenCV 3.x
- * C++ dev files, Eigen, Pangolin, DBoW2, g2o).  The third-party arithmetic it calls lives in
- * OpenCV (pinned by the reference as `find_package(OpenCV 3.1.0 ... opencv_3_4)`, CMakeLists.txt:32-35);
- * the restatements of cv::resize / cv::GaussianBlur / cv::FAST / cv::fastAtan2 below follow
- * OpenCV's published algorithms and are pinned bit-for-bit against cv2 4.13 (the closest
- * available build of the same library) in tests/test_oracle_vs_cv2.py, and against the committed
- * fixtures in tests/golden/ that were generated by an independent cv2+numpy pipeline
- * (tests/golden/make_golden.py).
+ * PARITY STATUS: *pinned to the reference's own code* for the extractor, Hamming distance and stereo
+ * rows: oracle/_ref compiles hySLAM's ORBExtractor / ORBFinder / DescriptorDistance / FeatureDescriptor /
+ * Stereomatcher / FeatureViews translation units UNMODIFIED (oracle/Makefile `ref`) against oracle/cvshim,
+ * and tests/test_oracle_vs_ref.py requires this file to reproduce their output bit for bit (C1 / C2 frames,
+ * other settings, strided views; tests/golden/ref_*.npz keep those results for boxes without the reference
+ * tree).  The reference has no tests or golden vectors of its own on this path.  The
+ * third-party arithmetic underneath (OpenCV: resize / GaussianBlur / FAST / fastAtan2 / gemm) is pinned
+ * bit-for-bit against cv2 4.13 in tests/test_oracle_vs_cv2.py and tests/test_cvshim_vs_cv2.py.
+ * Still unpinned (no reference code executed): the matcher rows (criteria, window query, projection) --
+ * see DESIGN.md section 2 -- and the BoW rows (DBoW2 is absent).
  *
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  * Compile with -ffp-contract=off: the reference is an x86-64 baseline build (no FMA).

@@ -1,0 +1,164 @@
+"""ctypes wrapper over oracle/_ref/libhyslam_ref.so -- the REFERENCE's own translation units (test infrastructure).
+
+The library holds hySLAM's ORBExtractor / ORBFinder / ORBDistance / FeatureDescriptor / Stereomatcher / FeatureViews
+compiled unmodified from /root/reference against oracle/cvshim (see oracle/Makefile, oracle/ref_glue.cpp).  It is the
+parity pin: tests compare the C oracle and the CUDA path against what the reference's code itself returns.
+Only tests/ and bench.py's CPU legs may import this module.  /root/reference exists only in the build container; on the
+GPU box the prebuilt library travels with the snapshot (oracle/_ref is git-ignored, not gpurun-ignored).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .oracle import KP_DTYPE, Params, StereoParams, default_params, level_sizes
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libhyslam_ref.so")
+REFERENCE_ROOT = os.environ.get("HYSLAM_REFERENCE", "/root/reference")
+
+
+def available():
+    return os.path.exists(_SO) or os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "features"))
+
+
+def build(force=False):
+    """Compile oracle/_ref from the reference tree when it is present (idempotent); otherwise use the prebuilt file."""
+    have_src = os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "features"))
+    if not have_src:
+        if os.path.exists(_SO):
+            return _SO
+        raise RuntimeError("oracle/_ref is not built and the reference tree is absent")
+    deps = [os.path.join(_HERE, f) for f in ("ref_glue.cpp", "Makefile", "cvshim/cvshim.cpp", "cvshim/opencv2/core/core.hpp")]
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in deps):
+        return _SO
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    subprocess.run(["make", "-C", _HERE, "ref", "CXX=g++", f"REF={REFERENCE_ROOT}"], check=True, capture_output=True, env=env)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.ref_hamming.restype = C.c_float
+        _lib.cvshim_fast_atan2.restype = C.c_float
+        _lib.cvshim_norm.restype = C.c_double
+        _lib.ref_process_stereo_pairs.restype = C.c_long
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def extract(img, p=None, cap=None, arena=True, levels=False):
+    """HYSLAM::ORBExtractor::operator() on one 8-bit frame.  arena=True: monotonic allocator (canonical quadtree tie
+    policy); arena=False: glibc malloc, like a stock hySLAM build."""
+    p = p or default_params()
+    img = np.ascontiguousarray(img, np.uint8)
+    H, W = img.shape
+    cap = cap or max(4 * p.nfeatures + 1024, 4096)
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = C.c_int32()
+    lv = None
+    ptrs = None
+    if levels:
+        sizes = level_sizes(p, W, H)
+        lv = [np.zeros((h, w), np.uint8) for (w, h) in sizes]
+        ptrs = (C.c_void_p * p.nlevels)(*[a.ctypes.data for a in lv])
+    rc = lib().ref_extract(C.byref(p), _p(img), W, H, img.strides[0], int(bool(arena)), _p(kps), _p(desc), cap, C.byref(n), ptrs)
+    if rc != 0:
+        raise RuntimeError(f"ref_extract rc={rc} n={n.value}")
+    k, d = kps[:n.value].copy(), desc[:n.value].copy()
+    return (k, d, lv) if levels else (k, d)
+
+
+def scale_tables(p):
+    n = p.nlevels
+    s, i, s2, i2 = (np.zeros(n, np.float32) for _ in range(4))
+    lib().ref_scale_tables(C.byref(p), _p(s), _p(i), _p(s2), _p(i2))
+    return s, i, s2, i2
+
+
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return float(lib().ref_hamming(_p(a), _p(b)))
+
+
+def stereo_match(sp, kl, dl, kr, dr):
+    kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    uR = np.empty(len(kl), np.float32); depth = np.empty(len(kl), np.float32)
+    rc = lib().ref_stereo_match(C.byref(sp), _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(uR), _p(depth))
+    if rc < 0:
+        raise RuntimeError(f"ref_stereo_match rc={rc}")
+    return uR, depth
+
+
+def process_stereo_pairs(p, sp, left, right, threads_per_pair=2):
+    """n pairs through extract L + R + Stereomatcher, in the reference's threading shape.  Returns (keypoints, matches)."""
+    left = np.ascontiguousarray(left, np.uint8); right = np.ascontiguousarray(right, np.uint8)
+    n, H, W = left.shape
+    m = C.c_long()
+    tot = lib().ref_process_stereo_pairs(C.byref(p), C.byref(sp) if sp is not None else None, _p(left), _p(right), n, W, H,
+                                         int(threads_per_pair), C.byref(m))
+    return int(tot), int(m.value)
+
+
+# ---- cvshim primitives (pinned against cv2 in tests/test_cvshim_vs_cv2.py) ----
+def shim_fast(img, threshold=20, nms=True):
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size // 2 + 16
+    x, y, r = (np.empty(cap, np.float32) for _ in range(3))
+    n = lib().cvshim_fast(_p(img), img.shape[1], img.shape[0], img.strides[0], threshold, int(nms), _p(x), _p(y), _p(r), cap)
+    assert n >= 0, n
+    return x[:n].copy(), y[:n].copy(), r[:n].copy()
+
+
+def shim_resize(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().cvshim_resize(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def shim_blur(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().cvshim_blur(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def shim_border(src, b, border_type=4):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((src.shape[0] + 2 * b, src.shape[1] + 2 * b), np.uint8)
+    lib().cvshim_border(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0], b, border_type)
+    return dst
+
+
+def shim_fast_atan2(y, x):
+    return float(lib().cvshim_fast_atan2(C.c_float(y), C.c_float(x)))
+
+
+def shim_gemm(A, B, Cm=None, ta=False):
+    A = np.ascontiguousarray(A, np.float32); B = np.ascontiguousarray(B, np.float32)
+    m = A.shape[1] if ta else A.shape[0]
+    k = A.shape[0] if ta else A.shape[1]
+    n = B.shape[1]
+    D = np.empty((m, n), np.float32)
+    Cc = None if Cm is None else np.ascontiguousarray(Cm, np.float32)
+    lib().cvshim_gemm(_p(A), m, k, int(ta), _p(B), n, _p(Cc), _p(D))
+    return D
+
+
+def shim_norm(a):
+    a = np.ascontiguousarray(a, np.float32).reshape(-1)
+    return float(lib().cvshim_norm(_p(a), len(a)))

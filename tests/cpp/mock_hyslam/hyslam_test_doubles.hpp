@@ -55,9 +55,8 @@ public:
 // ---- stands in for FeatureExtractor.h
 // TEST DOUBLE mirroring hySLAM src/features/FeatureExtractor.h:25-37.
 namespace HYSLAM {
-class FeatureExtractor {
+class FeatureExtractor {           // like the reference: NO virtual destructor
 public:
-    virtual ~FeatureExtractor() {}
     virtual void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint> &keypoints, std::vector<FeatureDescriptor> &descriptors) = 0;
     virtual int GetLevels() = 0;
     virtual float GetScaleFactor() = 0;
@@ -102,16 +101,24 @@ protected:
 namespace HYSLAM {
 class ORBFactory : public FeatureFactory {
 public:
-    ORBFactory() { extractor_settings.nFeatures = 1000; extractor_settings.fScaleFactor = 1.2f; extractor_settings.nLevels = 8;
-                   extractor_settings.init_threshold = 20; extractor_settings.min_threshold = 7; extractor_settings.N_CELLS = 30; }
-    ORBFactory(std::string) : ORBFactory() {}
-    std::shared_ptr<FeatureExtractor> getExtractor(std::string) override { return nullptr; }              // the CPU extractor is not built here
-    std::shared_ptr<FeatureExtractor> getExtractor(FeatureExtractorSettings) override { return nullptr; }
+    ORBFactory() { load("SLAM"); extractor_settings.min_threshold = 4; }
+    ORBFactory(std::string settings_path_) : settings_path(settings_path_) { load("SLAM"); }
+    // ORBFactory.cpp:32-35: re-read the block of this camera type, then dispatch VIRTUALLY to the settings overload
+    std::shared_ptr<FeatureExtractor> getExtractor(std::string type) override { load(type); return getExtractor(extractor_settings); }
+    std::shared_ptr<FeatureExtractor> getExtractor(FeatureExtractorSettings) override { return nullptr; }      // the CPU extractor is not built here
     FeatureVocabulary *getVocabulary(std::string) override { return nullptr; }
     std::shared_ptr<DescriptorDistance> getDistanceFunc() override { return std::make_shared<ORBDistance>(); }
     FeatureExtractorSettings getFeatureExtractorSettings() override { return extractor_settings; }
-protected:
+private:                                           // private in the reference too (ORBFactory.h:29-34)
     FeatureExtractorSettings extractor_settings;
+    std::string vocab_path, settings_path;
+    void load(const std::string &type)             // stands in for LoadSettings: the values of config/slam_feature_config.yaml
+    {
+        const bool imaging = type == "Imaging";
+        extractor_settings.nFeatures = imaging ? 3000 : 1000; extractor_settings.fScaleFactor = imaging ? 1.4f : 1.2f; extractor_settings.nLevels = 8;
+        extractor_settings.init_threshold = 20; extractor_settings.min_threshold = 4; extractor_settings.N_CELLS = 30;
+        matcher_settings.TH_HIGH = 100.0; matcher_settings.TH_LOW = 50.0;
+    }
 };
 }
 

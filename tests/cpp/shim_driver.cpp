@@ -1,6 +1,7 @@
 // Runs the C++ drop-in (include/hyorb_hyslam.hpp) through the call sequence of ImageProcessing::ProcessStereoImage
 // (hySLAM src/main/ImageProcessing.cpp:69-116) and dumps what it produced; tests/test_gpu_cpp_shim.py compares the
-// dump with the CPU oracle.  Compiled against the test doubles in tests/cpp/mock_hyslam (this image has no OpenCV C++).
+// dump with the CPU oracle.  Compiled against the REAL hySLAM headers of /root/reference (+ oracle/cvshim for OpenCV) when that tree is present, else against
+// the test doubles in tests/cpp/mock_hyslam (tests/cpp/Makefile).
 //   shim_driver left.raw right.raw W H nFeatures mbf fx out.bin
 #include <hyorb_hyslam.hpp>
 
@@ -38,6 +39,17 @@ int main(int argc, char **argv)
         FeatureExtractorSettings s = factory.getFeatureExtractorSettings();
         s.nFeatures = nf;
         std::shared_ptr<FeatureExtractor> extractor_left = factory.getExtractor(s), extractor_right = factory.getExtractor(s);
+
+        // ImageProcessing.cpp:31-36 asks the factory per camera TYPE; the SLAM and Imaging blocks of the settings differ
+        {
+            std::shared_ptr<FeatureExtractor> imaging = factory.getExtractor(std::string("Imaging"));
+            const FeatureExtractorSettings si = factory.getFeatureExtractorSettings();
+            std::shared_ptr<FeatureExtractor> slam = factory.getExtractor(std::string("SLAM"));
+            const FeatureExtractorSettings ss = factory.getFeatureExtractorSettings();
+            if (!imaging || !slam || imaging->GetScaleFactor() != 1.4f || slam->GetScaleFactor() != 1.2f || si.nFeatures != 3000 || ss.nFeatures != 1000 ||
+                !dynamic_cast<CudaORBExtractor *>(imaging.get())) { fprintf(stderr, "per-camera-type settings are not honoured\n"); return 1; }
+            printf("camera types ok\n");
+        }
 
         std::vector<cv::KeyPoint> mvKeys, mvKeysRight;
         std::vector<FeatureDescriptor> mDescriptors, mDescriptorsRight;

@@ -1,25 +1,53 @@
-"""The C++ drop-in (include/hyorb_hyslam.hpp: hySLAM's FeatureExtractor / ORBFactory / Stereomatcher surfaces over the C
-ABI) compiles against test doubles of the hySLAM and OpenCV headers.  Running it needs a GPU: tests/test_gpu_cpp_shim.py."""
+"""The C++ drop-in (include/hyorb_hyslam.hpp: hySLAM's FeatureExtractor / ORBFactory / Stereomatcher surfaces over the C ABI).
+With the reference tree present it must compile -- every `override` checked by the compiler -- against the REAL hySLAM headers
+(/root/reference/src/{features,core}) and link with the reference's own FeatureDescriptor / FeatureViews translation units;
+the test doubles used on a box without the reference tree must keep compiling too.  Running it needs a GPU:
+tests/test_gpu_cpp_shim.py."""
 import os
 import subprocess
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("HYSLAM_REFERENCE", "/root/reference")
+HAVE_REF = os.path.exists(os.path.join(REF, "src", "features", "FeatureExtractor.h"))
+
+
+def _make(*targets):
+    from hyslam_b200 import _ffi
+    _ffi.build()
+    return subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), f"REF={REF}", *targets], capture_output=True, text=True)
 
 
 def test_shim_compiles_and_links():
-    from hyslam_b200 import _ffi
-    _ffi.build()
-    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp")], capture_output=True, text=True)
+    r = _make()
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert os.path.exists(os.path.join(ROOT, "tests", "cpp", "_build", "shim_driver"))
 
 
-def test_shim_mirrors_the_reference_signatures():
-    """the names the reference's call sites use (ImageProcessing.cpp:82-103, System.cc:77-85) exist in the shim"""
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree absent")
+def test_shim_is_built_against_the_real_hyslam_headers():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "clean"], capture_output=True)
+    r = _make()
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "real hySLAM headers" in open(os.path.join(ROOT, "tests", "cpp", "_build", "flavour.txt")).read()
+    # the compiler, not a grep, is the judge of the signatures: every member the shim marks `override` exists as a virtual of the
+    # reference's FeatureExtractor / ORBFactory with exactly that signature, or the line above would not have compiled.
     src = open(os.path.join(ROOT, "include", "hyorb_hyslam.hpp")).read()
-    for needle in ["class CudaORBExtractor : public FeatureExtractor", "class CudaORBFactory : public ORBFactory",
-                   "void operator()(cv::InputArray image, cv::InputArray", "std::vector<cv::KeyPoint> &keypoints",
-                   "std::vector<FeatureDescriptor> &descriptors", "CudaStereomatcher(FeatureViews views, Camera cam_data, FeatureMatcherSettings settings",
-                   "void computeStereoMatches()", "void getData(std::vector<float> &mvuRight_, std::vector<float> &mvDepth_)",
-                   "void getData(FeatureViews &views)", "std::shared_ptr<FeatureExtractor> getExtractor(FeatureExtractorSettings s) override"]:
-        assert needle in src, needle
+    assert src.count(" override") >= 8 and "~CudaORBExtractor() override" not in src
+
+
+def test_test_doubles_still_compile():
+    r = _make("doubles")
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree absent")
+def test_doubles_declare_what_the_reference_declares():
+    """the doubles are only trustworthy if they do not promise more than hySLAM's headers: no virtual destructor on
+    FeatureExtractor (FeatureExtractor.h:25-37), extractor settings private to ORBFactory (ORBFactory.h:29-34)"""
+    real = open(os.path.join(REF, "src", "features", "FeatureExtractor.h")).read()
+    dbl = open(os.path.join(ROOT, "tests", "cpp", "mock_hyslam", "hyslam_test_doubles.hpp")).read()
+    assert "~FeatureExtractor" not in real and "~FeatureExtractor" not in dbl
+    for name in ("GetLevels", "GetScaleFactor", "GetScaleFactors", "GetInverseScaleFactors", "GetScaleSigmaSquares", "GetInverseScaleSigmaSquares"):
+        assert f"{name}()" in real and f"{name}()" in dbl

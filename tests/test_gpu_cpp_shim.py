@@ -32,6 +32,7 @@ def test_process_stereo_image_through_the_cpp_shim(tmp_path, kind, h, w, seed, n
     assert r.returncode == 0, r.stdout + r.stderr
     print(r.stdout)
     assert "fused stereo ok" in r.stdout          # CudaStereoFrontEnd (one device call) == extractor x 2 + CudaStereomatcher
+    assert "camera types ok" in r.stdout          # getExtractor("Imaging") / ("SLAM") read their own settings block
     assert "camera frame ok" in r.stdout          # PreProcessImg + extraction through the shim == the gray path
     buf = open(op, "rb").read()
     nl, nr, nlev, kpsz = (int(v) for v in np.frombuffer(buf, np.int32, 4))
