@@ -162,3 +162,142 @@ def shim_gemm(A, B, Cm=None, ta=False):
 def shim_norm(a):
     a = np.ascontiguousarray(a, np.float32).reshape(-1)
     return float(lib().cvshim_norm(_p(a), len(a)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# matcher side: the reference's FeatureMatcher / MatchCriteria / Frame / KeyFrame / MapPoint (oracle/ref_glue_match.cpp)
+# ---------------------------------------------------------------------------------------------------------------------
+class FrameDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kps", C.c_void_p), ("desc", C.c_void_p), ("uR", C.c_void_p), ("depth", C.c_void_p),
+                ("K", C.c_float * 9), ("mbf", C.c_float), ("sensor", C.c_int32),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("Tcw", C.c_float * 16), ("size_ref", C.c_float), ("sigma_ref", C.c_float)]
+
+
+class MatcherSettings(C.Structure):
+    _fields_ = [("nnratio", C.c_float), ("th_high", C.c_float), ("th_low", C.c_float), ("check_ori", C.c_int32)]
+
+
+def settings(nnratio=0.6, th_high=100.0, th_low=50.0, check_ori=True):
+    return MatcherSettings(nnratio, th_high, th_low, int(check_ori))
+
+
+class Scene:
+    """MapPoints + Frames / KeyFrames built from flat arrays inside the reference's own classes."""
+
+    def __init__(self, max_mappoints):
+        L = lib()
+        L.refm_scene_create.restype = C.c_void_p
+        self.h = C.c_void_p(L.refm_scene_create(int(max_mappoints)))
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            lib().refm_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def add_mappoints(self, Pw, desc, normal=None, size=None, min_dist=None, max_dist=None, bad=None, n_protected=None):
+        Pw = np.ascontiguousarray(Pw, np.float32).reshape(-1, 3)
+        n = len(Pw)
+        f = lambda a, dt=np.float32: None if a is None else np.ascontiguousarray(a, dt)
+        normal, size, min_dist, max_dist = f(normal), f(size), f(min_dist), f(max_dist)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        first = lib().refm_add_mappoints(self.h, n, _p(Pw), _p(normal), _p(size), _p(min_dist), _p(max_dist), _p(desc), _p(f(bad, np.uint8)),
+                                         _p(f(n_protected, np.int32)))
+        if first < 0:
+            raise RuntimeError("scene capacity exceeded")
+        return first
+
+    def add_frame(self, kps, desc, K, Tcw, bounds, mbf=0.0, stereo=False, uR=None, depth=None, assoc=None, keyframe=False, size_ref=31.0, sigma_ref=1.0):
+        kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+        d = FrameDesc()
+        d.n = len(kps); d.kps = kps.ctypes.data; d.desc = desc.ctypes.data
+        if uR is not None:
+            uR = np.ascontiguousarray(uR, np.float32)
+            depth = np.ascontiguousarray(depth if depth is not None else np.where(uR >= 0, 1.0, -1.0), np.float32)
+            d.uR = uR.ctypes.data; d.depth = depth.ctypes.data
+        d.K[:] = [float(v) for v in np.asarray(K, np.float32).reshape(9)]
+        d.Tcw[:] = [float(v) for v in np.asarray(Tcw, np.float32).reshape(16)]
+        d.mbf = float(mbf); d.sensor = 1 if stereo else 0
+        d.min_x, d.max_x, d.min_y, d.max_y = [float(v) for v in bounds]
+        d.size_ref = float(size_ref); d.sigma_ref = float(sigma_ref)
+        a = None if assoc is None else np.ascontiguousarray(assoc, np.int32)
+        self._keep += [kps, desc, uR, depth, a]
+        fid = lib().refm_add_frame(self.h, C.byref(d), _p(a), int(keyframe))
+        if fid < 0:
+            raise RuntimeError("refm_add_frame failed")
+        return fid
+
+    def set_feature_nodes(self, frame, node_of):
+        a = np.ascontiguousarray(node_of, np.int32)
+        lib().refm_set_feature_nodes(self.h, frame, _p(a), len(a))
+
+    def set_observation_count(self, mp, n):
+        lib().refm_set_observation_count(self.h, int(mp), int(n))
+
+    def assoc(self, frame, n):
+        out = np.empty(n, np.int32)
+        lib().refm_get_assoc(self.h, frame, _p(out), n)
+        return out
+
+    def features_in_area(self, frame, x, y, r, cap=20000):
+        out = np.empty(cap, np.int32)
+        n = lib().refm_features_in_area(self.h, frame, C.c_float(x), C.c_float(y), C.c_float(r), _p(out), cap)
+        assert n >= 0
+        return out[:n].copy()
+
+    def camera_center(self, frame):
+        o = np.empty(3, np.float32)
+        lib().refm_camera_center(self.h, frame, _p(o))
+        return o
+
+    def project(self, frame, mp):
+        uv = np.empty(3, np.float32); sz = C.c_float()
+        ok = lib().refm_project(self.h, frame, int(mp), _p(uv), C.byref(sz))
+        return bool(ok), uv, np.float32(sz.value)
+
+    def search_by_projection(self, frame, lm_ids, th, st):
+        a = np.ascontiguousarray(lm_ids, np.int32)
+        return lib().refm_search_by_projection(self.h, frame, _p(a), len(a), C.c_float(th), C.byref(st))
+
+    def search_by_projection_motion(self, cur, last, th, st, mono=False):
+        return lib().refm_search_by_projection_motion(self.h, cur, last, C.c_float(th), int(mono), C.byref(st))
+
+    def search_by_projection_reloc(self, cur, kf, found, th, orb_dist, st):
+        a = np.ascontiguousarray(found, np.int32)
+        return lib().refm_search_by_projection_reloc(self.h, cur, kf, _p(a), len(a), C.c_float(th), int(orb_dist), C.byref(st))
+
+    def fuse(self, kf, lm_ids, th, reproj_err, st):
+        a = np.ascontiguousarray(lm_ids, np.int32)
+        oi = np.empty(len(a) + 1, np.int32); ol = np.empty(len(a) + 1, np.int32)
+        n = lib().refm_fuse(self.h, kf, _p(a), len(a), C.c_float(th), C.c_float(reproj_err), C.byref(st), _p(oi), _p(ol), len(oi))
+        assert n >= 0
+        return oi[:n].copy(), ol[:n].copy()
+
+    def search_for_initialization(self, f1, f2, prev_matched, window, st):
+        pm = np.ascontiguousarray(prev_matched, np.float32).copy()
+        m12 = np.empty(len(pm), np.int32)
+        n = lib().refm_search_for_initialization(self.h, f1, f2, _p(pm), _p(m12), int(window), C.byref(st))
+        return n, m12, pm
+
+    def search_by_sim3(self, kf1, kf2, matches12, s12, R12, t12, th, st):
+        m = np.ascontiguousarray(matches12, np.int32).copy()
+        R = np.ascontiguousarray(R12, np.float32); t = np.ascontiguousarray(t12, np.float32)
+        n = lib().refm_search_by_sim3(self.h, kf1, kf2, _p(m), len(m), C.c_float(s12), _p(R), _p(t), C.c_float(th), C.byref(st))
+        return n, m
+
+    def search_for_triangulation(self, kf1, kf2, F12, only_stereo, st, cap=20000):
+        Fm = np.ascontiguousarray(F12, np.float32)
+        a = np.empty(cap, np.int32); b = np.empty(cap, np.int32)
+        n = lib().refm_search_for_triangulation(self.h, kf1, kf2, _p(Fm), int(only_stereo), C.byref(st), _p(a), _p(b), cap)
+        assert n >= 0
+        return a[:n].copy(), b[:n].copy()
+
+    def search_by_bow(self, kf, frame, st, cap=20000):
+        a = np.empty(cap, np.int32); b = np.empty(cap, np.int32)
+        n = lib().refm_search_by_bow(self.h, kf, frame, C.byref(st), _p(a), _p(b), cap)
+        assert n >= 0
+        return a[:n].copy(), b[:n].copy()
