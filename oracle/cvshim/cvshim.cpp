@@ -187,20 +187,22 @@ static Mat transpose_eval(const Mat &a)
     return d;
 }
 
-// element-wise a*sa + b*sb (fp32: evaluated the way cv::addWeighted / scaleAdd do for these shapes: in fp32 for plain
-// add / subtract, through double when a scale factor is involved)
+// element-wise a*sa + b*sb.  CV_32F follows OpenCV's work type for float data: a scaled Mat (`M * s`, `M / s`, `s * M.t()`) is
+// Mat::convertTo(..., alpha) = cvtScale_<float, float, float>: src * (float)alpha in FLOAT arithmetic; plain sums and
+// differences are cv::add / cv::subtract (exact float ops); a general two-term combination is addWeighted in float.
 static Mat lincomb(const Mat &a, double sa, const Mat &b, double sb)
 {
     assert(b.empty() || (a.rows == b.rows && a.cols == b.cols && a.type() == b.type()));
     Mat d(a.rows, a.cols, a.type());
     const bool plain = (sa == 1 || sa == -1) && (sb == 1 || sb == -1 || b.empty());
+    const float fa = (float)sa, fb = (float)sb;
     for (int r = 0; r < a.rows; r++)
         for (int c = 0; c < a.cols; c++) {
             if (a.depth() == CV_32F) {
                 const float x = a.at<float>(r, c), y = b.empty() ? 0.f : b.at<float>(r, c);
-                if (b.empty()) d.at<float>(r, c) = plain ? (sa < 0 ? -x : x) : (float)(x * sa);
+                if (b.empty()) d.at<float>(r, c) = plain ? (sa < 0 ? -x : x) : x * fa;
                 else if (plain) d.at<float>(r, c) = (sa < 0 ? -x : x) + (sb < 0 ? -y : y);
-                else d.at<float>(r, c) = (float)(x * sa + y * sb);
+                else d.at<float>(r, c) = x * fa + y * fb;
             } else if (a.depth() == CV_64F) {
                 const double x = a.at<double>(r, c), y = b.empty() ? 0.0 : b.at<double>(r, c);
                 d.at<double>(r, c) = x * sa + y * sb;

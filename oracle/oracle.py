@@ -380,3 +380,60 @@ def rotation_consistency(angle_prev, angle_curr):
     if rc != 0:
         raise RuntimeError(f"orc_rotation_consistency rc={rc}")
     return keep
+
+
+# ---- round 2: remaining matcher entry points (Fuse, SearchBySim3, SearchForInitialization) ----
+def viewing_angle(Ow, Pw, normal, max_angle=1.047):
+    """ViewingAngleCriterionCore (MatchCriteria.cpp:94-110)"""
+    Ow = np.ascontiguousarray(Ow, np.float32); Pw = np.ascontiguousarray(Pw, np.float32).reshape(-1, 3)
+    normal = np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+    out = np.empty(len(Pw), np.uint8)
+    lib().orc_viewing_angle(_p(Ow), _p(Pw), _p(normal), len(Pw), C.c_float(max_angle), _p(out))
+    return out
+
+
+def match_window_ex(kps, tdesc, t_uR, t_matched, bounds, off, idx, queries, qdesc, thr, ratio, rule=0, q_active=None, reproj_thr=-1.0,
+                    sigma_ref=1.0, size_ref=31.0):
+    kps = np.ascontiguousarray(kps); tdesc = np.ascontiguousarray(tdesc, np.uint8)
+    queries = np.ascontiguousarray(queries, WQ_DTYPE); qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    t_uR = None if t_uR is None else np.ascontiguousarray(t_uR, np.float32)
+    t_matched = None if t_matched is None else np.ascontiguousarray(t_matched, np.uint8)
+    q_active = None if q_active is None else np.ascontiguousarray(q_active, np.uint8)
+    idx = np.ascontiguousarray(idx, np.int32) if len(idx) else np.zeros(1, np.int32)
+    nq = len(queries)
+    bi = np.empty(nq, np.int32); b = np.empty(nq, np.uint16); s = np.empty(nq, np.uint16); acc = np.empty(nq, np.uint8)
+    rc = lib().orc_match_window_ex(_p(kps), _p(tdesc), _p(t_uR), _p(t_matched), len(kps), C.byref(bounds), _p(off), _p(idx), _p(queries), _p(qdesc),
+                                   _p(q_active), nq, C.c_float(thr), C.c_float(ratio), int(rule), C.c_float(reproj_thr), C.c_float(sigma_ref),
+                                   C.c_float(size_ref), _p(bi), _p(b), _p(s), _p(acc))
+    if rc != 0:
+        raise RuntimeError(f"orc_match_window_ex rc={rc}")
+    return bi, b, s, acc
+
+
+def project_sim3(R_a, t_a, sR_ba, t_ba, pr_b, lms, kps_b, th, size_ref=31.0):
+    """one direction of SearchBySim3 (FeatureMatcher.cc:783-845): (window queries, passed flags)"""
+    f = lambda a: np.ascontiguousarray(a, np.float32).reshape(-1)
+    lms = np.ascontiguousarray(lms, LM_DTYPE); kps_b = np.ascontiguousarray(kps_b)
+    n = len(lms)
+    q = np.zeros(n, WQ_DTYPE); passed = np.zeros(n, np.uint8)
+    Ra, ta, sR, tb = f(R_a), f(t_a), f(sR_ba), f(t_ba)
+    rc = lib().orc_project_sim3(_p(Ra), _p(ta), _p(sR), _p(tb), C.byref(pr_b), _p(lms), n, _p(kps_b), len(kps_b), C.c_float(th), C.c_float(size_ref),
+                                _p(q), _p(passed))
+    if rc != 0:
+        raise RuntimeError(f"orc_project_sim3 rc={rc}")
+    return q, passed
+
+
+def search_for_initialization(k1, d1, k2, d2, bounds, prev_xy, window, thr=50.0, ratio=0.9):
+    """FeatureMatcher::SearchForInitialization (FeatureMatcher.cc:404-462): (n_matches, matches12, updated prev_xy)"""
+    k1 = np.ascontiguousarray(k1); k2 = np.ascontiguousarray(k2)
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    off, idx = grid_build(k2, bounds)
+    idx = np.ascontiguousarray(idx, np.int32) if len(idx) else np.zeros(1, np.int32)
+    pm = np.ascontiguousarray(prev_xy, np.float32).copy()
+    m12 = np.empty(len(k1), np.int32)
+    n = lib().orc_search_for_initialization(_p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), C.byref(bounds), _p(off), _p(idx), _p(pm), int(window),
+                                            C.c_float(thr), C.c_float(ratio), _p(m12))
+    if n < 0:
+        raise RuntimeError(f"orc_search_for_initialization rc={n}")
+    return n, m12, pm

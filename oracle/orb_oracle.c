@@ -1339,3 +1339,186 @@ ORC_API int orc_rotation_consistency(const float *angle_prev, const float *angle
     free(bin);
     return ORC_OK;
 }
+
+/* ========================================================================================== */
+/* Round 2: the remaining matcher entry points of FeatureMatcher.h:105-176.                    */
+/* Every function below is pinned against the reference's own code (oracle/_ref) by            */
+/* tests/test_oracle_match_vs_ref.py.                                                          */
+/* ========================================================================================== */
+
+/* ViewingAngleCriterionCore (MatchCriteria.cpp:94-110), used by FeatureMatcher::Fuse (:469):   */
+/* PO = Pw - Ow; d = (float)cv::norm(PO); PO = PO / d  (cv::Mat / scalar = convertTo with        */
+/* alpha = 1/d: multiplication by (float)(1.0 / d) in float); pass iff PO.dot(Pn) > cos(angle),  */
+/* dot accumulated in double, cos(float) = cosf (the <math.h> float overload).                   */
+ORC_API int orc_viewing_angle(const float *Ow, const float *Pw, const float *normal, int n, float max_angle, uint8_t *pass)
+{
+    const float c = cosf(max_angle);
+    for (int i = 0; i < n; i++) {
+        const float PO[3] = {Pw[3 * i] - Ow[0], Pw[3 * i + 1] - Ow[1], Pw[3 * i + 2] - Ow[2]};
+        const float dist = (float)sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+        const float inv = (float)(1.0 / (double)dist);
+        double dot = 0.0;
+        for (int k = 0; k < 3; k++) dot += (double)(PO[k] * inv) * (double)normal[3 * i + k];
+        pass[i] = (uint8_t)(dot > c);
+    }
+    return ORC_OK;
+}
+
+/* Window scan with the full set of view criteria of FeatureMatcher.cc: as orc_match_window plus         */
+/*  * ProjectionViewCriterion (MatchCriteria.cpp:282-333 over KeyFrame::ReprojectionError,                  */
+/*    KeyFrame.cc:548-575) when reproj_thr >= 0: err = (u-x)^2 + (v-y)^2 + (uR_view >= 0 ? (ur-uR_view)^2 : 0), */
+/*    keep iff err / determineSigma2(kp.size) < (uR_view > 0 ? 1.3f : 1.0f) * reproj_thr;  views.uR(idx) = -1   */
+/*    for monocular views (t_uR == NULL);                                                                      */
+/*  * the acceptance rule as a parameter (0 landmark / 1 BoW / 2 mono-init).                                   */
+ORC_API int orc_match_window_ex(const orc_keypoint *kps, const uint8_t *tdesc, const float *t_uR, const uint8_t *t_matched, int nt,
+                                const orc_bounds *b, const int32_t *cell_off, const int32_t *cell_idx, const orc_window_query *q,
+                                const uint8_t *qdesc, const uint8_t *q_active, int nq, float thr, float ratio, int rule,
+                                float reproj_thr, float sigma_ref, float size_ref,
+                                int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted)
+{
+    int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nt + 1));
+    if (!cand) return ORC_ENOMEM;
+    for (int i = 0; i < nq; i++) {
+        best_idx[i] = -1; best[i] = 65535; second[i] = 65535; accepted[i] = 0;
+        if (q_active && !q_active[i]) continue;
+        int n = grid_query(kps, b, cell_off, cell_idx, q[i].u, q[i].v, q[i].r, cand, nt);
+        float bd = FLT_MAX, bd2 = FLT_MAX; int bi = -1;
+        for (int c = 0; c < n; c++) {
+            const int k = cand[c];
+            if (t_matched && t_matched[k]) continue;
+            if (!(kps[k].size > q[i].size_lo && kps[k].size < q[i].size_hi)) continue;
+            if (q[i].ur_radius >= 0) {
+                const float er = fabsf(q[i].ur - t_uR[k]);
+                if (!(er < q[i].ur_radius && t_uR[k] > 0)) continue;
+            }
+            if (reproj_thr >= 0) {
+                const float ur_view = t_uR ? t_uR[k] : -1.0f;
+                const float errX = q[i].u - kps[k].x, errY = q[i].v - kps[k].y;
+                float errXr = 0.0f;
+                if (ur_view >= 0.0f) errXr = q[i].ur - ur_view;
+                const float sserr = errX * errX + errY * errY + errXr * errXr;
+                const float sf = kps[k].size / size_ref;
+                const float sigma2 = sigma_ref * (sf * sf);                   /* FeatureExtractorSettings.cpp:5-8 */
+                const float stereo_factor = ur_view > 0 ? 1.30f : 1.00f;
+                if (!((sserr / sigma2) < stereo_factor * reproj_thr)) continue;
+            }
+            const float d = (float)orc_hamming(qdesc + (size_t)i * 32, tdesc + (size_t)k * 32);
+            if (d < bd) { bd2 = bd; bd = d; bi = k; }
+            else if (d < bd2) bd2 = d;
+        }
+        best_idx[i] = bi;
+        best[i] = bd == FLT_MAX ? 65535 : (uint16_t)bd;
+        second[i] = bd2 == FLT_MAX ? 65535 : (uint16_t)bd2;
+        accepted[i] = (uint8_t)(bi >= 0 && accept_rule(rule, bd, bd2, thr, ratio));
+    }
+    free(cand);
+    return ORC_OK;
+}
+
+/* One direction of FeatureMatcher::SearchBySim3 (FeatureMatcher.cc:783-845 / 848-910): landmark of keyframe A ->      */
+/* camera A (R_a * Pw + t_a) -> camera B through the similarity (sR_ba * p + t_ba) -> Camera::Project of B; the 3-D    */
+/* distance in B must lie in the landmark's scale-invariance range; search radius = th * B.landMarkSizePixels(lm) /     */
+/* size_ref, where landMarkSizePixels projects with B's OWN pose (pr_b), not the similarity.  No view criteria:        */
+/* the window query carries open size bounds and no stereo radius.                                                     */
+ORC_API int orc_project_sim3(const float *R_a, const float *t_a, const float *sR_ba, const float *t_ba, const orc_projection *pr_b,
+                             const orc_landmark *lms, int n, const orc_keypoint *kps_b, int nb, float th, float size_ref,
+                             orc_window_query *queries, uint8_t *passed)
+{
+    for (int i = 0; i < n; i++) {
+        const orc_landmark *lm = &lms[i];
+        float pa[3], pb[3], Pch[3], uv[3];
+        gemm31(R_a, lm->Pw, t_a, pa);
+        gemm31(sR_ba, pa, t_ba, pb);
+        const float z = pb[2], invz = 1.0f / z;
+        Pch[0] = pb[0] / z; Pch[1] = pb[1] / z; Pch[2] = pb[2] / z;
+        gemm31(pr_b->K, Pch, NULL, uv);
+        uv[2] = pr_b->stereo ? uv[0] - pr_b->mbf * invz : -1.0f;
+        const int valid = z > 0.0f && uv[0] >= pr_b->bounds.min_x && uv[0] <= pr_b->bounds.max_x && uv[1] >= pr_b->bounds.min_y && uv[1] <= pr_b->bounds.max_y;
+        const float dist = (float)sqrt((double)pb[0] * pb[0] + (double)pb[1] * pb[1] + (double)pb[2] * pb[2]);
+        const int dist_ok = !(dist < lm->min_dist || dist > lm->max_dist);
+        float size_px;
+        if (lm->assoc_idx >= 0) {
+            if (lm->assoc_idx >= nb) return ORC_EINVAL;
+            size_px = kps_b[lm->assoc_idx].size;
+        } else {
+            float L[3] = {lm->Pw[0] - lm->size / 2, lm->Pw[1], lm->Pw[2]}, R[3] = {lm->Pw[0] + lm->size / 2, lm->Pw[1], lm->Pw[2]};
+            float ul[3], ur[3];
+            project_point(pr_b, L, ul); project_point(pr_b, R, ur);
+            size_px = ur[0] - ul[0];
+        }
+        queries[i].u = uv[0]; queries[i].v = uv[1]; queries[i].r = th * size_px / size_ref;
+        queries[i].size_lo = -FLT_MAX; queries[i].size_hi = FLT_MAX;
+        queries[i].ur = uv[2]; queries[i].ur_radius = -1.0f;
+        passed[i] = (uint8_t)(valid && dist_ok);
+    }
+    return ORC_OK;
+}
+
+/* FeatureMatcher::SearchForInitialization (FeatureMatcher.cc:404-462) with MonoInitScoreExceedsPrevious and MonoInitBestScore       */
+/* (MatchCriteria.cpp:486-549).  Sequential by construction: feature i1 of frame 1 may only take a frame-2 feature away from an       */
+/* earlier i1' if its distance is smaller than the stored one -- compared after TRUNCATION to int (`int dist = d1.distance(d2)`, :539) */
+/* against the float distance of the previous match; accepted matches overwrite (matches[idx2] = i1).  Then RotationConsistency        */
+/* (rot = angle(frame 1) - angle(frame 2), keyed by idx2), and the inverse map.  prev_xy (n1 x 2) is updated like vbPrevMatched.       */
+ORC_API int orc_search_for_initialization(const orc_keypoint *k1, const uint8_t *d1, int n1, const orc_keypoint *k2, const uint8_t *d2, int n2,
+                                          const orc_bounds *b2, const int32_t *cell_off2, const int32_t *cell_idx2, float *prev_xy, int window,
+                                          float thr, float ratio, int32_t *matches12)
+{
+    int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n2 + 1));
+    int32_t *owner = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n2 + 1));      /* matches: idx2 -> i1 */
+    float *dprev = (float *)malloc(sizeof(float) * (size_t)(n2 + 1));            /* MonoCriteriaData::distances */
+    uint8_t *keep = (uint8_t *)malloc((size_t)n2 + 1);
+    if (!cand || !owner || !dprev || !keep) { free(cand); free(owner); free(dprev); free(keep); return ORC_ENOMEM; }
+    for (int j = 0; j < n2; j++) { owner[j] = -1; dprev[j] = -1.0f; }
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int n = grid_query(k2, b2, cell_off2, cell_idx2, prev_xy[2 * i1], prev_xy[2 * i1 + 1], (float)window, cand, n2);
+        if (n <= 0) continue;
+        float bd = FLT_MAX, bd2 = FLT_MAX; int bi = -1;
+        for (int c = 0; c < n; c++) {
+            const int i2 = cand[c];
+            const int dist = orc_hamming(d1 + (size_t)i1 * 32, d2 + (size_t)i2 * 32);
+            if (!(dprev[i2] < 0) && !((float)dist < dprev[i2])) continue;          /* MonoInitScoreExceedsPrevious */
+            const float d = (float)dist;
+            if (d < bd) { bd2 = bd; bd = d; bi = i2; }
+            else if (d < bd2) bd2 = d;
+        }
+        if (bi >= 0 && accept_rule(2, bd, bd2, thr, ratio)) { owner[bi] = i1; dprev[bi] = bd; }
+    }
+    /* RotationConsistency(matches, views2, views1): idx_curr = idx2, idx_prev = i1 (MatchCriteria.cpp:684-725) */
+    int hist[30]; memset(hist, 0, sizeof(hist));
+    const float factor = 1.0f / 30;
+    for (int j = 0; j < n2; j++) {
+        if (owner[j] < 0) continue;
+        float rot = k1[owner[j]].angle - k2[j].angle;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)roundf(rot * factor);
+        if (bin == 30) bin = 0;
+        hist[bin]++;
+    }
+    int max1 = 0, max2 = 0, max3 = 0, i1m = -1, i2m = -1, i3m = -1;
+    for (int i = 0; i < 30; i++) {
+        const int sz = hist[i];
+        if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; i3m = i2m; i2m = i1m; i1m = i; }
+        else if (sz > max2) { max3 = max2; max2 = sz; i3m = i2m; i2m = i; }
+        else if (sz > max3) { max3 = sz; i3m = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { i2m = -1; i3m = -1; }
+    else if (max3 < 0.1f * (float)max1) { i3m = -1; }
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    int nm = 0;
+    for (int j = 0; j < n2; j++) {
+        if (owner[j] < 0) continue;
+        float rot = k1[owner[j]].angle - k2[j].angle;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)roundf(rot * factor);
+        if (bin == 30) bin = 0;
+        keep[j] = (uint8_t)(bin == i1m || bin == i2m || bin == i3m);
+        if (keep[j]) nm++;
+    }
+    /* matches_inverse[i1] = idx2: ascending idx2, later entries overwrite (:447-450) -- an i1 can own several idx2 */
+    for (int j = 0; j < n2; j++)
+        if (owner[j] >= 0 && keep[j]) matches12[owner[j]] = j;
+    for (int i = 0; i < n1; i++)
+        if (matches12[i] >= 0) { prev_xy[2 * i] = k2[matches12[i]].x; prev_xy[2 * i + 1] = k2[matches12[i]].y; }
+    free(cand); free(owner); free(dprev); free(keep);
+    return nm;
+}

@@ -299,3 +299,171 @@ def test_search_by_bow_keyframe_frame(frames):
     assert len(gidx) > 100
     assert gidx.tolist() == sorted(want) and glm.tolist() == [want[k] for k in sorted(want)]
     sc.close()
+
+
+@pytest.mark.parametrize("seed,window,ratio", [(0, 100, 0.9), (1, 40, 0.9), (2, 100, 0.6)])
+def test_search_for_initialization(frames, seed, window, ratio):
+    """FeatureMatcher::SearchForInitialization (FeatureMatcher.cc:404-462): the sequential mono-initialisation matcher
+    (MonoInitScoreExceedsPrevious + MonoInitBestScore, MatchCriteria.cpp:486-549; window 100 at MonoInitializer.cpp:83)"""
+    k1, d1, _, _ = frames[0]
+    rng = np.random.default_rng(seed)
+    n2 = 1700
+    src = rng.integers(0, len(k1), n2)                  # frame 2 re-observes frame-1 features (some several times: contention)
+    k2 = k1[src].copy()
+    k2["x"] += rng.normal(0, 12, n2).astype(np.float32); k2["y"] += rng.normal(0, 8, n2).astype(np.float32)
+    k2["angle"] = (k2["angle"] + rng.choice([0.0, 0.0, 0.0, 45.0], n2) + rng.normal(0, 2, n2)).astype(np.float32) % np.float32(360)
+    d2 = noisy_desc(rng, d1[src], 20)
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    sc = R.Scene(1)
+    f1 = sc.add_frame(k1, d1, K, np.eye(4), BOUNDS)
+    f2 = sc.add_frame(k2, d2, K, np.eye(4), BOUNDS)
+    nref, m12, pm = sc.search_for_initialization(f1, f2, prev, window, R.settings(nnratio=ratio, th_low=50.0))
+    nor, om12, opm = O.search_for_initialization(k1, d1, k2, d2, O.Bounds(*BOUNDS), prev, window, 50.0, ratio)
+    assert nref == nor and nref > 100
+    assert np.array_equal(m12, om12)
+    assert pm.tobytes() == opm.tobytes()
+    sc.close()
+
+
+@pytest.mark.parametrize("seed,stereo", [(0, True), (1, False)])
+def test_fuse(frames, seed, stereo):
+    """FeatureMatcher::Fuse(pKF, landmarks, fuse_matches, th, reprojection_err)  (FeatureMatcher.cc:464-521): pre-screen (bad / already in
+    the keyframe / protected), Projection + Distance + ViewingAngle(1.047) criteria, FeatureSize + ProjectionView + BestScore(TH_LOW, 1.0);
+    the first landmark that reaches a keypoint keeps it (std::map::insert)"""
+    kk, dk, uRk, depk = frames[seed % 2]
+    rng = np.random.default_rng(seed)
+    Rcw, tcw, T = pose(rng)
+    n = 1500
+    pick, Pw, size, raw_min, raw_max = landmarks_around(rng, kk, uRk, Rcw, tcw, n, stereo)
+    lm_desc = noisy_desc(rng, dk[pick])
+    Ow_true = -(Rcw.T.astype(np.float64) @ tcw.astype(np.float64))
+    normal = Pw.astype(np.float64) - Ow_true
+    normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    tilt = rng.normal(0, 0.9, (n, 3))
+    normal = (normal + tilt * (rng.random((n, 1)) < 0.5))            # half of them viewed at an angle, some beyond 60 degrees
+    normal = (normal / np.linalg.norm(normal, axis=1, keepdims=True)).astype(np.float32)
+    bad = (rng.random(n) < 0.05).astype(np.uint8)
+    prot = (rng.random(n) < 0.05).astype(np.int32)
+    assoc = np.full(len(kk), -1, np.int32)
+    for i in range(7, n, 23):                                         # landmarks the keyframe already observes: pre-screened out
+        if assoc[pick[i]] < 0:
+            assoc[pick[i]] = i
+    sc = R.Scene(n)
+    sc.add_mappoints(Pw, lm_desc, normal=normal, size=size, min_dist=raw_min, max_dist=raw_max, bad=bad, n_protected=prot)
+    kf = sc.add_frame(kk, dk, K, T, BOUNDS, mbf=MBF, stereo=stereo, uR=uRk if stereo else None, depth=depk if stereo else None, assoc=assoc, keyframe=True)
+    gidx, glm = sc.fuse(kf, np.arange(n), 3.0, 5.99, R.settings(th_low=50.0))
+    # oracle composition
+    in_kf = np.zeros(n, bool); in_kf[assoc[assoc >= 0]] = True
+    cand = np.nonzero(~(bad.astype(bool) | in_kf | (prot > 0)))[0]
+    Ow = sc.camera_center(kf)
+    pr = O.make_projection(Rcw, tcw, Ow, K, MBF, stereo, BOUNDS)
+    lms = np.zeros(len(cand), O.LM_DTYPE)
+    lms["Pw"] = Pw[cand]; lms["size"] = size[cand]; lms["min_dist"] = np.float32(0.8) * raw_min[cand]; lms["max_dist"] = np.float32(1.2) * raw_max[cand]
+    lms["assoc_idx"] = -1
+    q, passed = O.project_landmarks(pr, lms, kk, 3.0)
+    q["ur_radius"] = -1                                              # no StereoConsistencyCriterion in Fuse
+    passed &= O.viewing_angle(Ow, Pw[cand], normal[cand], 1.047)
+    bounds = O.Bounds(*BOUNDS)
+    off, idx = O.grid_build(kk, bounds)
+    bi, b, s, acc = O.match_window_ex(kk, dk, uRk if stereo else None, None, bounds, off, idx, q, lm_desc[cand], 50.0, 1.0, rule=0, q_active=passed,
+                                      reproj_thr=5.99)
+    want = {}
+    for j in range(len(cand)):
+        if acc[j] and int(bi[j]) not in want:
+            want[int(bi[j])] = int(cand[j])
+    assert len(gidx) > 30
+    assert gidx.tolist() == sorted(want) and glm.tolist() == [want[k] for k in sorted(want)]
+    sc.close()
+
+
+@pytest.mark.parametrize("seed,s12", [(0, 1.0), (1, 1.07)])
+def test_search_by_sim3(frames, seed, s12):
+    """FeatureMatcher::SearchBySim3 (FeatureMatcher.cc:739-937): each keyframe's landmarks are carried into the other camera through the
+    similarity [s12 R12 | t12], best Hamming in the window (<= TH_HIGH), and only mutually agreeing matches survive"""
+    k1, d1, uR1, dep1 = frames[0]
+    rng = np.random.default_rng(seed)
+    R1, t1, T1 = pose(rng, 0.05, 0.5)
+    R2, t2, T2 = pose(rng, 0.05, 0.5)
+    # one physical point per KF1 feature; KF2 sees (most of) them where its own pose projects them, with a noisy descriptor.  Both
+    # keyframes carry their OWN MapPoint for a point (duplicates -- the situation loop closing resolves): ids 0..n1-1 belong to KF1,
+    # n1.. to KF2
+    N = len(k1)
+    z = rng.uniform(4, 30, N)
+    Pc1 = np.stack([(k1["x"] - CX) * z / FX, (k1["y"] - CY) * z / FX, z], 1)
+    Pw = (Pc1 - t1.astype(np.float64)) @ R1.astype(np.float64)
+    Pc2 = Pw @ R2.astype(np.float64).T + t2.astype(np.float64)
+    u2 = FX * Pc2[:, 0] / Pc2[:, 2] + CX; v2 = FX * Pc2[:, 1] / Pc2[:, 2] + CY
+    vis = (Pc2[:, 2] > 0) & (u2 > 20) & (u2 < 1220) & (v2 > 20) & (v2 < 356)
+    src = np.nonzero(vis)[0]
+    src = src[rng.permutation(len(src))]
+    k2 = k1[src].copy()
+    k2["x"] = (u2[src] + rng.normal(0, 1.0, len(src))).astype(np.float32); k2["y"] = (v2[src] + rng.normal(0, 1.0, len(src))).astype(np.float32)
+    d2 = noisy_desc(rng, d1[src], 10)
+    uR2 = (k2["x"] - MBF / Pc2[src, 2]).astype(np.float32); dep2 = Pc2[src, 2].astype(np.float32)
+    has1 = rng.random(N) < 0.5                                       # KF1 features that carry a MapPoint
+    has2 = rng.random(len(src)) < 0.6
+    f1 = np.nonzero(has1)[0]; f2 = np.nonzero(has2)[0]
+    n1, n2 = len(f1), len(f2)
+    a1 = np.full(N, -1, np.int32); a2 = np.full(len(src), -1, np.int32)
+    a1[f1] = np.arange(n1); a2[f2] = n1 + np.arange(n2)
+    Pw1 = (Pw[f1] + rng.normal(0, 0.02, (n1, 3))).astype(np.float32); Pw2 = (Pw[src[f2]] + rng.normal(0, 0.02, (n2, 3))).astype(np.float32)
+    size1 = (k1["size"][f1] * z[f1] / FX).astype(np.float32); size2 = (k1["size"][src[f2]] * z[src[f2]] / FX).astype(np.float32)
+    rmin1 = (z[f1] * 0.5).astype(np.float32); rmax1 = (z[f1] * 1.6).astype(np.float32)
+    rmin2 = (z[src[f2]] * 0.5).astype(np.float32); rmax2 = (z[src[f2]] * 1.6).astype(np.float32)
+    ld1 = noisy_desc(rng, d1[f1], 8); ld2 = noisy_desc(rng, d2[f2], 8)
+    u1 = f1
+    bad = (rng.random(n1 + n2) < 0.04).astype(np.uint8)
+    sc = R.Scene(n1 + n2)
+    sc.add_mappoints(np.concatenate([Pw1, Pw2]), np.concatenate([ld1, ld2]), size=np.concatenate([size1, size2]),
+                     min_dist=np.concatenate([rmin1, rmin2]) * 0.3, max_dist=np.concatenate([rmax1, rmax2]) * 2, bad=bad)
+    kf1 = sc.add_frame(k1, d1, K, T1, BOUNDS, mbf=MBF, stereo=True, uR=uR1, depth=dep1, assoc=a1, keyframe=True)
+    kf2 = sc.add_frame(k2, d2, K, T2, BOUNDS, mbf=MBF, stereo=True, uR=uR2, depth=dep2, assoc=a2, keyframe=True)
+    # relative transform camera2 -> camera1 as the loop closer would hand it over: T12 = T1 * inv(T2) (+ scale)
+    T12 = T1.astype(np.float64) @ np.linalg.inv(T2.astype(np.float64))
+    R12 = T12[:3, :3].astype(np.float32); t12 = T12[:3, 3].astype(np.float32)
+    pre = np.full(len(k1), -1, np.int32)
+    pre[u1[::15]] = n1 + rng.integers(0, n2, len(u1[::15]))          # matches found earlier (e.g. by SearchByBoW): both ends are skipped
+    nref, m12 = sc.search_by_sim3(kf1, kf2, pre, s12, R12, t12, 7.5, R.settings(th_high=100.0))
+    # ---- oracle composition
+    f32 = np.float32
+    sR12 = (f32(s12) * R12).astype(f32)                              # cv::Mat * scalar: float multiply by (float)alpha
+    sR21 = (f32(1.0 / s12) * R12.T).astype(f32)
+    t21 = -np.array([(sR21[i, 0] * t12[0] + sR21[i, 1] * t12[1]) + sR21[i, 2] * t12[2] for i in range(3)], f32)       # -sR21*t12: small-matrix gemm, alpha -1
+    bounds = O.Bounds(*BOUNDS)
+    lmA = dict(Pw=np.concatenate([Pw1, Pw2]), size=np.concatenate([size1, size2]), mn=f32(0.8) * (np.concatenate([rmin1, rmin2]) * 0.3).astype(f32),
+               mx=f32(1.2) * (np.concatenate([rmax1, rmax2]) * 2).astype(f32), desc=np.concatenate([ld1, ld2]))
+    matched1 = pre >= 0
+    matched2 = np.zeros(len(k2), bool)
+    for i in np.nonzero(matched1)[0]:
+        j = np.nonzero(a2 == pre[i])[0]                              # pMP->GetIndexInKeyFrame(pKF2)
+        if len(j):
+            matched2[j[0]] = True
+
+    def direction(kA, assocA, matchedA, RA, tA, sR, t, kB, dB, assocB, RB, tB, OwB):
+        feats = np.array([i for i in range(len(kA)) if assocA[i] >= 0 and not matchedA[i] and not bad[assocA[i]]], np.int32)
+        ids = assocA[feats]
+        lms = np.zeros(len(ids), O.LM_DTYPE)
+        lms["Pw"] = lmA["Pw"][ids]; lms["size"] = lmA["size"][ids]; lms["min_dist"] = lmA["mn"][ids]; lms["max_dist"] = lmA["mx"][ids]
+        lms["assoc_idx"] = -1
+        for j, lid in enumerate(ids):                               # pKF_B->landMarkSizePixels: B's own association, if any
+            w = np.nonzero(assocB == lid)[0]
+            if len(w):
+                lms["assoc_idx"][j] = w[0]
+        prB = O.make_projection(RB, tB, OwB, K, MBF, True, BOUNDS)
+        q, passed = O.project_sim3(RA, tA, sR, t, prB, lms, kB, 7.5)
+        off, idx = O.grid_build(kB, bounds)
+        bi, b, s, acc = O.match_window_ex(kB, dB, None, None, bounds, off, idx, q, lmA["desc"][ids], 100.0, np.inf, rule=0, q_active=passed)
+        out = np.full(len(kA), -1, np.int32)
+        out[feats[acc > 0]] = bi[acc > 0]
+        return out
+    vn1 = direction(k1, a1, matched1, R1, t1, sR21, t21, k2, d2, a2, R2, t2, sc.camera_center(kf2))
+    vn2 = direction(k2, a2, matched2, R2, t2, sR12, t12, k1, d1, a1, R1, t1, sc.camera_center(kf1))
+    want = pre.copy()
+    nfound = 0
+    for i1 in range(len(k1)):
+        if vn1[i1] >= 0 and vn2[vn1[i1]] == i1:
+            want[i1] = a2[vn1[i1]]
+            nfound += 1
+    assert nref == nfound and nref > 20
+    assert np.array_equal(m12, want)
+    sc.close()
