@@ -71,6 +71,7 @@ SYMBOLS = [
     "hyorb_extractor_stage_times", "hyorb_extractor_set_pipelining", "hyorb_distinctive_descriptor_host", "hyorb_project_landmarks_host", "hyorb_search_by_projection_host", "hyorb_search_by_projection_ex_host",
     "hyorb_vocabulary_create", "hyorb_vocabulary_destroy", "hyorb_bow_transform_host", "hyorb_search_by_bow_host",
     "hyorb_preprocess_size", "hyorb_preprocess_device", "hyorb_extract_color_host", "hyorb_search_for_triangulation_host", "hyorb_match_csr_epipolar_host",
+    "hyorb_fuse_host", "hyorb_search_by_sim3_host", "hyorb_search_for_initialization_host",
 ]
 N_STAGES = 6
 STAGE_NAMES = ("pyramid", "fast", "quadtree", "blur", "describe", "stereo")
@@ -165,6 +166,14 @@ def lib():
         L.hyorb_search_by_projection_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                                       C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hyorb_fuse_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hyorb_search_by_sim3_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p]
+        L.hyorb_search_for_initialization_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, Bounds,
+                                                           C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -1037,6 +1037,139 @@ HYORB_API int hyorb_search_by_projection_ex_host(hyorb_matcher *m, const hyorb_p
     return m_sync(m);
 }
 
+// shared tail of the projection-style searches: grid over the target keypoints (already in d_a), window scan of the queries in d_g gated by
+// d_k, results in d_c / d_d / d_pkey / d_f
+static int m_window_scan(hyorb_matcher *m, const hyorb_bounds &bounds, const uint8_t *t_desc, const float *t_uR, const uint8_t *t_matched, int nt,
+                         const uint8_t *q_desc, int n, float thr, float ratio, const WindowCriteria &wc)
+{
+    constexpr int NC = HYORB_GRID_COLS * HYORB_GRID_ROWS;
+    HY_TRY(m_upload(m, m->d_b, t_desc, (size_t)nt * 32));
+    if (t_uR) HY_TRY(m_upload(m, m->d_l, t_uR, sizeof(float) * (size_t)nt));
+    if (t_matched) HY_TRY(m_upload(m, m->d_bestd, t_matched, (size_t)nt));
+    HY_TRY(m_upload(m, m->d_h, q_desc, (size_t)n * 32));
+    HY_TRY(m->d_i.ensure(sizeof(int32_t) * (NC + 1)));
+    HY_TRY(m->d_j.ensure(sizeof(int32_t) * std::max(nt, 1)));
+    HY_TRY(m->d_cellof.ensure(sizeof(int32_t) * std::max(nt, 1)));
+    HY_TRY(m->d_cellcnt.ensure(sizeof(int32_t) * NC));
+    HY_TRY(m->d_c.ensure(sizeof(int32_t) * (size_t)n));
+    HY_TRY(m->d_d.ensure(sizeof(uint16_t) * (size_t)n));
+    HY_TRY(m->d_pkey.ensure(sizeof(uint16_t) * (size_t)n));
+    HY_TRY(m->d_f.ensure((size_t)n));
+    HY_TRY(launch_grid_build(m->d_a.as<hyorb_keypoint>(), nt, bounds, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(), m->d_cellof.as<int32_t>(),
+                             m->d_cellcnt.as<int32_t>(), m->stream, &m->launches));
+    return launch_match_window(m->d_a.as<hyorb_keypoint>(), m->d_b.as<uint8_t>(), t_uR ? m->d_l.as<float>() : nullptr,
+                               t_matched ? m->d_bestd.as<uint8_t>() : nullptr, nt, bounds, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(),
+                               m->d_g.as<hyorb_window_query>(), m->d_h.as<uint8_t>(), n, thr, ratio, m->d_c.as<int32_t>(), m->d_d.as<uint16_t>(),
+                               m->d_pkey.as<uint16_t>(), m->d_f.as<uint8_t>(), m->stream, &m->launches, m->d_k.as<uint8_t>(), wc);
+}
+
+HYORB_API int hyorb_fuse_host(hyorb_matcher *m, const hyorb_projection *pr, const hyorb_landmark *lms, const float *lm_normal, const uint8_t *lm_desc, int n,
+                              const hyorb_keypoint *t_kps, const uint8_t *t_desc, const float *t_uR, int nt, float th, float size_ref, float sigma_ref,
+                              float reproj_err, float cos_max_angle, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
+                              uint8_t *accepted, uint8_t *passed)
+{
+    HY_TRY(m_prepare(m));
+    if (n < 0 || nt < 0 || !pr) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (n == 0) return HYORB_OK;
+    if (!lms || !lm_normal || !lm_desc || !best_idx || !best || !second || !accepted || (nt > 0 && (!t_kps || !t_desc))) { set_error("null argument"); return HYORB_EINVAL; }
+    HY_TRY(m_upload(m, m->d_e, lms, sizeof(hyorb_landmark) * (size_t)n));
+    HY_TRY(m_upload(m, m->d_a, t_kps, sizeof(hyorb_keypoint) * (size_t)nt));
+    HY_TRY(m_upload(m, m->d_psecond, lm_normal, sizeof(float) * 3 * (size_t)n));
+    HY_TRY(m->d_g.ensure(sizeof(hyorb_window_query) * (size_t)n));
+    HY_TRY(m->d_k.ensure((size_t)n));
+    // no StereoConsistencyCriterion in Fuse (FeatureMatcher.cc:471-474): HYORB_SBP_STEREO stays off, the queries carry ur for the reprojection error only
+    HY_TRY(launch_project_landmarks(*pr, m->d_e.as<hyorb_landmark>(), n, m->d_a.as<hyorb_keypoint>(), nt, th, size_ref, 0.5f, 1.5f,
+                                    HYORB_SBP_DISTANCE | HYORB_SBP_VIEWANGLE, m->d_g.as<hyorb_window_query>(), m->d_k.as<uint8_t>(), m->d_status.as<int>(),
+                                    m->stream, &m->launches, m->d_psecond.as<float>(), cos_max_angle));
+    WindowCriteria wc;
+    wc.rule = HYORB_RULE_LANDMARK; wc.reproj_thr = reproj_err; wc.sigma_ref = sigma_ref; wc.size_ref = size_ref;
+    HY_TRY(m_window_scan(m, pr->bounds, t_desc, t_uR, nullptr, nt, lm_desc, n, thr, ratio, wc));
+    HY_CUDA(cudaMemcpyAsync(best_idx, m->d_c.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(best, m->d_d.p, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(second, m->d_pkey.p, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(accepted, m->d_f.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    if (passed) HY_CUDA(cudaMemcpyAsync(passed, m->d_k.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    return m_sync(m);
+}
+
+HYORB_API int hyorb_search_by_sim3_host(hyorb_matcher *m, const float *R_a, const float *t_a, const float *sR_ba, const float *t_ba, const hyorb_projection *pr_b,
+                                        const hyorb_landmark *lms, const uint8_t *lm_desc, int n, const hyorb_keypoint *kps_b, const uint8_t *desc_b, int nb,
+                                        float th, float size_ref, float thr, int32_t *best_idx, uint16_t *best, uint8_t *accepted, uint8_t *passed)
+{
+    HY_TRY(m_prepare(m));
+    if (n < 0 || nb < 0 || !pr_b || !R_a || !t_a || !sR_ba || !t_ba) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (n == 0) return HYORB_OK;
+    if (!lms || !lm_desc || !best_idx || !best || !accepted || (nb > 0 && (!kps_b || !desc_b))) { set_error("null argument"); return HYORB_EINVAL; }
+    HY_TRY(m_upload(m, m->d_e, lms, sizeof(hyorb_landmark) * (size_t)n));
+    HY_TRY(m_upload(m, m->d_a, kps_b, sizeof(hyorb_keypoint) * (size_t)nb));
+    HY_TRY(m->d_g.ensure(sizeof(hyorb_window_query) * (size_t)n));
+    HY_TRY(m->d_k.ensure((size_t)n));
+    HY_TRY(launch_project_sim3(R_a, t_a, sR_ba, t_ba, *pr_b, m->d_e.as<hyorb_landmark>(), n, m->d_a.as<hyorb_keypoint>(), nb, th, size_ref,
+                               m->d_g.as<hyorb_window_query>(), m->d_k.as<uint8_t>(), m->d_status.as<int>(), m->stream, &m->launches));
+    // `bestDist <= TH_HIGH` is the whole acceptance test (:840): the landmark rule with an infinite ratio never rejects on the second best
+    HY_TRY(m_window_scan(m, pr_b->bounds, desc_b, nullptr, nullptr, nb, lm_desc, n, thr, INFINITY, WindowCriteria()));
+    HY_CUDA(cudaMemcpyAsync(best_idx, m->d_c.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(best, m->d_d.p, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(accepted, m->d_f.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    if (passed) HY_CUDA(cudaMemcpyAsync(passed, m->d_k.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    return m_sync(m);
+}
+
+HYORB_API int hyorb_search_for_initialization_host(hyorb_matcher *m, const hyorb_keypoint *k1, const uint8_t *d1, int n1, const hyorb_keypoint *k2,
+                                                   const uint8_t *d2, int n2, hyorb_bounds bounds2, float *prev_xy, int window, float thr, float ratio,
+                                                   int32_t *matches12, int32_t *n_matches)
+{
+    HY_TRY(m_prepare(m));
+    if (n1 < 0 || n2 < 0 || window < 0) { set_error("bad argument"); return HYORB_EINVAL; }
+    if (n_matches) *n_matches = 0;
+    if (n1 == 0) return HYORB_OK;
+    if (!k1 || !d1 || !prev_xy || !matches12 || (n2 > 0 && (!k2 || !d2))) { set_error("null argument"); return HYORB_EINVAL; }
+    constexpr int NC = HYORB_GRID_COLS * HYORB_GRID_ROWS;
+    HY_TRY(m_upload(m, m->d_kp1, k1, sizeof(hyorb_keypoint) * (size_t)n1));
+    HY_TRY(m_upload(m, m->d_a, k2, sizeof(hyorb_keypoint) * (size_t)n2));
+    HY_TRY(m_upload(m, m->d_h, d1, (size_t)n1 * 32));
+    HY_TRY(m_upload(m, m->d_b, d2, (size_t)n2 * 32));
+    HY_TRY(m_upload(m, m->d_l, prev_xy, sizeof(float) * 2 * (size_t)n1));
+    HY_TRY(m->d_i.ensure(sizeof(int32_t) * (NC + 1)));
+    HY_TRY(m->d_j.ensure(sizeof(int32_t) * std::max(n2, 1)));
+    HY_TRY(m->d_cellof.ensure(sizeof(int32_t) * std::max(n2, 1)));
+    HY_TRY(m->d_cellcnt.ensure(sizeof(int32_t) * NC));
+    // claims, double-buffered: [claim2 | claimd] x 2; per-i2 list heads, per-i1 links, owner, result, flags
+    HY_TRY(m->d_c.ensure(sizeof(int32_t) * 4 * (size_t)n1));
+    HY_TRY(m->d_d.ensure(sizeof(int32_t) * (size_t)std::max(n2, 1)));      // head
+    HY_TRY(m->d_e.ensure(sizeof(int32_t) * (size_t)n1));                   // next
+    HY_TRY(m->d_rowtab.ensure(sizeof(int32_t) * (size_t)std::max(n2, 1))); // owner
+    HY_TRY(m->d_g.ensure(sizeof(int32_t) * (size_t)n1));                   // matches12
+    HY_TRY(m->d_f.ensure(sizeof(int) * 2));                                // changed, n_matches
+    HY_TRY(launch_grid_build(m->d_a.as<hyorb_keypoint>(), n2, bounds2, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(), m->d_cellof.as<int32_t>(),
+                             m->d_cellcnt.as<int32_t>(), m->stream, &m->launches));
+    int32_t *buf = m->d_c.as<int32_t>();
+    HY_CUDA(cudaMemsetAsync(buf, 0xFF, sizeof(int32_t) * 4 * (size_t)n1, m->stream));      // no claims yet
+    int cur = 0, passes = 0;
+    for (;;) {
+        int32_t *c2 = buf + (size_t)cur * 2 * n1, *cd = c2 + n1, *o2 = buf + (size_t)(cur ^ 1) * 2 * n1, *od = o2 + n1;
+        HY_TRY(launch_mono_pass(m->d_h.as<uint8_t>(), n1, m->d_a.as<hyorb_keypoint>(), m->d_b.as<uint8_t>(), n2, bounds2, m->d_i.as<int32_t>(), m->d_j.as<int32_t>(),
+                                m->d_l.as<float>(), (float)window, thr, ratio, c2, cd, m->d_d.as<int32_t>(), m->d_e.as<int32_t>(), o2, od, m->d_f.as<int>(),
+                                m->stream, &m->launches));
+        int changed = 0;
+        HY_CUDA(cudaMemcpyAsync(&changed, m->d_f.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        HY_CUDA(cudaStreamSynchronize(m->stream));
+        cur ^= 1;
+        ++passes;
+        if (!changed) break;
+        if (passes > n1 + 1) { set_error("mono initialisation matcher did not converge"); return HYORB_EUNSUPPORTED; }   // cannot happen: pass k fixes feature k
+    }
+    HY_TRY(launch_mono_finish(buf + (size_t)cur * 2 * n1, n1, m->d_kp1.as<hyorb_keypoint>(), m->d_a.as<hyorb_keypoint>(), n2, m->d_rowtab.as<int32_t>(),
+                              m->d_g.as<int32_t>(), m->d_l.as<float>(), m->d_f.as<int>() + 1, m->d_status.as<int>(), m->stream, &m->launches));
+    HY_CUDA(cudaMemcpyAsync(matches12, m->d_g.p, sizeof(int32_t) * (size_t)n1, cudaMemcpyDeviceToHost, m->stream));
+    HY_CUDA(cudaMemcpyAsync(prev_xy, m->d_l.p, sizeof(float) * 2 * (size_t)n1, cudaMemcpyDeviceToHost, m->stream));
+    int nm = 0;
+    HY_CUDA(cudaMemcpyAsync(&nm, m->d_f.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    HY_TRY(m_sync(m));
+    if (n_matches) *n_matches = nm;
+    return HYORB_OK;
+}
+
 HYORB_API int hyorb_rotation_consistency_host(hyorb_matcher *m, const float *angle_prev, const float *angle_curr, int n, uint8_t *keep)
 {
     HY_TRY(m_prepare(m));

@@ -151,13 +151,23 @@ int launch_match_csr(const uint8_t *q, int nq, const uint8_t *t, int nt, const i
                      cudaStream_t st, long *launches);
 int launch_grid_build(const hyorb_keypoint *kps, int n, hyorb_bounds b, int32_t *cell_off, int32_t *cell_idx, int32_t *cell_of, int32_t *cell_cnt,
                       cudaStream_t st, long *launches);
+// acceptance rule of the window scan + the optional ProjectionViewCriterion (reproj_thr < 0: off)
+struct WindowCriteria { int rule = HYORB_RULE_LANDMARK; float reproj_thr = -1.0f, sigma_ref = 1.0f, size_ref = 31.0f; };
 int launch_match_window(const hyorb_keypoint *kps, const uint8_t *tdesc, const float *t_uR, const uint8_t *t_matched, int nt, hyorb_bounds b,
                         const int32_t *cell_off, const int32_t *cell_idx, const hyorb_window_query *q, const uint8_t *qdesc, int nq,
                         float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, cudaStream_t st, long *launches,
-                        const uint8_t *q_active = nullptr);
+                        const uint8_t *q_active = nullptr, WindowCriteria wc = WindowCriteria());
+int launch_project_sim3(const float *R_a, const float *t_a, const float *sR_ba, const float *t_ba, const hyorb_projection &prb, const hyorb_landmark *lms, int n,
+                        const hyorb_keypoint *kps_b, int nb, float th, float size_ref, hyorb_window_query *queries, uint8_t *passed, int *status,
+                        cudaStream_t st, long *launches);
+int launch_mono_pass(const uint8_t *d1, int n1, const hyorb_keypoint *k2, const uint8_t *d2, int n2, hyorb_bounds b, const int32_t *cell_off, const int32_t *cell_idx,
+                     const float *prev_xy, float r, float thr, float ratio, const int32_t *claim2, const int32_t *claimd, int32_t *head, int32_t *next,
+                     int32_t *out2, int32_t *outd, int *changed, cudaStream_t st, long *launches);
+int launch_mono_finish(const int32_t *claim2, int n1, const hyorb_keypoint *k1, const hyorb_keypoint *k2, int n2, int32_t *owner, int32_t *matches12,
+                       float *prev_xy, int *n_matches, int *status, cudaStream_t st, long *launches);
 int launch_project_landmarks(const hyorb_projection &pr, const hyorb_landmark *lms, int n, const hyorb_keypoint *t_kps, int nt, float th, float size_ref,
                              float frac_smaller, float frac_larger, unsigned flags, hyorb_window_query *queries, uint8_t *passed, int *status, cudaStream_t st,
-                             long *launches);
+                             long *launches, const float *normals = nullptr, float cos_max_angle = 0.0f);
 int launch_projection_rotation(const int32_t *best_idx, uint8_t *accepted, int n, const float *prev_angle, const hyorb_keypoint *t_kps, int nt,
                                int32_t *owner, int *status, cudaStream_t st, long *launches);
 int launch_rotation(const float *a_prev, const float *a_curr, int n, uint8_t *keep, int *status, cudaStream_t st, long *launches);

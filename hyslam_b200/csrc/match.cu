@@ -222,13 +222,14 @@ __global__ void __launch_bounds__(256)
 k_match_window(const hyorb_keypoint *__restrict__ kps, const uint4 *__restrict__ tdesc, const float *__restrict__ t_uR,
                const uint8_t *__restrict__ t_matched, int nt, hyorb_bounds b, const int32_t *__restrict__ cell_off,
                const int32_t *__restrict__ cell_idx, const hyorb_window_query *__restrict__ qs, const uint4 *__restrict__ qdesc, int nq,
-               float thr, float ratio, const uint8_t *__restrict__ q_active, int32_t *best_idx, uint16_t *best, uint16_t *sec, uint8_t *accepted)
+               float thr, float ratio, const uint8_t *__restrict__ q_active, int32_t *best_idx, uint16_t *best, uint16_t *sec, uint8_t *accepted,
+               WindowCriteria wc)
 {
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= nq) return;
     if (q_active && !q_active[qi]) {        // landmark rejected by the landmark criteria: no candidates, no match
-        if (lane == 0) write_result(qi, KEY_NONE, DIST_NONE, -1, HYORB_RULE_LANDMARK, thr, ratio, best_idx, best, sec, accepted);
+        if (lane == 0) write_result(qi, KEY_NONE, DIST_NONE, -1, wc.rule, thr, ratio, best_idx, best, sec, accepted);
         return;
     }
     const hyorb_window_query Q = qs[qi];
@@ -260,6 +261,16 @@ k_match_window(const hyorb_keypoint *__restrict__ kps, const uint4 *__restrict__
                         const float ur = t_uR[k];
                         if (!(fabsf(__fsub_rn(Q.ur, ur)) < Q.ur_radius && ur > 0)) continue;
                     }
+                    if (wc.reproj_thr >= 0.0f) {                                      // ProjectionViewCriterion (MatchCriteria.cpp:282-333, KeyFrame.cc:548-575)
+                        const float ur_view = t_uR ? t_uR[k] : -1.0f;                 // FeatureViews::uR: -1 for monocular views
+                        const float errX = __fsub_rn(Q.u, kp.x), errY = __fsub_rn(Q.v, kp.y);
+                        const float errXr = ur_view >= 0.0f ? __fsub_rn(Q.ur, ur_view) : 0.0f;
+                        const float sserr = __fadd_rn(__fadd_rn(__fmul_rn(errX, errX), __fmul_rn(errY, errY)), __fmul_rn(errXr, errXr));
+                        const float sf = __fdiv_rn(kp.size, wc.size_ref);
+                        const float sigma2 = __fmul_rn(wc.sigma_ref, __fmul_rn(sf, sf));   // FeatureExtractorSettings::determineSigma2
+                        const float stereo_factor = ur_view > 0.0f ? 1.30f : 1.00f;
+                        if (!(__fdiv_rn(sserr, sigma2) < __fmul_rn(stereo_factor, wc.reproj_thr))) continue;
+                    }
                     const int d = hamming256(a0, a1, tdesc[2 * (size_t)k], tdesc[2 * (size_t)k + 1]);
                     const uint32_t pos = (pos0 + (uint32_t)(j - lo)) & POS_MASK;
                     const uint32_t key = ((uint32_t)d << POS_BITS) | pos;
@@ -278,7 +289,7 @@ k_match_window(const hyorb_keypoint *__restrict__ kps, const uint4 *__restrict__
         if (ok < bkey) bestT = ot;
         scan_merge(bkey, second, ok, os);
     }
-    if (lane == 0) write_result(qi, bkey, second, bestT, HYORB_RULE_LANDMARK, thr, ratio, best_idx, best, sec, accepted);
+    if (lane == 0) write_result(qi, bkey, second, bestT, wc.rule, thr, ratio, best_idx, best, sec, accepted);
 }
 
 // ---------------- rotation histogram (single CTA)
@@ -363,11 +374,11 @@ int launch_grid_build(const hyorb_keypoint *kps, int n, hyorb_bounds b, int32_t 
 int launch_match_window(const hyorb_keypoint *kps, const uint8_t *tdesc, const float *t_uR, const uint8_t *t_matched, int nt, hyorb_bounds b,
                         const int32_t *cell_off, const int32_t *cell_idx, const hyorb_window_query *q, const uint8_t *qdesc, int nq,
                         float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, cudaStream_t st, long *launches,
-                        const uint8_t *q_active)
+                        const uint8_t *q_active, WindowCriteria wc)
 {
     if (nq <= 0) return HYORB_OK;
     k_match_window<<<(nq + 7) / 8, 256, 0, st>>>(kps, (const uint4 *)tdesc, t_uR, t_matched, nt, b, cell_off, cell_idx, q, (const uint4 *)qdesc, nq,
-                                                 thr, ratio, q_active, best_idx, best, second, accepted);
+                                                 thr, ratio, q_active, best_idx, best, second, accepted, wc);
     ++*launches;
     HY_CUDA(cudaGetLastError());
     return HYORB_OK;
@@ -403,7 +414,7 @@ __device__ __forceinline__ bool project_point(const hyorb_projection &pr, const 
 __global__ void __launch_bounds__(128)
 k_project_landmarks(hyorb_projection pr, const hyorb_landmark *__restrict__ lms, int n, const hyorb_keypoint *__restrict__ t_kps, int nt,
                     float th, float size_ref, float frac_smaller, float frac_larger, unsigned flags, hyorb_window_query *__restrict__ queries,
-                    uint8_t *__restrict__ passed, int *status)
+                    uint8_t *__restrict__ passed, int *status, const float *__restrict__ normals, float cos_max_angle)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -413,7 +424,16 @@ k_project_landmarks(hyorb_projection pr, const hyorb_landmark *__restrict__ lms,
     const float PO[3] = {__fsub_rn(lm.Pw[0], pr.Ow[0]), __fsub_rn(lm.Pw[1], pr.Ow[1]), __fsub_rn(lm.Pw[2], pr.Ow[2])};
     const double sq = __dadd_rn(__dadd_rn(__dmul_rn((double)PO[0], (double)PO[0]), __dmul_rn((double)PO[1], (double)PO[1])), __dmul_rn((double)PO[2], (double)PO[2]));
     const float dist = (float)__dsqrt_rn(sq);
-    const bool dist_ok = !(flags & HYORB_SBP_DISTANCE) || !(dist < lm.min_dist || dist > lm.max_dist);
+    bool dist_ok = !(flags & HYORB_SBP_DISTANCE) || !(dist < lm.min_dist || dist > lm.max_dist);
+    if (flags & HYORB_SBP_VIEWANGLE) {
+        // ViewingAngleCriterionCore (MatchCriteria.cpp:94-110): PO / d is cv::Mat::convertTo with alpha = 1/d (a float multiply by
+        // (float)(1.0 / d)); Mat::dot accumulates in double; the bound is cosf(max_angle), evaluated by the host's libm
+        const float inv = (float)__ddiv_rn(1.0, (double)dist);
+        double dot = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) dot = __dadd_rn(dot, __dmul_rn((double)__fmul_rn(PO[k], inv), (double)normals[3 * i + k]));
+        dist_ok = dist_ok && (dot > (double)cos_max_angle);
+    }
     float size_px;
     if (lm.assoc_idx >= 0) {
         if (lm.assoc_idx >= nt) { atomicOr(status, ST_BAD_INDEX); size_px = 0.f; }
@@ -497,10 +517,223 @@ int launch_projection_rotation(const int32_t *best_idx, uint8_t *accepted, int n
 
 int launch_project_landmarks(const hyorb_projection &pr, const hyorb_landmark *lms, int n, const hyorb_keypoint *t_kps, int nt, float th, float size_ref,
                              float frac_smaller, float frac_larger, unsigned flags, hyorb_window_query *queries, uint8_t *passed, int *status, cudaStream_t st,
-                             long *launches)
+                             long *launches, const float *normals, float cos_max_angle)
 {
     if (n <= 0) return HYORB_OK;
-    k_project_landmarks<<<(n + 127) / 128, 128, 0, st>>>(pr, lms, n, t_kps, nt, th, size_ref, frac_smaller, frac_larger, flags, queries, passed, status);
+    k_project_landmarks<<<(n + 127) / 128, 128, 0, st>>>(pr, lms, n, t_kps, nt, th, size_ref, frac_smaller, frac_larger, flags, queries, passed, status,
+                                                         normals, cos_max_angle);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+// ---------------- one direction of FeatureMatcher::SearchBySim3 (FeatureMatcher.cc:783-845 / 848-910): landmark of keyframe A -> camera A
+// (R_a * Pw + t_a) -> camera B through the similarity (sR_ba * p + t_ba) -> Camera::Project of B; the 3-D distance in B must lie in the
+// landmark's scale-invariance range; radius = th * B.landMarkSizePixels(lm) / size_ref with B's OWN pose.  No view criteria follow.
+struct Sim3Dev { float R_a[9], t_a[3], sR_ba[9], t_ba[3]; };
+__global__ void __launch_bounds__(128)
+k_project_sim3(Sim3Dev T, hyorb_projection prb, const hyorb_landmark *__restrict__ lms, int n, const hyorb_keypoint *__restrict__ kps_b, int nb, float th,
+               float size_ref, hyorb_window_query *__restrict__ queries, uint8_t *__restrict__ passed, int *status)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const hyorb_landmark lm = lms[i];
+    float pa[3], pb[3], Pch[3], uv[3];
+    gemm31(T.R_a, lm.Pw, T.t_a, pa);
+    gemm31(T.sR_ba, pa, T.t_ba, pb);
+    const float z = pb[2], invz = __fdiv_rn(1.0f, z);
+    Pch[0] = __fdiv_rn(pb[0], z); Pch[1] = __fdiv_rn(pb[1], z); Pch[2] = __fdiv_rn(pb[2], z);
+    gemm31(prb.K, Pch, nullptr, uv);
+    uv[2] = prb.stereo ? __fsub_rn(uv[0], __fmul_rn(prb.mbf, invz)) : -1.0f;
+    const bool valid = z > 0.0f && uv[0] >= prb.bounds.min_x && uv[0] <= prb.bounds.max_x && uv[1] >= prb.bounds.min_y && uv[1] <= prb.bounds.max_y;
+    const double sq = __dadd_rn(__dadd_rn(__dmul_rn((double)pb[0], (double)pb[0]), __dmul_rn((double)pb[1], (double)pb[1])), __dmul_rn((double)pb[2], (double)pb[2]));
+    const float dist = (float)__dsqrt_rn(sq);
+    const bool dist_ok = !(dist < lm.min_dist || dist > lm.max_dist);
+    float size_px;
+    if (lm.assoc_idx >= 0) {
+        if (lm.assoc_idx >= nb) { atomicOr(status, ST_BAD_INDEX); size_px = 0.f; }
+        else size_px = kps_b[lm.assoc_idx].size;
+    } else {
+        const float half = __fdiv_rn(lm.size, 2.0f);
+        const float L[3] = {__fsub_rn(lm.Pw[0], half), lm.Pw[1], lm.Pw[2]}, R[3] = {__fadd_rn(lm.Pw[0], half), lm.Pw[1], lm.Pw[2]};
+        float ul[3], ur[3];
+        project_point(prb, L, ul); project_point(prb, R, ur);
+        size_px = __fsub_rn(ur[0], ul[0]);
+    }
+    hyorb_window_query q;
+    q.u = uv[0]; q.v = uv[1]; q.r = __fdiv_rn(__fmul_rn(th, size_px), size_ref);
+    q.size_lo = -FLT_MAX; q.size_hi = FLT_MAX; q.ur = uv[2]; q.ur_radius = -1.0f;
+    queries[i] = q;
+    passed[i] = (uint8_t)(valid && dist_ok);
+}
+
+int launch_project_sim3(const float *R_a, const float *t_a, const float *sR_ba, const float *t_ba, const hyorb_projection &prb, const hyorb_landmark *lms, int n,
+                        const hyorb_keypoint *kps_b, int nb, float th, float size_ref, hyorb_window_query *queries, uint8_t *passed, int *status,
+                        cudaStream_t st, long *launches)
+{
+    if (n <= 0) return HYORB_OK;
+    Sim3Dev T;
+    for (int i = 0; i < 9; i++) { T.R_a[i] = R_a[i]; T.sR_ba[i] = sR_ba[i]; }
+    for (int i = 0; i < 3; i++) { T.t_a[i] = t_a[i]; T.t_ba[i] = t_ba[i]; }
+    k_project_sim3<<<(n + 127) / 128, 128, 0, st>>>(T, prb, lms, n, kps_b, nb, th, size_ref, queries, passed, status);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
+// ---------------- FeatureMatcher::SearchForInitialization (FeatureMatcher.cc:404-462) with MonoInitScoreExceedsPrevious + MonoInitBestScore
+// (MatchCriteria.cpp:486-549).  The reference walks the frame-1 features in order; feature i1 may only consider a frame-2 feature i2 that an
+// earlier i1' matched if its own distance is smaller than that match's.  The decision of i1 is therefore a function of the decisions of all
+// i1' < i1 -- a triangular system with exactly one solution.  It is solved by fixed-point iteration: every pass recomputes ALL decisions in
+// parallel from the previous pass's claims (per i2: the smallest distance claimed by an EARLIER feature); after pass k the first k features are
+// final, and in practice the dependency chains are a handful long.  The host stops at the first pass that changes nothing.
+//   claim2[i1] / claimd[i1]: frame-2 feature and distance i1 currently claims (-1: none); head[i2] / next[i1]: per-i2 lists of claimers.
+__global__ void k_mono_lists(const int32_t *__restrict__ claim2, int n1, int32_t *__restrict__ head, int32_t *__restrict__ next)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const int j = claim2[i];
+    next[i] = j >= 0 ? atomicExch(&head[j], i) : -1;
+}
+
+__global__ void __launch_bounds__(256)
+k_mono_pass(const uint4 *__restrict__ d1, int n1, const hyorb_keypoint *__restrict__ k2, const uint4 *__restrict__ d2, hyorb_bounds b,
+            const int32_t *__restrict__ cell_off, const int32_t *__restrict__ cell_idx, const float *__restrict__ prev_xy, float r, float thr, float ratio,
+            const int32_t *__restrict__ claim2, const int32_t *__restrict__ claimd, const int32_t *__restrict__ head, const int32_t *__restrict__ next,
+            int32_t *__restrict__ out2, int32_t *__restrict__ outd, int *__restrict__ changed)
+{
+    const int lane = threadIdx.x & 31;
+    const int i1 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i1 >= n1) return;
+    const float qu = prev_xy[2 * i1], qv = prev_xy[2 * i1 + 1];
+    const uint4 a0 = d1[2 * i1], a1 = d1[2 * i1 + 1];
+    const float invW = __fdiv_rn((float)HYORB_GRID_COLS, __fsub_rn(b.max_x, b.min_x));
+    const float invH = __fdiv_rn((float)HYORB_GRID_ROWS, __fsub_rn(b.max_y, b.min_y));
+    int x0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(qu, b.min_x), r), invW));
+    int x1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(qu, b.min_x), r), invW));
+    int y0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(qv, b.min_y), r), invH));
+    int y1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(qv, b.min_y), r), invH));
+    x0 = max(x0, 0); x1 = min(x1, HYORB_GRID_COLS - 1); y0 = max(y0, 0); y1 = min(y1, HYORB_GRID_ROWS - 1);
+    uint32_t bkey = KEY_NONE; int second = DIST_NONE;
+    int bestT = -1;
+    uint32_t pos0 = 0;
+    if (x0 < HYORB_GRID_COLS && x1 >= 0 && y0 < HYORB_GRID_ROWS && y1 >= 0) {
+        for (int ix = x0; ix <= x1; ix++)
+            for (int iy = y0; iy <= y1; iy++) {
+                const int c = ix * HYORB_GRID_ROWS + iy;
+                const int lo = cell_off[c], hi = cell_off[c + 1];
+                for (int j = lo + lane; j < hi; j += 32) {
+                    const int k = cell_idx[j];
+                    const hyorb_keypoint kp = k2[k];
+                    if (!(fabsf(__fsub_rn(kp.x, qu)) < r && fabsf(__fsub_rn(kp.y, qv)) < r)) continue;
+                    const int d = hamming256(a0, a1, d2[2 * (size_t)k], d2[2 * (size_t)k + 1]);
+                    // MonoInitScoreExceedsPrevious: the smallest distance an EARLIER feature claims on k (claims on one i2 decrease with i1)
+                    int dprev = DIST_NONE;
+                    for (int e = head[k]; e >= 0; e = next[e])
+                        if (e < i1) dprev = min(dprev, claimd[e]);
+                    if (dprev != DIST_NONE && !(d < dprev)) continue;
+                    const uint32_t pos = (pos0 + (uint32_t)(j - lo)) & POS_MASK;
+                    const uint32_t key = ((uint32_t)d << POS_BITS) | pos;
+                    if (key < bkey) bestT = k;
+                    scan_update(bkey, second, d, pos);
+                }
+                pos0 += (uint32_t)(hi - lo);
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t ok = __shfl_xor_sync(0xffffffffu, bkey, o);
+        const int os = __shfl_xor_sync(0xffffffffu, second, o);
+        const int ot = __shfl_xor_sync(0xffffffffu, bestT, o);
+        if (ok < bkey) bestT = ot;
+        scan_merge(bkey, second, ok, os);
+    }
+    if (lane == 0) {
+        const int bd = (int)(bkey >> POS_BITS);
+        const bool has = bd < DIST_NONE;
+        const bool acc = has && accept_rule(HYORB_RULE_MONOINIT, (float)bd, second < DIST_NONE ? (float)second : FLT_MAX, thr, ratio);
+        const int c2 = acc ? bestT : -1, cd = acc ? bd : -1;
+        if (c2 != claim2[i1] || cd != claimd[i1]) *changed = 1;
+        out2[i1] = c2; outd[i1] = cd;
+    }
+}
+
+// owner of every claimed frame-2 feature = the last claimer (matches[idx2] = i1 overwrites), RotationConsistency keyed by idx2
+// (rot = angle(frame 1) - angle(frame 2)), then matches12 / vbPrevMatched (FeatureMatcher.cc:441-458).  Single CTA.
+__global__ void __launch_bounds__(256)
+k_mono_finish(const int32_t *__restrict__ claim2, int n1, const hyorb_keypoint *__restrict__ k1, const hyorb_keypoint *__restrict__ k2, int n2,
+              int32_t *__restrict__ owner, int32_t *__restrict__ matches12, float *__restrict__ prev_xy, int *__restrict__ n_matches, int *status)
+{
+    constexpr int HL = 30;
+    __shared__ int hist[HL];
+    __shared__ int ind[3];
+    __shared__ int s_n;
+    if (threadIdx.x < HL) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_n = 0;
+    for (int j = threadIdx.x; j < n2; j += blockDim.x) owner[j] = -1;
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) matches12[i] = -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n1; i += blockDim.x)
+        if (claim2[i] >= 0) atomicMax(&owner[claim2[i]], i);
+    __syncthreads();
+    const float factor = 1.0f / HL;
+    auto bin_of = [&](int j) {
+        float rot = __fsub_rn(k1[owner[j]].angle, k2[j].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, factor));
+        return bin == HL ? 0 : bin;
+    };
+    for (int j = threadIdx.x; j < n2; j += blockDim.x) {
+        if (owner[j] < 0) continue;
+        const int bin = bin_of(j);
+        if (bin < 0 || bin >= HL) { atomicOr(status, ST_BAD_INDEX); continue; }
+        atomicAdd(&hist[bin], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < HL; i++) {
+            const int s = hist[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+            else if (s > max3) { max3 = s; i3 = i; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3 = -1; }
+        ind[0] = i1; ind[1] = i2; ind[2] = i3;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n2; j += blockDim.x) {
+        if (owner[j] < 0) continue;
+        const int bin = bin_of(j);
+        if (bin == ind[0] || bin == ind[1] || bin == ind[2]) {      // a feature of frame 1 owns at most one feature of frame 2
+            const int i = owner[j];
+            matches12[i] = j;
+            prev_xy[2 * i] = k2[j].x; prev_xy[2 * i + 1] = k2[j].y;
+            atomicAdd(&s_n, 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *n_matches = s_n;
+}
+
+int launch_mono_pass(const uint8_t *d1, int n1, const hyorb_keypoint *k2, const uint8_t *d2, int n2, hyorb_bounds b, const int32_t *cell_off, const int32_t *cell_idx,
+                     const float *prev_xy, float r, float thr, float ratio, const int32_t *claim2, const int32_t *claimd, int32_t *head, int32_t *next,
+                     int32_t *out2, int32_t *outd, int *changed, cudaStream_t st, long *launches)
+{
+    HY_CUDA(cudaMemsetAsync(head, 0xFF, sizeof(int32_t) * (size_t)std::max(n2, 1), st));
+    HY_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), st));
+    k_mono_lists<<<(n1 + 255) / 256, 256, 0, st>>>(claim2, n1, head, next);
+    k_mono_pass<<<(n1 + 7) / 8, 256, 0, st>>>((const uint4 *)d1, n1, k2, (const uint4 *)d2, b, cell_off, cell_idx, prev_xy, r, thr, ratio, claim2, claimd, head, next,
+                                             out2, outd, changed);
+    *launches += 2;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+int launch_mono_finish(const int32_t *claim2, int n1, const hyorb_keypoint *k1, const hyorb_keypoint *k2, int n2, int32_t *owner, int32_t *matches12,
+                       float *prev_xy, int *n_matches, int *status, cudaStream_t st, long *launches)
+{
+    k_mono_finish<<<1, 256, 0, st>>>(claim2, n1, k1, k2, n2, owner, matches12, prev_xy, n_matches, status);
     ++*launches;
     HY_CUDA(cudaGetLastError());
     return HYORB_OK;

@@ -217,6 +217,52 @@ class FeatureMatcher(_Handle):
                                                            int(flags), F.ptr(bi), F.ptr(b), F.ptr(s), F.ptr(acc), F.ptr(passed)))
         return bi, b, s, acc, passed
 
+    def Fuse(self, pr, landmarks, lm_normal, lm_desc, t_kps, t_desc, th=3.0, reprojection_err=5.99, t_uR=None, size_ref=31.0, sigma_ref=1.0,
+             max_angle=1.047, thr=None, ratio=1.0):
+        """FeatureMatcher::Fuse(pKF, landmarks, fuse_matches, th, reprojection_err) (FeatureMatcher.cc:464-521) up to the insertion into
+        fuse_matches, for landmarks the caller has pre-screened like :480-487.  Returns (best_idx, best, second, accepted, passed);
+        ``fuse_matches`` = first accepted landmark per keypoint (std::map::insert)."""
+        lms = np.ascontiguousarray(landmarks, F.LM_DTYPE); lm_desc = np.ascontiguousarray(lm_desc, np.uint8)
+        nrm = np.ascontiguousarray(lm_normal, np.float32).reshape(-1, 3)
+        t_kps = np.ascontiguousarray(t_kps, F.KP_DTYPE); t_desc = np.ascontiguousarray(t_desc, np.uint8)
+        t_uR = None if t_uR is None else np.ascontiguousarray(t_uR, np.float32)
+        thr = float(self.settings.TH_LOW if thr is None else thr)
+        n = len(lms)
+        bi, b, s, acc = self._outs(n)
+        passed = np.zeros(n, np.uint8)
+        cos_max = float(np.cos(np.float32(max_angle), dtype=np.float32))      # the reference evaluates cos(float) = cosf on the host
+        F.check(F.lib().hyorb_fuse_host(self._h, C.byref(pr), F.ptr(lms), F.ptr(nrm), F.ptr(lm_desc), n, F.ptr(t_kps), F.ptr(t_desc), F.ptr(t_uR), len(t_kps),
+                                        float(th), float(size_ref), float(sigma_ref), float(reprojection_err), cos_max, thr, float(ratio),
+                                        F.ptr(bi), F.ptr(b), F.ptr(s), F.ptr(acc), F.ptr(passed)))
+        return bi, b, s, acc, passed
+
+    def SearchBySim3Direction(self, R_a, t_a, sR_ba, t_ba, pr_b, landmarks, lm_desc, kps_b, desc_b, th, size_ref=31.0, thr=None):
+        """One direction of FeatureMatcher::SearchBySim3 (FeatureMatcher.cc:783-845 / 848-910).  Returns (best_idx, best, accepted, passed)."""
+        f = lambda a: np.ascontiguousarray(a, np.float32).reshape(-1)
+        Ra, ta, sR, tb = f(R_a), f(t_a), f(sR_ba), f(t_ba)
+        lms = np.ascontiguousarray(landmarks, F.LM_DTYPE); lm_desc = np.ascontiguousarray(lm_desc, np.uint8)
+        kb = np.ascontiguousarray(kps_b, F.KP_DTYPE); db = np.ascontiguousarray(desc_b, np.uint8)
+        thr = float(self.settings.TH_HIGH if thr is None else thr)
+        n = len(lms)
+        bi = np.full(n, -1, np.int32); b = np.full(n, 65535, np.uint16); acc = np.zeros(n, np.uint8); passed = np.zeros(n, np.uint8)
+        F.check(F.lib().hyorb_search_by_sim3_host(self._h, F.ptr(Ra), F.ptr(ta), F.ptr(sR), F.ptr(tb), C.byref(pr_b), F.ptr(lms), F.ptr(lm_desc), n, F.ptr(kb),
+                                                  F.ptr(db), len(kb), float(th), float(size_ref), thr, F.ptr(bi), F.ptr(b), F.ptr(acc), F.ptr(passed)))
+        return bi, b, acc, passed
+
+    def SearchForInitialization(self, k1, d1, k2, d2, bounds, prev_matched, window=100, thr=None, ratio=None):
+        """FeatureMatcher::SearchForInitialization (FeatureMatcher.cc:404-462).  Returns (n_matches, vnMatches12, updated vbPrevMatched)."""
+        k1 = np.ascontiguousarray(k1, F.KP_DTYPE); k2 = np.ascontiguousarray(k2, F.KP_DTYPE)
+        d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+        pm = np.ascontiguousarray(prev_matched, np.float32).copy()
+        thr = float(self.settings.TH_LOW if thr is None else thr)
+        ratio = float(self.settings.nnratio if ratio is None else ratio)
+        m12 = np.full(len(k1), -1, np.int32)
+        nm = C.c_int32(0)
+        b = F.Bounds(*[float(v) for v in bounds])
+        F.check(F.lib().hyorb_search_for_initialization_host(self._h, F.ptr(k1), F.ptr(d1), len(k1), F.ptr(k2), F.ptr(d2), len(k2), b, F.ptr(pm), int(window),
+                                                             thr, ratio, F.ptr(m12), C.addressof(nm)))
+        return nm.value, m12, pm
+
     def BowTransform(self, vocab, desc, levelsup=4):
         """ORBVocabulary::transform (ORBVocabulary.cpp:31-42) per feature: (word_id, node_id at level L - levelsup, weight).
         ``feature_vector(node_id)`` / ``bow_vector(word_id, weight)`` assemble DBoW2's two containers from them."""

@@ -280,7 +280,8 @@ HYORB_API int hyorb_project_landmarks_host(hyorb_matcher *m, const hyorb_project
  * relocalisation against a keyframe (:180-213) = DISTANCE | ROTATION with ratio 1.0. */
 enum { HYORB_SBP_DISTANCE = 1,   /* DistanceCriterion (MatchCriteria.cpp:46-77) */
        HYORB_SBP_STEREO = 2,     /* StereoConsistencyCriterion(th) (:149-177); only has an effect for a stereo camera */
-       HYORB_SBP_ROTATION = 4 }; /* RotationConsistencyCriterion (:363-401) against lm_prev_angle */
+       HYORB_SBP_ROTATION = 4,   /* RotationConsistencyCriterion (:363-401) against lm_prev_angle */
+       HYORB_SBP_VIEWANGLE = 8 };/* ViewingAngleCriterion (:84-110); hyorb_fuse_host only (needs the landmark normals) */
 
 /* As hyorb_search_by_projection_host with the criteria chosen by `flags`.  HYORB_SBP_ROTATION needs lm_prev_angle[i] = angle of
  * the keypoint landmark i is associated with in the previous frame, and the landmarks listed in the reference's map order
@@ -297,6 +298,42 @@ HYORB_API int hyorb_search_by_projection_host(hyorb_matcher *m, const hyorb_proj
                                               const float *t_uR, const uint8_t *t_matched, int nt, float th, float size_ref,
                                               float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
                                               uint8_t *accepted, uint8_t *passed);
+
+/* FeatureMatcher::Fuse(KeyFrame*, landmarks, fuse_matches, th, reprojection_err) (FeatureMatcher.cc:464-521) up to the insertion into
+ * fuse_matches.  The caller pre-screens the landmarks the way :480-487 does (not null / bad / already in the keyframe / protected) and
+ * lists the survivors in vector order.  On the device: ProjectionCriterion + DistanceCriterion + ViewingAngleCriterion(max_angle)
+ * (MatchCriteria.cpp:13-110; lm_normal = MapPoint::GetNormal(), cos_max_angle = cosf(max_angle) evaluated by the caller's libm, as
+ * the reference's `cos(max_angle)` is), KeyFrame::ProjectLandMark / landMarkSizePixels, GetFeaturesInArea, FeatureSizeCriterion(0.5, 1.5),
+ * ProjectionViewCriterion(reproj_err) (:282-333 over KeyFrame::ReprojectionError, KeyFrame.cc:548-575; sigma_ref / size_ref =
+ * FeatureExtractorSettings of the keyframe's views; t_uR = NULL for monocular views) and BestScoreCriterion(thr = TH_LOW, ratio = 1.0).
+ * accepted[i] != 0 <=> the reference would call fuse_matches.insert({best_idx[i], landmark i}); std::map::insert keeps the FIRST
+ * landmark that reaches a keypoint. */
+HYORB_API int hyorb_fuse_host(hyorb_matcher *m, const hyorb_projection *pr, const hyorb_landmark *lms, const float *lm_normal,
+                              const uint8_t *lm_desc, int n, const hyorb_keypoint *t_kps, const uint8_t *t_desc, const float *t_uR, int nt,
+                              float th, float size_ref, float sigma_ref, float reproj_err, float cos_max_angle, float thr, float ratio,
+                              int32_t *best_idx, uint16_t *best, uint16_t *second, uint8_t *accepted, uint8_t *passed);
+
+/* One direction of FeatureMatcher::SearchBySim3 (FeatureMatcher.cc:739-937; :783-845 is KF1 -> KF2, :848-910 the mirror image): the
+ * landmarks of keyframe A (lms / lm_desc, those that pass :787-793) are carried into camera A with its pose (R_a, t_a), into camera B
+ * with the similarity (sR_ba, t_ba) -- the caller forms sR21 = (1/s12) * R12.t(), t21 = -sR21 * t12 / sR12 = s12 * R12, t12 exactly as
+ * :753-756 does -- projected with B's camera, range-checked against the landmark's distance invariance, and matched against B's
+ * features inside th * B.landMarkSizePixels(lm) / size_ref (pr_b = B's own pose and camera; assoc_idx = B.hasAssociation(lm)) with no
+ * view criteria: accepted[i] <=> best distance <= thr (TH_HIGH), best_idx[i] = vnMatch[i].  The caller runs both directions and keeps
+ * the mutually agreeing pairs (:913-930). */
+HYORB_API int hyorb_search_by_sim3_host(hyorb_matcher *m, const float *R_a, const float *t_a, const float *sR_ba, const float *t_ba,
+                                        const hyorb_projection *pr_b, const hyorb_landmark *lms, const uint8_t *lm_desc, int n,
+                                        const hyorb_keypoint *kps_b, const uint8_t *desc_b, int nb, float th, float size_ref, float thr,
+                                        int32_t *best_idx, uint16_t *best, uint8_t *accepted, uint8_t *passed);
+
+/* FeatureMatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (FeatureMatcher.cc:404-462) with
+ * MonoInitScoreExceedsPrevious and MonoInitBestScore(thr = TH_LOW, ratio = nnratio) (MatchCriteria.cpp:486-549) and the rotation
+ * histogram.  prev_xy (n1 x 2) is vbPrevMatched, updated in place for matched features; matches12[i1] = index in frame 2 or -1;
+ * *n_matches = the reference's return value.  The reference's loop is sequential (a later feature may take a frame-2 feature from an
+ * earlier one only with a smaller distance); the device solves the same triangular system by fixed-point passes (match.cu). */
+HYORB_API int hyorb_search_for_initialization_host(hyorb_matcher *m, const hyorb_keypoint *k1, const uint8_t *d1, int n1,
+                                                   const hyorb_keypoint *k2, const uint8_t *d2, int n2, hyorb_bounds bounds2,
+                                                   float *prev_xy, int window, float thr, float ratio, int32_t *matches12,
+                                                   int32_t *n_matches);
 
 /* RotationConsistency + ComputeThreeMaxima (MatchCriteria.cpp:684-767): keep[i] = 1 if match i (angles of the
  * two matched keypoints, pairs in ascending current-index order) falls in one of the 3 dominant rotation bins. */
