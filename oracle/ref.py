@@ -30,7 +30,7 @@ def build(force=False):
         if os.path.exists(_SO):
             return _SO
         raise RuntimeError("oracle/_ref is not built and the reference tree is absent")
-    deps = [os.path.join(_HERE, f) for f in ("ref_glue.cpp", "Makefile", "cvshim/cvshim.cpp", "cvshim/opencv2/core/core.hpp")]
+    deps = [os.path.join(_HERE, f) for f in ("ref_glue.cpp", "ref_glue_match.cpp", "ref_scene.hpp", "Makefile", "cvshim/cvshim.cpp", "cvshim/opencv2/core/core.hpp")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in deps):
         return _SO
     env = dict(os.environ)
@@ -185,11 +185,18 @@ def settings(nnratio=0.6, th_high=100.0, th_low=50.0, check_ori=True):
 class Scene:
     """MapPoints + Frames / KeyFrames built from flat arrays inside the reference's own classes."""
 
-    def __init__(self, max_mappoints):
+    def __init__(self, max_mappoints, matcher_lib=None, prefix="refm_"):
+        """matcher_lib / prefix: which library's matcher entry points drive this scene -- oracle/_ref's refm_* (the reference's
+        FeatureMatcher, default) or tests/cpp/_build/libmatcher_shim_test.so's shimm_* (the C++ drop-in CudaFeatureMatcher)."""
         L = lib()
         L.refm_scene_create.restype = C.c_void_p
         self.h = C.c_void_p(L.refm_scene_create(int(max_mappoints)))
         self._keep = []
+        self._mlib = matcher_lib or L
+        self._prefix = prefix
+
+    def _m(self, name):
+        return getattr(self._mlib, self._prefix + name)
 
     def close(self):
         if self.h:
@@ -261,43 +268,43 @@ class Scene:
 
     def search_by_projection(self, frame, lm_ids, th, st):
         a = np.ascontiguousarray(lm_ids, np.int32)
-        return lib().refm_search_by_projection(self.h, frame, _p(a), len(a), C.c_float(th), C.byref(st))
+        return self._m("search_by_projection")(self.h, frame, _p(a), len(a), C.c_float(th), C.byref(st))
 
     def search_by_projection_motion(self, cur, last, th, st, mono=False):
-        return lib().refm_search_by_projection_motion(self.h, cur, last, C.c_float(th), int(mono), C.byref(st))
+        return self._m("search_by_projection_motion")(self.h, cur, last, C.c_float(th), int(mono), C.byref(st))
 
     def search_by_projection_reloc(self, cur, kf, found, th, orb_dist, st):
         a = np.ascontiguousarray(found, np.int32)
-        return lib().refm_search_by_projection_reloc(self.h, cur, kf, _p(a), len(a), C.c_float(th), int(orb_dist), C.byref(st))
+        return self._m("search_by_projection_reloc")(self.h, cur, kf, _p(a), len(a), C.c_float(th), int(orb_dist), C.byref(st))
 
     def fuse(self, kf, lm_ids, th, reproj_err, st):
         a = np.ascontiguousarray(lm_ids, np.int32)
         oi = np.empty(len(a) + 1, np.int32); ol = np.empty(len(a) + 1, np.int32)
-        n = lib().refm_fuse(self.h, kf, _p(a), len(a), C.c_float(th), C.c_float(reproj_err), C.byref(st), _p(oi), _p(ol), len(oi))
+        n = self._m("fuse")(self.h, kf, _p(a), len(a), C.c_float(th), C.c_float(reproj_err), C.byref(st), _p(oi), _p(ol), len(oi))
         assert n >= 0
         return oi[:n].copy(), ol[:n].copy()
 
     def search_for_initialization(self, f1, f2, prev_matched, window, st):
         pm = np.ascontiguousarray(prev_matched, np.float32).copy()
         m12 = np.empty(len(pm), np.int32)
-        n = lib().refm_search_for_initialization(self.h, f1, f2, _p(pm), _p(m12), int(window), C.byref(st))
+        n = self._m("search_for_initialization")(self.h, f1, f2, _p(pm), _p(m12), int(window), C.byref(st))
         return n, m12, pm
 
     def search_by_sim3(self, kf1, kf2, matches12, s12, R12, t12, th, st):
         m = np.ascontiguousarray(matches12, np.int32).copy()
         R = np.ascontiguousarray(R12, np.float32); t = np.ascontiguousarray(t12, np.float32)
-        n = lib().refm_search_by_sim3(self.h, kf1, kf2, _p(m), len(m), C.c_float(s12), _p(R), _p(t), C.c_float(th), C.byref(st))
+        n = self._m("search_by_sim3")(self.h, kf1, kf2, _p(m), len(m), C.c_float(s12), _p(R), _p(t), C.c_float(th), C.byref(st))
         return n, m
 
     def search_for_triangulation(self, kf1, kf2, F12, only_stereo, st, cap=20000):
         Fm = np.ascontiguousarray(F12, np.float32)
         a = np.empty(cap, np.int32); b = np.empty(cap, np.int32)
-        n = lib().refm_search_for_triangulation(self.h, kf1, kf2, _p(Fm), int(only_stereo), C.byref(st), _p(a), _p(b), cap)
+        n = self._m("search_for_triangulation")(self.h, kf1, kf2, _p(Fm), int(only_stereo), C.byref(st), _p(a), _p(b), cap)
         assert n >= 0
         return a[:n].copy(), b[:n].copy()
 
     def search_by_bow(self, kf, frame, st, cap=20000):
         a = np.empty(cap, np.int32); b = np.empty(cap, np.int32)
-        n = lib().refm_search_by_bow(self.h, kf, frame, C.byref(st), _p(a), _p(b), cap)
+        n = self._m("search_by_bow")(self.h, kf, frame, C.byref(st), _p(a), _p(b), cap)
         assert n >= 0
         return a[:n].copy(), b[:n].copy()

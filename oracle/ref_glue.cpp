@@ -59,12 +59,14 @@ struct ArenaScope {
     ~ArenaScope() { g_arena.active = false; }
 };
 }  // namespace
-void *operator new(size_t n) { return arena_or_malloc(n); }
-void *operator new[](size_t n) { return arena_or_malloc(n); }
-void operator delete(void *p) noexcept { if (p && !in_arena(p)) std::free(p); }
-void operator delete[](void *p) noexcept { if (p && !in_arena(p)) std::free(p); }
-void operator delete(void *p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
-void operator delete[](void *p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
+// hidden: only this library's own (-Bsymbolic) allocations come here; nothing that links against the library may bind to them
+#define REF_HIDDEN __attribute__((visibility("hidden")))
+REF_HIDDEN void *operator new(size_t n) { return arena_or_malloc(n); }
+REF_HIDDEN void *operator new[](size_t n) { return arena_or_malloc(n); }
+REF_HIDDEN void operator delete(void *p) noexcept { if (p && !in_arena(p)) std::free(p); }
+REF_HIDDEN void operator delete[](void *p) noexcept { if (p && !in_arena(p)) std::free(p); }
+REF_HIDDEN void operator delete(void *p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
+REF_HIDDEN void operator delete[](void *p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
 
 extern "C" {
 

@@ -30,6 +30,18 @@
 #include <set>
 #include <vector>
 
+#include "ref_scene.hpp"
+
+// Which matcher class the entry points below drive, and their symbol prefix: the reference's FeatureMatcher as refm_* (oracle/_ref), or --
+// compiled a second time by tests/cpp/matcher_shim_test.cpp -- the C++ drop-in CudaFeatureMatcher as shimm_* on the SAME scene objects.
+#ifndef REFM_MATCHER
+#define REFM_MATCHER FeatureMatcher
+#endif
+#ifndef REFM_NAME
+#define REFM_NAME(x) refm_##x
+#endif
+
+#ifndef REFM_ENTRY_POINTS_ONLY
 // ---- link stubs for the three symbols the matcher TUs reference from files that cannot be compiled here -------------
 // util/GenUtils.cpp and util/Converter.cc need Eigen / g2o.  GenUtils::Epipole is four lines over the reference's own
 // KeyFrame::ProjectLandMark (GenUtils.cpp:11-18); the two Converter functions only run when a frame carries IMU data
@@ -52,51 +64,9 @@ using namespace HYSLAM;
 extern "C" {
 #define REF_API __attribute__((visibility("default")))
 
-struct refm_keypoint { float x, y, size, angle, response; int32_t octave, class_id; };
-struct refm_frame_desc {
-    int32_t n;
-    const refm_keypoint *kps;
-    const uint8_t *desc;            // n x 32
-    const float *uR, *depth;        // null = monocular views
-    float K[9];                     // row-major 3x3
-    float mbf;
-    int32_t sensor;                 // Camera::sensor: 0 mono, 1 stereo
-    float min_x, max_x, min_y, max_y;
-    float Tcw[16];                  // row-major 4x4
-    float size_ref, sigma_ref;      // FeatureExtractorSettings of the views
-};
-struct refm_settings { float nnratio, th_high, th_low; int32_t check_ori; };
 }
 
-namespace {
-struct Scene {
-    int cap = 0, n_mp = 0;
-    MapPoint *mp = nullptr;         // ONE block: id order == pointer order
-    std::shared_ptr<DescriptorDistance> dist = std::make_shared<ORBDistance>();
-    std::vector<std::unique_ptr<Frame>> frames;
-    std::vector<std::unique_ptr<KeyFrame>> keyframes;       // same index as frames; null when the entry is a plain Frame
-    ~Scene()
-    {
-        keyframes.clear(); frames.clear();
-        for (int i = 0; i < n_mp; i++) mp[i].~MapPoint();
-        std::free(mp);
-    }
-    int id_of(MapPoint *p) const { return p ? (int)(p - mp) : -1; }
-};
-
-FeatureMatcherSettings to_settings(const refm_settings *s)
-{
-    FeatureMatcherSettings m;
-    m.nnratio = s->nnratio; m.TH_HIGH = s->th_high; m.TH_LOW = s->th_low; m.checkOri = s->check_ori != 0;
-    return m;
-}
-cv::Mat mat_from(const float *v, int r, int c)
-{
-    cv::Mat m(r, c, CV_32F);
-    for (int i = 0; i < r; i++) for (int j = 0; j < c; j++) m.at<float>(i, j) = v[i * c + j];
-    return m;
-}
-}  // namespace
+using namespace refm;
 
 extern "C" {
 
@@ -230,42 +200,52 @@ REF_API int refm_project(void *h, int frame, int mp, float *uv_ur, float *size_p
     return ok ? 1 : 0;
 }
 
+}  // extern "C"
+#endif  // REFM_ENTRY_POINTS_ONLY
+
+#ifdef REFM_ENTRY_POINTS_ONLY
+using namespace refm;
+#define REF_API __attribute__((visibility("default")))
+#endif
+
+extern "C" {
+
 // FeatureMatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)   (FeatureMatcher.cc:123-143), lm_ids[i] < 0 = null entry
-REF_API int refm_search_by_projection(void *h, int frame, const int32_t *lm_ids, int n, float th, const refm_settings *st)
+REF_API int REFM_NAME(search_by_projection)(void *h, int frame, const int32_t *lm_ids, int n, float th, const refm_settings *st)
 {
     Scene *s = (Scene *)h;
     std::vector<MapPoint *> lms(n);
     for (int i = 0; i < n; i++) lms[i] = lm_ids[i] >= 0 ? s->mp + lm_ids[i] : nullptr;
-    FeatureMatcher m(to_settings(st));
+    REFM_MATCHER m(to_settings(st));
     return m.SearchByProjection(*s->frames[frame], lms, th);
 }
 
 // FeatureMatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono)   (:145-176)
-REF_API int refm_search_by_projection_motion(void *h, int cur, int last, float th, int mono, const refm_settings *st)
+REF_API int REFM_NAME(search_by_projection_motion)(void *h, int cur, int last, float th, int mono, const refm_settings *st)
 {
     Scene *s = (Scene *)h;
-    FeatureMatcher m(to_settings(st));
+    REFM_MATCHER m(to_settings(st));
     return m.SearchByProjection(*s->frames[cur], *s->frames[last], th, mono != 0);
 }
 
 // FeatureMatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame*, const set<MapPoint*> &sAlreadyFound, th, ORBdist)   (:180-213)
-REF_API int refm_search_by_projection_reloc(void *h, int cur, int kf, const int32_t *found, int n_found, float th, int orb_dist, const refm_settings *st)
+REF_API int REFM_NAME(search_by_projection_reloc)(void *h, int cur, int kf, const int32_t *found, int n_found, float th, int orb_dist, const refm_settings *st)
 {
     Scene *s = (Scene *)h;
     std::set<MapPoint *> already;
     for (int i = 0; i < n_found; i++) already.insert(s->mp + found[i]);
-    FeatureMatcher m(to_settings(st));
+    REFM_MATCHER m(to_settings(st));
     return m.SearchByProjection(*s->frames[cur], s->keyframes[kf].get(), already, th, orb_dist);
 }
 
 // FeatureMatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, map<size_t, MapPoint*> &fuse_matches, th, reprojection_err)   (:464-521)
 // out_idx / out_lm: the (keypoint index, MapPoint id) pairs of fuse_matches in map order
-REF_API int refm_fuse(void *h, int kf, const int32_t *lm_ids, int n, float th, float reproj_err, const refm_settings *st, int32_t *out_idx, int32_t *out_lm, int cap)
+REF_API int REFM_NAME(fuse)(void *h, int kf, const int32_t *lm_ids, int n, float th, float reproj_err, const refm_settings *st, int32_t *out_idx, int32_t *out_lm, int cap)
 {
     Scene *s = (Scene *)h;
     std::vector<MapPoint *> lms(n);
     for (int i = 0; i < n; i++) lms[i] = lm_ids[i] >= 0 ? s->mp + lm_ids[i] : nullptr;
-    FeatureMatcher m(to_settings(st));
+    REFM_MATCHER m(to_settings(st));
     std::map<std::size_t, MapPoint *> fm;
     m.Fuse(s->keyframes[kf].get(), lms, fm, th, reproj_err);
     if ((int)fm.size() > cap) return -2;
@@ -275,7 +255,7 @@ REF_API int refm_fuse(void *h, int kf, const int32_t *lm_ids, int n, float th, f
 }
 
 // FeatureMatcher::SearchForInitialization(Frame &F1, Frame &F2, vector<Point2f> &vbPrevMatched, vector<int> &vnMatches12, windowSize)   (:404-462)
-REF_API int refm_search_for_initialization(void *h, int f1, int f2, float *prev_matched_xy /* n1 x 2, in/out */, int32_t *matches12 /* n1 */, int window,
+REF_API int REFM_NAME(search_for_initialization)(void *h, int f1, int f2, float *prev_matched_xy /* n1 x 2, in/out */, int32_t *matches12 /* n1 */, int window,
                                            const refm_settings *st)
 {
     Scene *s = (Scene *)h;
@@ -283,31 +263,31 @@ REF_API int refm_search_for_initialization(void *h, int f1, int f2, float *prev_
     std::vector<cv::Point2f> prev(n1);
     for (int i = 0; i < n1; i++) prev[i] = cv::Point2f(prev_matched_xy[2 * i], prev_matched_xy[2 * i + 1]);
     std::vector<int> m12;
-    FeatureMatcher m(to_settings(st));
+    REFM_MATCHER m(to_settings(st));
     const int r = m.SearchForInitialization(*s->frames[f1], *s->frames[f2], prev, m12, window);
     for (int i = 0; i < n1; i++) { matches12[i] = m12[i]; prev_matched_xy[2 * i] = prev[i].x; prev_matched_xy[2 * i + 1] = prev[i].y; }
     return r;
 }
 
 // FeatureMatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)   (:739-937); matches12: MapPoint ids (in: already matched, out)
-REF_API int refm_search_by_sim3(void *h, int kf1, int kf2, int32_t *matches12, int n1, float s12, const float *R12, const float *t12, float th,
+REF_API int REFM_NAME(search_by_sim3)(void *h, int kf1, int kf2, int32_t *matches12, int n1, float s12, const float *R12, const float *t12, float th,
                                 const refm_settings *st)
 {
     Scene *s = (Scene *)h;
     std::vector<MapPoint *> m12(n1);
     for (int i = 0; i < n1; i++) m12[i] = matches12[i] >= 0 ? s->mp + matches12[i] : nullptr;
-    FeatureMatcher m(to_settings(st));
+    REFM_MATCHER m(to_settings(st));
     const int r = m.SearchBySim3(s->keyframes[kf1].get(), s->keyframes[kf2].get(), m12, s12, mat_from(R12, 3, 3), mat_from(t12, 3, 1), th);
     for (int i = 0; i < n1; i++) matches12[i] = s->id_of(m12[i]);
     return r;
 }
 
 // FeatureMatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)   (:373-402)
-REF_API int refm_search_for_triangulation(void *h, int kf1, int kf2, const float *F12, int only_stereo, const refm_settings *st, int32_t *out_i1, int32_t *out_i2, int cap)
+REF_API int REFM_NAME(search_for_triangulation)(void *h, int kf1, int kf2, const float *F12, int only_stereo, const refm_settings *st, int32_t *out_i1, int32_t *out_i2, int cap)
 {
     Scene *s = (Scene *)h;
     std::vector<std::pair<size_t, size_t>> pairs;
-    FeatureMatcher m(to_settings(st));
+    REFM_MATCHER m(to_settings(st));
     m.SearchForTriangulation(s->keyframes[kf1].get(), s->keyframes[kf2].get(), mat_from(F12, 3, 3), pairs, only_stereo != 0);
     if ((int)pairs.size() > cap) return -2;
     for (size_t i = 0; i < pairs.size(); i++) { out_i1[i] = (int32_t)pairs[i].first; out_i2[i] = (int32_t)pairs[i].second; }
@@ -315,11 +295,11 @@ REF_API int refm_search_for_triangulation(void *h, int kf1, int kf2, const float
 }
 
 // FeatureMatcher::SearchByBoW(KeyFrame *pKF, Frame &F, map<size_t, MapPoint*> &matches)   (:216-280): (F keypoint index, MapPoint id) pairs
-REF_API int refm_search_by_bow(void *h, int kf, int frame, const refm_settings *st, int32_t *out_idx, int32_t *out_lm, int cap)
+REF_API int REFM_NAME(search_by_bow)(void *h, int kf, int frame, const refm_settings *st, int32_t *out_idx, int32_t *out_lm, int cap)
 {
     Scene *s = (Scene *)h;
     std::map<size_t, MapPoint *> matches;
-    FeatureMatcher m(to_settings(st));
+    REFM_MATCHER m(to_settings(st));
     m.SearchByBoW(s->keyframes[kf].get(), *s->frames[frame], matches);
     if ((int)matches.size() > cap) return -2;
     int k = 0;

@@ -51,3 +51,22 @@ def test_doubles_declare_what_the_reference_declares():
     assert "~FeatureExtractor" not in real and "~FeatureExtractor" not in dbl
     for name in ("GetLevels", "GetScaleFactor", "GetScaleFactors", "GetInverseScaleFactors", "GetScaleSigmaSquares", "GetInverseScaleSigmaSquares"):
         assert f"{name}()" in real and f"{name}()" in dbl
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree absent")
+def test_matcher_shim_links_against_the_reference_classes():
+    """include/hyorb_hyslam_matcher.hpp (CudaFeatureMatcher: FeatureMatcher.h:105-176's public signatures) compiles against the real hySLAM
+    headers and links (-z defs) against the reference's own Frame / KeyFrame / MapPoint objects in oracle/_ref"""
+    from oracle import ref as R
+    R.build()
+    r = _make()
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert os.path.exists(os.path.join(ROOT, "tests", "cpp", "_build", "libmatcher_shim_test.so"))
+    hdr = open(os.path.join(ROOT, "include", "hyorb_hyslam_matcher.hpp")).read()
+    ref = open(os.path.join(REF, "src", "features", "FeatureMatcher.h")).read()
+    for sig in ("int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th = 3)",
+                "int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)",
+                "int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize = 10)"):
+        assert sig.replace(" ", "") in ref.replace(" ", "")          # the reference declares it ...
+    for name in ("SearchByProjection", "SearchByBoW", "SearchForTriangulation", "SearchForInitialization", "Fuse", "SearchBySim3"):
+        assert f"int {name}(" in hdr                                   # ... and the drop-in defines the same entry point
