@@ -80,9 +80,10 @@ struct hyorb_extractor {
     DevBuf d_in, d_raw, d_kps, d_desc, d_counts;   // staging of the _host entry points: d_raw = byte-for-byte mirror of a dense host batch,
                                                    // d_in = level 0 in TMA-compatible layout (repacked on the device when the source is not)
     // TMA: tensor maps of the pyramid levels (FAST tile boxes) live in device memory, level 0's travels as a kernel parameter
-    DevBuf d_tmaps;
-    CUtensorMap h_tmaps[HYORB_MAX_LEVELS];
-    CUtensorMap tm0;
+    DevBuf d_tmaps, d_tmaps_lv, d_lvtab;
+    CUtensorMap h_tmaps[HYORB_MAX_LEVELS], h_tmaps_lv[HYORB_MAX_LEVELS];
+    CUtensorMap tm0, tmL0;    // level 0 with the FAST box / with the fused-level box (level.cu)
+    int fused_levels = 1;     // 1: level.cu (pyramid + blur in one pass per level); 0: pyramid.cu + blur.cu (HYORB_FUSED_LEVELS)
     struct { const void *base; int pitch; unsigned long long stride; int B, w, h; } tm0_key = {nullptr, 0, 0, 0, 0, 0};
     int sm_count = 0;
     DevBuf d_rowtab, d_bestd, d_uR, d_depth;    // stereo stage of the ProcessStereoImage entry points
@@ -106,12 +107,14 @@ static int ex_ensure_plan(hyorb_extractor *h, int w, int hgt)
     HY_TRY(h->d_plan.ensure(sizeof(PlanDev)));
     HY_TRY(h->d_resize.ensure(sizeof(ResizeTab) * std::max<size_t>(np.resize.size(), 1)));
     HY_TRY(h->d_lut.ensure(sizeof(uint32_t) * std::max<size_t>(np.lut.size(), 1)));
+    HY_TRY(h->d_lvtab.ensure(sizeof(int) * std::max<size_t>(np.lvtab.size(), 1)));
     // the tables must not be overwritten while earlier launches may still read them
     HY_CUDA(cudaStreamSynchronize(h->stream));
     h->plan = np;
     HY_CUDA(cudaMemcpyAsync(h->d_plan.p, &h->plan.dev, sizeof(PlanDev), cudaMemcpyHostToDevice, h->stream));
     if (!np.resize.empty()) HY_CUDA(cudaMemcpyAsync(h->d_resize.p, h->plan.resize.data(), sizeof(ResizeTab) * np.resize.size(), cudaMemcpyHostToDevice, h->stream));
     HY_CUDA(cudaMemcpyAsync(h->d_lut.p, h->plan.lut.data(), sizeof(uint32_t) * np.lut.size(), cudaMemcpyHostToDevice, h->stream));
+    HY_CUDA(cudaMemcpyAsync(h->d_lvtab.p, h->plan.lvtab.data(), sizeof(int) * np.lvtab.size(), cudaMemcpyHostToDevice, h->stream));
     HY_CUDA(cudaStreamSynchronize(h->stream));
     h->have_plan = true;
     h->Bcap = 0;
@@ -143,6 +146,13 @@ static int ex_ensure_workspace(hyorb_extractor *h, int B)
         HY_TRY(tma_encode_u8_3d(&h->h_tmaps[l], h->d_pyr.as<uint8_t>() + P.lv[l].off, P.lv[l].w, P.lv[l].h, B, (size_t)P.lv[l].pitch,
                                 (size_t)P.pyrStride, FT_BOXW, FT_PH));
     HY_CUDA(cudaMemcpyAsync(h->d_tmaps.p, h->h_tmaps, sizeof(h->h_tmaps), cudaMemcpyHostToDevice, h->stream));
+    // the same levels with the box of the fused pyramid + blur kernel
+    HY_TRY(h->d_tmaps_lv.ensure(sizeof(CUtensorMap) * HYORB_MAX_LEVELS));
+    memset(h->h_tmaps_lv, 0, sizeof(h->h_tmaps_lv));
+    for (int l = 1; l < P.nlevels; l++)
+        HY_TRY(tma_encode_u8_3d(&h->h_tmaps_lv[l], h->d_pyr.as<uint8_t>() + P.lv[l].off, P.lv[l].w, P.lv[l].h, B, (size_t)P.lv[l].pitch,
+                                (size_t)P.pyrStride, LV_BW, LV_BH));
+    HY_CUDA(cudaMemcpyAsync(h->d_tmaps_lv.p, h->h_tmaps_lv, sizeof(h->h_tmaps_lv), cudaMemcpyHostToDevice, h->stream));
     HY_CUDA(cudaStreamSynchronize(h->stream));      // h_tmaps is pageable host memory
     h->Bcap = B;
     return HYORB_OK;
@@ -154,6 +164,7 @@ static int ex_ensure_tm0(hyorb_extractor *h, Level0 l0, int B, int w, int hgt)
     auto &k = h->tm0_key;
     if (k.base == l0.base && k.pitch == l0.pitch && k.stride == l0.stride && k.B == B && k.w == w && k.h == hgt) return HYORB_OK;
     HY_TRY(tma_encode_u8_3d(&h->tm0, l0.base, w, hgt, B, (size_t)l0.pitch, (size_t)l0.stride, FT_BOXW, FT_PH));
+    HY_TRY(tma_encode_u8_3d(&h->tmL0, l0.base, w, hgt, B, (size_t)l0.pitch, (size_t)l0.stride, LV_BW, LV_BH));
     k.base = l0.base; k.pitch = l0.pitch; k.stride = l0.stride; k.B = B; k.w = w; k.h = hgt;
     return HYORB_OK;
 }
@@ -245,16 +256,20 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
                 }
                 HY_CUDA(cudaMemsetAsync(candCount, 0, sizeof(int) * HYORB_MAX_LEVELS * (size_t)Bk, st));
                 HY_TRY(ex_event(h, st, &evs[k]));
-                HY_TRY(launch_pyramid(P, dp, l0k, pyr, h->d_resize.as<ResizeTab>(), Bk, st, &h->launches));
+                if (h->fused_levels)      // pyramid + blur of every level in one pass per level (level.cu)
+                    HY_TRY(launch_levels(P, dp, h->tmL0, h->d_tmaps_lv.as<CUtensorMap>(), i0, l0k, pyr, blur, h->d_resize.as<ResizeTab>(), h->d_lvtab.as<int>(), Bk,
+                                         h->sm_count, st, &h->launches));
+                else
+                    HY_TRY(launch_pyramid(P, dp, l0k, pyr, h->d_resize.as<ResizeTab>(), Bk, st, &h->launches));
                 HY_TRY(ex_event(h, st, &evs[k]));
                 break;
             case 1:
-                if (h->side_blur == 1) {
+                if (h->side_blur == 1 && !h->fused_levels) {
                     HY_CUDA(cudaEventRecord(h->ev_pyr[k], st));
                     HY_CUDA(cudaStreamWaitEvent(h->side[k], h->ev_pyr[k], 0));
                 }
                 HY_TRY(launch_fast(P, dp, h->tm0, h->d_tmaps.as<CUtensorMap>(), i0, cand, candCount, status, Bk, h->sm_count, st, &h->launches));
-                if (h->side_blur == 2) {        // the latency-bound quadtree CTAs are dispatched first, the blur fills the rest of each SM
+                if (h->side_blur == 2 && !h->fused_levels) {        // the latency-bound quadtree CTAs are dispatched first, the blur fills the rest of each SM
                     HY_CUDA(cudaEventRecord(h->ev_pyr[k], st));
                     HY_CUDA(cudaStreamWaitEvent(h->side[k], h->ev_pyr[k], 0));
                 }
@@ -267,12 +282,13 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
                 HY_TRY(ex_event(h, st, &evs[k]));
                 break;
             case 3: {
-                cudaStream_t bs = h->side_blur ? h->side[k] : st;
+                const int side = h->fused_levels ? 0 : h->side_blur;
+                cudaStream_t bs = side ? h->side[k] : st;
                 std::vector<cudaEvent_t> evb;
                 HY_TRY(ex_event(h, bs, &evb));
-                HY_TRY(launch_blur(P, dp, l0k, pyr, blur, Bk, bs, &h->launches));
+                if (!h->fused_levels) HY_TRY(launch_blur(P, dp, l0k, pyr, blur, Bk, bs, &h->launches));
                 HY_TRY(ex_event(h, bs, &evb));
-                if (h->side_blur) {
+                if (side) {
                     HY_CUDA(cudaEventRecord(h->ev_blur[k], bs));
                     HY_CUDA(cudaStreamWaitEvent(st, h->ev_blur[k], 0));
                 }
@@ -408,6 +424,7 @@ HYORB_API int hyorb_extractor_create(const hyorb_extractor_params *params, int d
     if (const char *v = getenv("HYORB_LANES")) h->lanes = atoi(v);
     if (const char *v = getenv("HYORB_HOST_LANES")) h->host_lanes = atoi(v);
     if (const char *v = getenv("HYORB_SIDE_BLUR")) h->side_blur = atoi(v);
+    if (const char *v = getenv("HYORB_FUSED_LEVELS")) h->fused_levels = atoi(v) != 0;
     if (e != cudaSuccess) {
         set_error("CUDA init: %s", cudaGetErrorString(e));
         cudaGetLastError();
@@ -434,7 +451,7 @@ HYORB_API int hyorb_extractor_destroy(hyorb_extractor *h)
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     DevBuf *bufs[] = {&h->d_plan, &h->d_resize, &h->d_lut, &h->d_pyr, &h->d_blur, &h->d_cand, &h->d_qcode, &h->d_qnode, &h->d_qleaf, &h->d_sel,
                       &h->d_candCount, &h->d_selCount, &h->d_status, &h->d_in, &h->d_raw, &h->d_kps, &h->d_desc, &h->d_counts,
-                      &h->d_rowtab, &h->d_bestd, &h->d_uR, &h->d_depth, &h->d_tmaps};
+                      &h->d_rowtab, &h->d_bestd, &h->d_uR, &h->d_depth, &h->d_tmaps, &h->d_tmaps_lv, &h->d_lvtab};
     for (DevBuf *b : bufs) b->release();
     for (auto &set : h->ev_pending) for (cudaEvent_t e : set) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_free) cudaEventDestroy(e);
@@ -769,7 +786,7 @@ static int m_upload(hyorb_matcher *m, DevBuf &buf, const void *src, size_t bytes
 static int bf_splits(int nq, int nt)
 {
     // enough CTAs to fill 148 SMs a few times over, without slicing the target list below one smem tile
-    const int qblocks = (nq + 127) / 128;
+    const int qblocks = (nq + 255) / 256;      // k_bf_partial: 128 threads x 2 queries
     int s = (148 * 8 + qblocks - 1) / qblocks;
     const int maxs = std::max(1, nt / 128);
     return std::max(1, std::min(s, std::min(maxs, 64)));

@@ -49,6 +49,11 @@ constexpr int FT_OW = FT_SW - 8, FT_OH = FT_SH - 2;     // emitted interior: 88 
 constexpr int FT_BOXW = FT_SW + 16;                     // TMA box width in bytes: region + up to 15 bytes of left alignment slack
 constexpr int FT_THREADS = 32 * FT_NSEG * (FT_PH / 32); // 192: one transposition unit (row, segment) and at most one test item per thread
 
+// fused pyramid + blur tiles (level.cu): 128 x 56 interior, halo of 16 columns (TMA boxes start at multiples of 16 bytes) and 3 rows
+constexpr int LV_TW = 128, LV_TH = 56, LV_HX = 16, LV_HY = 3;
+constexpr int LV_BW = LV_TW + 2 * LV_HX, LV_BH = LV_TH + 2 * LV_HY;   // 160 x 62 box
+constexpr int LV_THREADS = 192;                                      // warps 0-3 blur, warps 4-5 resize
+
 constexpr int QT_DMAX = 13;          // quadtree path bits per axis
 constexpr int QT_THREADS = 512;
 constexpr int QT_MAX_ROOTS = 64;
@@ -73,6 +78,8 @@ struct LevelDev {
     float kpSize;             // (float)(int)(PATCH_SIZE*scale)  (:478)
     int qtMaxN;               // power of two >= 4*quota: node arrays of the quadtree kernel
     unsigned mulW, mulH;      // ceil(2^20 / wCell), ceil(2^20 / hCell): exact division of a lattice coordinate (< 4096) by the cell size
+    int lvTilesX, lvTilesY;   // fused pyramid + blur tiles of this level (level.cu)
+    int lvDx, lvDy;           // offsets into the level-tile table: first destination column / row of level l+1 owned by each tile column / row
 };
 
 struct PlanDev {
@@ -117,7 +124,9 @@ struct HostPlan {
     PlanDev dev;
     std::vector<ResizeTab> resize;      // all levels, x tables then y tables
     std::vector<uint32_t> lut;          // quadtree path LUTs
+    std::vector<int> lvtab;             // level.cu: destination ranges per tile column / row
 };
+void level_tiles(HostPlan *plan);
 int scale_tables(const hyorb_extractor_params &p, float *scale, float *inv, float *sigma2, float *inv_sigma2, int *quota);
 int build_plan(const hyorb_extractor_params &p, int width, int height, HostPlan *out);
 void blur_tiles(PlanDev *hp);
@@ -125,6 +134,10 @@ const char *last_error();
 
 // ---- kernel launchers (each returns a HYORB status; all enqueue on `st`) ----
 int launch_pyramid(const PlanDev &hp, const PlanDev *dp, Level0 l0, uint8_t *pyr, const ResizeTab *tabs, int B, cudaStream_t st, long *launches);
+int launch_resize_level(const PlanDev &hp, int l, Level0 l0, uint8_t *pyr, const ResizeTab *tabs, int B, cudaStream_t st, long *launches);
+// fused pyramid + blur: tmL0 / tmaps[l] = tensor maps of level 0 / levels >= 1 with the LV_BW x LV_BH box
+int launch_levels(const PlanDev &hp, const PlanDev *dp, const CUtensorMap &tmL0, const CUtensorMap *tmaps, int img0, Level0 l0, uint8_t *pyr, uint8_t *blur,
+                  const ResizeTab *tabs, const int *lvtab, int B, int sm_count, cudaStream_t st, long *launches);
 // img0 = index of the lane's first image inside the tensors tm0 (level 0) / tmaps[l] (pyramid levels >= 1) describe
 int launch_fast(const PlanDev &hp, const PlanDev *dp, const CUtensorMap &tm0, const CUtensorMap *tmaps, int img0, uint32_t *cand, int *candCount,
                 int *status, int B, int sm_count, cudaStream_t st, long *launches);
@@ -202,6 +215,25 @@ __host__ __device__ inline bool accept_rule(int rule, float best, float second, 
     default: return false;
     }
 }
+
+// ---- 256-bit Hamming distance (ORBDistance::distance, src/features/low_level/DescriptorDistance.cpp:9-25).
+// The plain form is 8 XOR + 8 POPC; POPC issues at 15.3 / clk / SM on B200 (profiles/r2_popc_peak.json), a quarter of the LOP3 rate, so
+// the 8 XOR words are first compressed with carry-save adders (sum = x^y^z and carry = majority are ONE LOP3 each) into four words of
+// weight 1, 2, 4, 8: 4 POPC instead of 8.  Measured on the box: 0.114 -> 0.092 ms per 8000 x 8000 distances.  Exact integer arithmetic.
+#ifdef __CUDACC__
+__device__ __forceinline__ void hy_csa(uint32_t x, uint32_t y, uint32_t z, uint32_t &s, uint32_t &c) { s = x ^ y ^ z; c = (x & y) | (z & (x | y)); }
+__device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1)
+{
+    const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w, x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
+    uint32_t s1, c1, s2, c2, s3, c3, s5, c5;
+    hy_csa(x0, x1, x2, s1, c1); hy_csa(x3, x4, x5, s2, c2); hy_csa(s1, s2, x6, s3, c3);
+    const uint32_t ones = s3 ^ x7, c4 = s3 & x7;
+    hy_csa(c1, c2, c3, s5, c5);
+    const uint32_t twos = s5 ^ c4, c6 = s5 & c4;
+    const uint32_t fours = c5 ^ c6, eights = c5 & c6;
+    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+}
+#endif
 
 // ---- programmatic dependent launch (sm_90+): a kernel that only depends on the launch before it in its stream is queued with
 // programmatic stream serialisation, so its launch latency is hidden behind the predecessor's execution; it waits on

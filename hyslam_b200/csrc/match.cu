@@ -23,12 +23,6 @@ constexpr int POS_BITS = 22;
 constexpr uint32_t POS_MASK = (1u << POS_BITS) - 1;
 constexpr int DIST_NONE = 1023;    // > 256: "no candidate" (the reference's FLT_MAX)
 
-__device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1)
-{
-    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
-           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-}
-
 // running (best key, second distance) update with one more candidate
 __device__ __forceinline__ void scan_update(uint32_t &bkey, int &second, int d, uint32_t pos)
 {
@@ -68,16 +62,23 @@ __device__ __forceinline__ void write_result(int q, uint32_t bkey, int second, i
 // ---------------- brute force: every target in index order (C4: 8000 x 8000)
 constexpr int BF_THREADS = 128, BF_TILE = 128;
 
+// Two queries per thread: a target's two 128-bit shared-memory loads and its position bookkeeping are shared by two distances.
+constexpr int BF_QPT = 2;
 __global__ void __launch_bounds__(BF_THREADS)
 k_bf_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, int chunk,
              uint32_t *__restrict__ pkey, uint16_t *__restrict__ psecond)
 {
     __shared__ uint4 s_t[BF_TILE * 2];
-    const int qi = blockIdx.x * BF_THREADS + threadIdx.x;
+    const int q0 = (blockIdx.x * BF_THREADS + threadIdx.x) * BF_QPT;
     const int t0 = blockIdx.y * chunk, t1 = min(t0 + chunk, nt);
-    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
-    if (qi < nq) { a0 = q[2 * qi]; a1 = q[2 * qi + 1]; }
-    uint32_t bkey = KEY_NONE; int second = DIST_NONE;
+    uint4 a0[BF_QPT], a1[BF_QPT];
+    uint32_t bkey[BF_QPT]; int second[BF_QPT];
+#pragma unroll
+    for (int k = 0; k < BF_QPT; k++) {
+        a0[k] = a1[k] = make_uint4(0, 0, 0, 0);
+        if (q0 + k < nq) { a0[k] = q[2 * (size_t)(q0 + k)]; a1[k] = q[2 * (size_t)(q0 + k) + 1]; }
+        bkey[k] = KEY_NONE; second[k] = DIST_NONE;
+    }
     for (int base = t0; base < t1; base += BF_TILE) {
         const int cnt = min(BF_TILE, t1 - base);
         __syncthreads();
@@ -85,14 +86,17 @@ k_bf_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, i
         __syncthreads();
 #pragma unroll 4
         for (int j = 0; j < cnt; j++) {
-            const int d = hamming256(a0, a1, s_t[2 * j], s_t[2 * j + 1]);
-            scan_update(bkey, second, d, (uint32_t)(base + j));
+            const uint4 b0 = s_t[2 * j], b1 = s_t[2 * j + 1];
+#pragma unroll
+            for (int k = 0; k < BF_QPT; k++) scan_update(bkey[k], second[k], hamming256(a0[k], a1[k], b0, b1), (uint32_t)(base + j));
         }
     }
-    if (qi < nq) {
-        pkey[(size_t)blockIdx.y * nq + qi] = bkey;
-        psecond[(size_t)blockIdx.y * nq + qi] = (uint16_t)second;
-    }
+#pragma unroll
+    for (int k = 0; k < BF_QPT; k++)
+        if (q0 + k < nq) {
+            pkey[(size_t)blockIdx.y * nq + q0 + k] = bkey[k];
+            psecond[(size_t)blockIdx.y * nq + q0 + k] = (uint16_t)second[k];
+        }
 }
 
 __global__ void k_bf_finalize(const uint32_t *__restrict__ pkey, const uint16_t *__restrict__ psecond, int nsplit, int nq,
@@ -341,7 +345,7 @@ int launch_match_bruteforce(const uint8_t *q, int nq, const uint8_t *t, int nt, 
     if (nq <= 0) return HYORB_OK;
     if (nt >= (1 << POS_BITS)) { set_error("more than %d targets", (1 << POS_BITS) - 1); return HYORB_EUNSUPPORTED; }
     const int chunk = nt > 0 ? (nt + nsplit - 1) / nsplit : 1;
-    dim3 grd((nq + BF_THREADS - 1) / BF_THREADS, nsplit);
+    dim3 grd((nq + BF_THREADS * BF_QPT - 1) / (BF_THREADS * BF_QPT), nsplit);
     k_bf_partial<<<grd, BF_THREADS, 0, st>>>((const uint4 *)q, nq, (const uint4 *)t, nt, chunk, pkey, psecond);
     k_bf_finalize<<<(nq + 255) / 256, 256, 0, st>>>(pkey, psecond, nsplit, nq, rule, thr, ratio, best_idx, best, second, accepted);
     *launches += 2;

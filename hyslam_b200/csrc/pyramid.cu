@@ -122,27 +122,32 @@ k_resize(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride
     }
 }
 
+// one level (l >= 1) from level l-1
+int launch_resize_level(const PlanDev &hp, int l, Level0 l0, uint8_t *pyr, const ResizeTab *tabs, int B, cudaStream_t st, long *launches)
+{
+    const LevelDev &S = hp.lv[l - 1], &D = hp.lv[l];
+    const uint8_t *src = (l == 1) ? l0.base : pyr + S.off;
+    const int spitch = (l == 1) ? l0.pitch : S.pitch;
+    const unsigned long long sstride = (l == 1) ? l0.stride : hp.pyrStride;
+    const int nx = (D.w + 3) / 4, ny = (D.h + RS_ROWS - 1) / RS_ROWS;
+    const long long total = (long long)nx * ny * B;
+    if (total > 0x7fffffffLL) { set_error("pyramid level too large for one launch"); return HYORB_EUNSUPPORTED; }
+    // levels 2.. depend only on the launch before them (level 1 follows the caller's copies)
+    const dim3 grd((unsigned)((total + RS_THREADS - 1) / RS_THREADS));
+    if (l > 1)
+        HY_CUDA(launch_dependent(k_resize, grd, dim3(RS_THREADS), 0, st, src, spitch, sstride, S.w, S.h, pyr + D.off, D.pitch, hp.pyrStride, D.w, D.h,
+                                 tabs + D.rsX, tabs + D.rsY, D.area2x, nx, ny, (int)total));
+    else
+        k_resize<<<grd, RS_THREADS, 0, st>>>(src, spitch, sstride, S.w, S.h, pyr + D.off, D.pitch, hp.pyrStride, D.w, D.h, tabs + D.rsX, tabs + D.rsY, D.area2x,
+                                             nx, ny, (int)total);
+    ++*launches;
+    HY_CUDA(cudaGetLastError());
+    return HYORB_OK;
+}
+
 int launch_pyramid(const PlanDev &hp, const PlanDev *, Level0 l0, uint8_t *pyr, const ResizeTab *tabs, int B, cudaStream_t st, long *launches)
 {
-    for (int l = 1; l < hp.nlevels; l++) {
-        const LevelDev &S = hp.lv[l - 1], &D = hp.lv[l];
-        const uint8_t *src = (l == 1) ? l0.base : pyr + S.off;
-        const int spitch = (l == 1) ? l0.pitch : S.pitch;
-        const unsigned long long sstride = (l == 1) ? l0.stride : hp.pyrStride;
-        const int nx = (D.w + 3) / 4, ny = (D.h + RS_ROWS - 1) / RS_ROWS;
-        const long long total = (long long)nx * ny * B;
-        if (total > 0x7fffffffLL) { set_error("pyramid level too large for one launch"); return HYORB_EUNSUPPORTED; }
-        // levels 2.. depend only on the launch before them (level 1 follows the caller's copies)
-        const dim3 grd((unsigned)((total + RS_THREADS - 1) / RS_THREADS));
-        if (l > 1)
-            HY_CUDA(launch_dependent(k_resize, grd, dim3(RS_THREADS), 0, st, src, spitch, sstride, S.w, S.h, pyr + D.off, D.pitch, hp.pyrStride, D.w, D.h,
-                                     tabs + D.rsX, tabs + D.rsY, D.area2x, nx, ny, (int)total));
-        else
-            k_resize<<<grd, RS_THREADS, 0, st>>>(src, spitch, sstride, S.w, S.h, pyr + D.off, D.pitch, hp.pyrStride, D.w, D.h, tabs + D.rsX, tabs + D.rsY, D.area2x,
-                                                 nx, ny, (int)total);
-        ++*launches;
-    }
-    HY_CUDA(cudaGetLastError());
+    for (int l = 1; l < hp.nlevels; l++) HY_TRY(launch_resize_level(hp, l, l0, pyr, tabs, B, st, launches));
     return HYORB_OK;
 }
 

@@ -123,8 +123,7 @@ k_stereo_search(StereoArgs A)
                 const float u = kr[iR].x;
                 if (u >= minU && u <= maxU) {                                  // :105
                     const uint4 b0 = dr[2 * iR], b1 = dr[2 * iR + 1];
-                    const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
-                                  __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+                    const int d = hamming256(a0, a1, b0, b1);
                     if ((float)d < A.sp.th_high) bestKey = min(bestKey, ((uint32_t)d << 16) | (uint32_t)iR);   // :110-114
                 }
             }

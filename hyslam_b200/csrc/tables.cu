@@ -178,6 +178,7 @@ int build_plan(const hyorb_extractor_params &p, int width, int height, HostPlan 
         }
     }
     blur_tiles(&P);
+    level_tiles(out);
     P.tilesPerImage = tileBase;
     P.pyrStride = off;
     P.candStride = candOff;

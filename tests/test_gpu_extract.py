@@ -41,8 +41,10 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("fused", [0, 1])      # pyramid.cu + blur.cu / level.cu (one pass per level produces both)
 @pytest.mark.parametrize("kind,h,w,seed,nf", CASES)
-def test_extract_stages_match_oracle(kind, h, w, seed, nf):
+def test_extract_stages_match_oracle(kind, h, w, seed, nf, fused, monkeypatch):
+    monkeypatch.setenv("HYORB_FUSED_LEVELS", str(fused))
     img = (synth.noise_image if kind == "noise" else synth.blocks_image)(h, w, seed)
     s = _settings(nf)
     ok, od, info = O.extract(img, _oparams(s), debug=True)

@@ -4,7 +4,7 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/../hyslam_b200/csrc"
 mkdir -p ../build_$name ../lib
-for f in tables tma preprocess pyramid fast quadtree blur describe match stereo api; do
+for f in tables tma preprocess pyramid level fast quadtree blur describe match stereo api; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --fmad=false -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off "$@" -c $f.cu -o ../build_$name/$f.o &
 done
 wait
