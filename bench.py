@@ -45,25 +45,157 @@ def workload_name(pairs):
     return f"C2: {W}x{H} stereo pairs, {NFEAT} features/image, 8 levels, scale 1.2, extract L+R + ComputeStereoMatches; {pairs} pairs per step"
 
 
-def make_pairs(n_pairs, seed0=1000, distinct=8):
+def make_pairs(n_pairs, seed0=1000, distinct=8, first=0):
     """[2*n_pairs, H, W] uint8, (left, right) interleaved.  `distinct` pairs come from the seeded generators
     (hyslam_b200/synth.py, G-noise); the rest are horizontal rolls of them (distinct addresses and content
     positions, same statistics) to keep host-side generation short."""
     from hyslam_b200 import synth
-    base = [synth.stereo_pair(H, W, seed0 + i) for i in range(min(distinct, n_pairs))]
+    base = [synth.stereo_pair(H, W, seed0 + i) for i in range(distinct if first else min(distinct, n_pairs))]
     out = np.empty((2 * n_pairs, H, W), np.uint8)
-    for p in range(n_pairs):
+    for q in range(n_pairs):
+        p = first + q              # `first`: pairs [first, first + n_pairs) of the same endless sequence
         L, R = base[p % len(base)]
         s = 37 * (p // len(base))
-        out[2 * p] = np.roll(L, s, axis=1)
-        out[2 * p + 1] = np.roll(R, s, axis=1)
+        out[2 * q] = np.roll(L, s, axis=1)
+        out[2 * q + 1] = np.roll(R, s, axis=1)
     return out
 
 
-def level_bytes():
-    """sum of pyramid level pixels for one WxH image (ORBExtractor.cpp:569)"""
-    from oracle import oracle as O      # cpu-side constant tables only (bench.py may use oracle/ as the checker/baseline)
-    return [w * h for (w, h) in O.level_sizes(O.default_params(NFEAT), W, H)]
+def level_bytes(ex):
+    """pyramid level pixels of one WxH image as the library lays them out (ORBExtractor.cpp:569)"""
+    out = []
+    for l in range(ex.GetLevels()):
+        lw, lh = ex.level_size(W, H, l)
+        out.append(lw * lh)
+    return out
+
+
+def bind_near_gpu(local):
+    """Pin this rank's host threads (and therefore the first-touch placement of its pinned staging buffers) to the NUMA node
+    of its GPU: with 8 ranks on one box every rank otherwise pulls its uploads from whichever socket the allocator picked."""
+    info = {"numa_node": None, "cpus": len(os.sched_getaffinity(0))}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info = {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return info
+
+
+def other_configs(hb, F, torch, dev, local, stream, P):
+    """Line items for the BASELINE.json configs that are not the headline (rank 0 only, a few steps each):
+    C1 / C3 through the host-buffer batch call, and the C2 step on SPARSE-corner frames (G-blocks, about 1 % FAST corners --
+    a camera-like density; the headline's G-noise frames have 24 %), device-resident, with its serialised stage times."""
+    from hyslam_b200 import synth
+    out = {}
+    for name, (h, w), nf, nb in (("C1", (480, 752), 1000, 64), ("C3", (2160, 3840), 8000, 8)):
+        try:
+            imgs = np.stack([synth.noise_image(h, w, i) for i in range(4)] * (nb // 4))
+            pin = torch.from_numpy(imgs).pin_memory().numpy()
+            ex = hb.ORBExtractor(hb.FeatureExtractorSettings(nFeatures=nf), device=local)
+            capn = ex.keypoint_bound(w, h) + 64
+            ex.extract_batch(pin, capacity=capn)
+            t0 = time.perf_counter(); reps = 5
+            for _ in range(reps):
+                _, _, counts = ex.extract_batch(pin, capacity=capn)
+            dt = (time.perf_counter() - t0) / reps
+            one = pin[0]
+            ex(one, None, capacity=capn)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                ex(one, None, capacity=capn)
+            d1 = (time.perf_counter() - t0) / 20
+            out[name] = {"workload": f"{w}x{h} mono, {nf} features, 8 levels, scale 1.2; hyorb_extract_batch_host, {nb} frames per call, copies included",
+                         "frames_per_s": nb / dt, "keypoints_per_frame": float(counts.mean()), "single_frame_call_ms": 1e3 * d1}
+            ex.close()
+        except Exception as e:
+            out[name] = {"error": str(e)[:200]}
+    try:
+        B = 2 * P
+        base = [synth.stereo_pair(H, W, 7000 + i, kind="blocks") for i in range(8)]
+        WP = (W + 15) & ~15
+        t = torch.zeros((B, H, WP), dtype=torch.uint8, device=dev)
+        host = np.empty((B, H, W), np.uint8)
+        for p_ in range(P):
+            L, R = base[p_ % 8]
+            host[2 * p_] = np.roll(L, 37 * (p_ // 8), axis=1); host[2 * p_ + 1] = np.roll(R, 37 * (p_ // 8), axis=1)
+        t[:, :, :W] = torch.from_numpy(host).to(dev)
+        cap = 2560
+        ex = hb.ORBExtractor(hb.FeatureExtractorSettings(nFeatures=NFEAT), device=local, stream=stream.cuda_stream)
+        sp = ex.stereo_params(hb.StereoCamera(**CAM))
+        d_kps = torch.empty((B, cap, 7), dtype=torch.float32, device=dev); d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
+        d_counts = torch.zeros(B, dtype=torch.int32, device=dev)
+        d_uR = torch.empty((P, cap), dtype=torch.float32, device=dev); d_depth = torch.empty((P, cap), dtype=torch.float32, device=dev)
+        step = lambda: ex.process_stereo_batch_device(sp, t.data_ptr(), P, W, H, WP, WP * H, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                                      d_counts.data_ptr(), d_uR.data_ptr(), d_depth.data_ptr())
+        for _ in range(3):
+            step()
+        ex.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(10):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        ex.set_pipelining(device_lanes=1, side_blur=0)
+        step(); ex.sync()
+        ex.set_profiling(True); ex.stage_times(reset=True)
+        for _ in range(5):
+            step()
+        st_ms, calls = ex.stage_times(reset=True)
+        out["C2_sparse_corners"] = {"workload": f"the C2 step on G-blocks frames (flat canvas + rectangles + +-2 noise), {P} pairs per step, device-resident",
+                                    "frames_per_s": P / (ms * 1e-3), "ms_per_step": ms, "keypoints_per_frame": float(d_counts.sum().item()) / P,
+                                    "stage_ms_per_step": {k: v / max(calls, 1) for k, v in st_ms.items()}}
+        ex.close()
+    except Exception as e:
+        out["C2_sparse_corners"] = {"error": str(e)[:200]}
+    return out
+
+
+def output_digest(ex, cam, cap, rank, world, dist, n_pairs=256, chunk=64):
+    """SHA-256 over the outputs of a FIXED set of `n_pairs` stereo pairs (the same frames whatever the number of ranks): rank r
+    processes its contiguous share through the host-buffer ABI call, every pair is hashed on its own (counts, keypoints,
+    descriptors, uR, depth -- only the entries that exist), rank 0 hashes the per-pair digests in frame order.  Equal digests
+    at N = 1, 2, 4, 8 mean frame k produced the same bytes on every partition."""
+    import hashlib
+    lo, hi = n_pairs * rank // world, n_pairs * (rank + 1) // world
+    mine = []
+    for a in range(lo, hi, chunk):
+        b = min(a + chunk, hi)
+        imgs = make_pairs(b - a, seed0=5000, distinct=8, first=a)
+        k, d, c, uR, dep = ex.process_stereo_batch(imgs, cam, capacity=cap)
+        for p in range(b - a):
+            nl, nr = int(c[2 * p]), int(c[2 * p + 1])
+            hsh = hashlib.sha256()
+            hsh.update(np.int32([nl, nr]).tobytes())
+            hsh.update(np.ascontiguousarray(k[2 * p][:nl]).tobytes()); hsh.update(np.ascontiguousarray(k[2 * p + 1][:nr]).tobytes())
+            hsh.update(np.ascontiguousarray(d[2 * p][:nl]).tobytes()); hsh.update(np.ascontiguousarray(d[2 * p + 1][:nr]).tobytes())
+            hsh.update(np.ascontiguousarray(uR[p][:nl]).tobytes()); hsh.update(np.ascontiguousarray(dep[p][:nl]).tobytes())
+            mine.append(hsh.digest())
+    parts = [mine]
+    if dist is not None:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    if rank != 0:
+        return None
+    top = hashlib.sha256()
+    for part in parts:
+        for dg in part:
+            top.update(dg)
+    return {"sha256": top.hexdigest(), "pairs": n_pairs, "frames": "make_pairs(256, seed0=5000): identical frames for every N, sharded contiguously by rank"}
 
 
 class ClockSampler:
@@ -314,6 +446,8 @@ def main():
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (libhyorb has no CPU fallback)")
     torch.cuda.set_device(local)
+    full_affinity = os.sched_getaffinity(0)
+    affinity = bind_near_gpu(local)          # before any pinned allocation
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -389,6 +523,21 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_max = float(tmax.item())
     value = world * P * args.steps / (ms_max / 1e3)
+
+    # ---- the same measurement over a timed region of at least ~0.6 s (K steps of 3 ms are a 60 ms window)
+    sus_steps = max(args.steps, int(0.6 / max(ms_max / args.steps / 1e3, 1e-6)) + 1)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for i in range(sus_steps):
+        step_device(i)
+    s1.record(stream)
+    barrier()
+    ex.sync()
+    tsus = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tsus, op=dist.ReduceOp.MAX)
+    sustained = {"steps": sus_steps, "seconds": float(tsus.item()) / 1e3, "value": world * P * sus_steps / (float(tsus.item()) / 1e3), "unit": UNIT}
 
     # ---- per-kernel durations for the roofline: the same steps once more with the kernels serialised (one lane, no side
     # stream), CUDA events on the launching stream around every stage; under the default pipelining kernels of different
@@ -469,7 +618,17 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     e2e_single = world * P * e2e_steps / float(tm[0].item())
     e2e_value = world * P * n_workers * e2e_steps / float(tm[1].item())
-    d2h = sum(o.nbytes for o in outs)
+    # bytes the call moves per step: the images up; per image min(capacity, the extractor's keypoint bound) entries down (2-D copies)
+    rows = min(cap, ex.keypoint_bound(W, H))
+    d2h = B * 4 + B * rows * (F.KP_DTYPE.itemsize + 32) + 2 * P * rows * 4
+    # what each rank's PCIe link carried during its own end-to-end leg
+    link = torch.tensor([in_bytes * n_workers * e2e_steps / dt2 / 1e9, d2h * n_workers * e2e_steps / dt2 / 1e9], dtype=torch.float64, device=dev)
+    links = [link]
+    if dist is not None:
+        links = [torch.zeros_like(link) for _ in range(world)]
+        dist.all_gather(links, link)
+    per_rank_gbs = [{"h2d": round(float(l[0]), 2), "d2h": round(float(l[1]), 2)} for l in links]
+    digest = output_digest(ex, cam, cap, rank, world, dist)
 
     if rank != 0:
         if dist is not None:
@@ -503,8 +662,18 @@ def main():
         mms = m0.elapsed_time(m1) / reps
         c4 = {"workload": "C4: 8000 x 8000 descriptors, brute force, best/second-best + ratio test", "ms_per_pair_of_keyframes": mms,
               "distance_evals_per_s": nq * nt / (mms * 1e-3), "popc32_per_s": 8 * nq * nt / (mms * 1e-3), "accepted": int(oacc.sum().item())}
+        try:      # the POPC32 issue rate measured on a B200 of this pool by tools/popc_bench.cu (profiles/r2_popc_peak.json)
+            pk = json.load(open(os.path.join(ROOT, "profiles", "r2_popc_peak.json")))
+            c4["popc32_peak_measured_per_s"] = pk["popc_plus_iadd"]["popc_per_s"]
+            c4["frac_of_popc_peak_plain_form"] = c4["popc32_per_s"] / pk["popc_plus_iadd"]["popc_per_s"]
+            c4["note"] = ("popc32_per_s counts the plain form's 8 POPC32 per 256-bit distance; the kernel issues 4 (carry-save compression of the 8 XOR words, "
+                          "hamming256() in common.cuh), so the plain-form fraction may exceed what the POPC pipe alone could do")
+        except Exception:
+            pass
     except Exception as e:                      # never let the auxiliary item break the headline line
         c4 = {"error": str(e)[:200]}
+
+    others = other_configs(hb, F, torch, dev, local, stream, P)
 
     # ---- roofline of the dominant kernel
     peaks = {}
@@ -514,7 +683,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    lv = level_bytes()
+    lv = level_bytes(ex)
     sumP = sum(lv)
     alg = {   # algorithmic bytes per image
         "pyramid": sum(lv[:-1]) + sum(lv[1:]),
@@ -550,6 +719,7 @@ def main():
     # ---- CPU baseline: the reference's own code on all host threads, bounded sample (kind "reference"; "port" without _ref)
     cpu = None
     if not args.no_cpu:
+        os.sched_setaffinity(0, full_affinity)        # the GPU legs ran on the GPU's NUMA node; the CPU arm gets every host thread
         cores = len(os.sched_getaffinity(0))
         sample_pairs = max(1, min(P, cores))
         cpu = cpu_baseline_block(host_batches[0][: 2 * sample_pairs], cores, args.cpu_seconds)
@@ -558,14 +728,15 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": workload_name(P), "pairs_per_step_per_gpu": P, "partition": "frames sharded by rank, no collective on the data path",
+        "config": {"workload": workload_name(P), "frame": "one stereo pair = 2 images (images/s = 2 x value)", "pairs_per_step_per_gpu": P, "partition": "frames sharded by rank, no collective on the data path",
                    "l2": f"{args.rotate} distinct device-resident input batches cycled ({args.rotate * in_bytes / 1e6:.0f} MB of inputs > 126 MB L2); "
                          f"per-step intermediates ({B} pyramids + blurred copies) also exceed L2"},
         "kpts_per_sec": value * kp_per_step / P, "keypoints_per_frame": kp_per_step / P, "stereo_matches_per_frame": matched / P,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h, "steps": n_workers * e2e_steps,
                 "api": f"hyorb_process_stereo_batch_host (pinned host buffers in and out), {n_workers} host threads with one extractor handle each",
-                "single_handle_value": e2e_single},
-        "gpu_launches": int(launches), "roofline": roofline, "stages": stages, "c4_match": c4, "cpu_baseline": cpu, "clocks": clocks,
+                "single_handle_value": e2e_single, "per_rank_link_GBps": per_rank_gbs, "host_affinity": affinity},
+        "sustained": sustained, "digest": digest,
+        "gpu_launches": int(launches), "roofline": roofline, "stages": stages, "c4_match": c4, "other_configs": others, "cpu_baseline": cpu, "clocks": clocks,
     }
     print(json.dumps(line))
     if dist is not None:

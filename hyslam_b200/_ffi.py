@@ -62,7 +62,7 @@ class HyorbError(RuntimeError):
 SYMBOLS = [
     "hyorb_extractor_create", "hyorb_extractor_destroy", "hyorb_extractor_get_levels", "hyorb_extractor_get_scales",
     "hyorb_extract_host", "hyorb_extract_batch_host", "hyorb_extract_batch_device", "hyorb_extractor_sync",
-    "hyorb_extractor_level_size", "hyorb_extractor_debug_read", "hyorb_extractor_launch_count",
+    "hyorb_extractor_level_size", "hyorb_extractor_keypoint_bound", "hyorb_extractor_debug_read", "hyorb_extractor_launch_count",
     "hyorb_matcher_create", "hyorb_matcher_destroy", "hyorb_matcher_sync", "hyorb_matcher_launch_count",
     "hyorb_stereo_match_host", "hyorb_stereo_match_batch_device", "hyorb_match_csr_host",
     "hyorb_match_bruteforce_device", "hyorb_grid_build_host", "hyorb_match_window_host",
@@ -130,6 +130,7 @@ def lib():
         L.hyorb_extractor_launch_count.argtypes = [C.c_void_p]
         L.hyorb_extractor_get_scales.argtypes = [C.c_void_p] * 6
         L.hyorb_extractor_level_size.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.hyorb_extractor_keypoint_bound.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.hyorb_matcher_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.hyorb_matcher_destroy.argtypes = [C.c_void_p]
         L.hyorb_matcher_sync.argtypes = [C.c_void_p]

@@ -83,6 +83,8 @@ struct hyorb_extractor {
     DevBuf d_tmaps, d_tmaps_lv, d_lvtab;
     CUtensorMap h_tmaps[HYORB_MAX_LEVELS], h_tmaps_lv[HYORB_MAX_LEVELS];
     CUtensorMap tm0, tmL0;    // level 0 with the FAST box / with the fused-level box (level.cu)
+    int kp_bound = 0;         // sum over levels of (quota + 3): the most keypoints DistributeOctTree returns per image (ORBExtractor.cpp:107-290 stops
+                              // splitting at the first node count >= quota, one split adds at most 3); host downloads are sized by it
     int fused_levels = 1;     // 1: level.cu (pyramid + blur in one pass per level); 0: pyramid.cu + blur.cu (HYORB_FUSED_LEVELS)
     struct { const void *base; int pitch; unsigned long long stride; int B, w, h; } tm0_key = {nullptr, 0, 0, 0, 0, 0};
     int sm_count = 0;
@@ -117,6 +119,11 @@ static int ex_ensure_plan(hyorb_extractor *h, int w, int hgt)
     HY_CUDA(cudaMemcpyAsync(h->d_lvtab.p, h->plan.lvtab.data(), sizeof(int) * np.lvtab.size(), cudaMemcpyHostToDevice, h->stream));
     HY_CUDA(cudaStreamSynchronize(h->stream));
     h->have_plan = true;
+    h->kp_bound = 0;
+    for (int l = 0; l < np.dev.nlevels; l++) {      // the first pass splits every root unconditionally: at most 4 * round(width / height) nodes
+        const int roots = np.dev.lv[l].h > 0 ? np.dev.lv[l].w / np.dev.lv[l].h + 2 : 2;
+        h->kp_bound += std::max(h->quota[l] + 3, 4 * roots);
+    }
     h->Bcap = 0;
     return HYORB_OK;
 }
@@ -319,18 +326,22 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
                     HY_CUDA(cudaEventRecord(e, st));
                     evs[k][6] = e;
                 }
-                if (io && !io->defer_results) {       // download this lane's results
+                if (io && !io->defer_results) {
+                    // download this lane's results: per image only the first `rows` entries of its capacity-sized block (2-D copies), where
+                    // rows = what the quadtree can produce at most for these quotas; ex_fetch_overflow() covers an image that still exceeded it
+                    const size_t rows = (size_t)std::min(capacity, h->kp_bound);
                     HY_CUDA(cudaMemcpyAsync(io->counts + i0, d_counts + i0, sizeof(int32_t) * Bk, cudaMemcpyDeviceToHost, st));
-                    HY_CUDA(cudaMemcpyAsync(io->kps + (size_t)i0 * capacity, d_kps + (size_t)i0 * capacity, sizeof(hyorb_keypoint) * (size_t)capacity * Bk,
-                                            cudaMemcpyDeviceToHost, st));
-                    HY_CUDA(cudaMemcpyAsync(io->desc + (size_t)i0 * capacity * HYORB_DESC_BYTES, d_desc + (size_t)i0 * capacity * HYORB_DESC_BYTES,
-                                            (size_t)HYORB_DESC_BYTES * capacity * Bk, cudaMemcpyDeviceToHost, st));
+                    HY_CUDA(cudaMemcpy2DAsync(io->kps + (size_t)i0 * capacity, sizeof(hyorb_keypoint) * (size_t)capacity, d_kps + (size_t)i0 * capacity,
+                                              sizeof(hyorb_keypoint) * (size_t)capacity, sizeof(hyorb_keypoint) * rows, Bk, cudaMemcpyDeviceToHost, st));
+                    HY_CUDA(cudaMemcpy2DAsync(io->desc + (size_t)i0 * capacity * HYORB_DESC_BYTES, (size_t)HYORB_DESC_BYTES * capacity,
+                                              d_desc + (size_t)i0 * capacity * HYORB_DESC_BYTES, (size_t)HYORB_DESC_BYTES * capacity, (size_t)HYORB_DESC_BYTES * rows, Bk,
+                                              cudaMemcpyDeviceToHost, st));
                     if (sp && io->uR && io->depth) {
                         const int p0 = i0 / 2;
-                        HY_CUDA(cudaMemcpyAsync(io->uR + (size_t)p0 * capacity, d_uR + (size_t)p0 * capacity, sizeof(float) * (size_t)capacity * (Bk / 2),
-                                                cudaMemcpyDeviceToHost, st));
-                        HY_CUDA(cudaMemcpyAsync(io->depth + (size_t)p0 * capacity, d_depth + (size_t)p0 * capacity, sizeof(float) * (size_t)capacity * (Bk / 2),
-                                                cudaMemcpyDeviceToHost, st));
+                        HY_CUDA(cudaMemcpy2DAsync(io->uR + (size_t)p0 * capacity, sizeof(float) * (size_t)capacity, d_uR + (size_t)p0 * capacity,
+                                                  sizeof(float) * (size_t)capacity, sizeof(float) * rows, Bk / 2, cudaMemcpyDeviceToHost, st));
+                        HY_CUDA(cudaMemcpy2DAsync(io->depth + (size_t)p0 * capacity, sizeof(float) * (size_t)capacity, d_depth + (size_t)p0 * capacity,
+                                                  sizeof(float) * (size_t)capacity, sizeof(float) * rows, Bk / 2, cudaMemcpyDeviceToHost, st));
                     }
                 }
                 if (k > 0) {
@@ -366,6 +377,30 @@ static int ex_download_small(hyorb_extractor *h, const HostIO &io, int B, int ca
         }
     }
     HY_CUDA(cudaStreamSynchronize(h->stream));
+    return HYORB_OK;
+}
+
+// large host batches download min(capacity, kp_bound) entries per image while the batch is still running; an image that produced more
+// (quotas the bound does not cover) gets the rest here, after the counts have arrived
+static int ex_fetch_overflow(hyorb_extractor *h, const HostIO &io, int B, int capacity, const hyorb_keypoint *d_kps, const uint8_t *d_desc,
+                             const float *d_uR, const float *d_depth)
+{
+    const int rows = std::min(capacity, h->kp_bound);
+    bool any = false;
+    for (int i = 0; i < B; i++) {
+        const int n = std::min(io.counts[i], capacity);
+        if (n <= rows) continue;
+        any = true;
+        const size_t o = (size_t)i * capacity + rows, m = (size_t)(n - rows);
+        HY_CUDA(cudaMemcpyAsync(io.kps + o, d_kps + o, sizeof(hyorb_keypoint) * m, cudaMemcpyDeviceToHost, h->stream));
+        HY_CUDA(cudaMemcpyAsync(io.desc + o * HYORB_DESC_BYTES, d_desc + o * HYORB_DESC_BYTES, (size_t)HYORB_DESC_BYTES * m, cudaMemcpyDeviceToHost, h->stream));
+        if (d_uR && io.uR && io.depth && (i & 1) == 0) {
+            const size_t q = (size_t)(i / 2) * capacity + rows;
+            HY_CUDA(cudaMemcpyAsync(io.uR + q, d_uR + q, sizeof(float) * m, cudaMemcpyDeviceToHost, h->stream));
+            HY_CUDA(cudaMemcpyAsync(io.depth + q, d_depth + q, sizeof(float) * m, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    if (any) HY_CUDA(cudaStreamSynchronize(h->stream));
     return HYORB_OK;
 }
 
@@ -532,7 +567,8 @@ HYORB_API int hyorb_extract_batch_host(hyorb_extractor *h, const uint8_t *images
                   nullptr, nullptr, nullptr, &io));
     if (io.defer_results)
         return ex_download_small(h, io, n_images, capacity, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), h->d_counts.as<int32_t>(), nullptr, nullptr);
-    return ex_sync(h);
+    HY_TRY(ex_sync(h));
+    return ex_fetch_overflow(h, io, n_images, capacity, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), nullptr, nullptr);
 }
 
 HYORB_API int hyorb_extract_host(hyorb_extractor *h, const uint8_t *gray, int width, int height, int stride, hyorb_keypoint *kps,
@@ -640,7 +676,8 @@ HYORB_API int hyorb_process_stereo_batch_host(hyorb_extractor *h, const hyorb_st
     if (io.defer_results)
         return ex_download_small(h, io, n_images, capacity, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), h->d_counts.as<int32_t>(),
                                  h->d_uR.as<float>(), h->d_depth.as<float>());
-    return ex_sync(h);
+    HY_TRY(ex_sync(h));
+    return ex_fetch_overflow(h, io, n_images, capacity, h->d_kps.as<hyorb_keypoint>(), h->d_desc.as<uint8_t>(), h->d_uR.as<float>(), h->d_depth.as<float>());
 }
 
 HYORB_API int hyorb_extractor_set_profiling(hyorb_extractor *h, int enable)
@@ -663,6 +700,14 @@ HYORB_API int hyorb_extractor_set_pipelining(hyorb_extractor *h, int device_lane
     if (host_lanes > 0) h->host_lanes = host_lanes;
     if (side_blur >= 0) h->side_blur = side_blur;
     return HYORB_OK;
+}
+
+HYORB_API int hyorb_extractor_keypoint_bound(hyorb_extractor *h, int width, int height)
+{
+    if (!h) { set_error("null handle"); return HYORB_EINVAL; }
+    HY_CUDA(cudaSetDevice(h->device));
+    HY_TRY(ex_ensure_plan(h, width, height));
+    return h->kp_bound;
 }
 
 HYORB_API int hyorb_extractor_stage_times(hyorb_extractor *h, double *ms, long *calls, int reset)

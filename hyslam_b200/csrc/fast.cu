@@ -74,6 +74,9 @@ __device__ __forceinline__ uint32_t bit_range(int a, int b)
     return hi & ~lo;
 }
 
+#ifndef HYORB_FT_EXP
+#define HYORB_FT_EXP 0      // timing experiments only (tools/build_variant.sh): 1 = no corners after the test, 2 = no NMS, 3 = no test
+#endif
 #ifndef HYORB_FT_MINB
 #define HYORB_FT_MINB 5      // 64 registers: five 192-thread CTAs per SM (measured faster than 4 x 80 or 3 x 86 registers)
 #endif
@@ -169,8 +172,15 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         const int cl = max(3, DET_MIN - x0), ch = min(FT_SW - 3, xEnd - x0);
         uint32_t valid = bit_range(cl - 32 * a_seg, ch - 32 * a_seg);
         if (sy < DET_MIN || sy >= yEnd) valid = 0;
+#if HYORB_FT_EXP == 3
+        if (valid == 0x12345u) flags = bs_corners<FT_PLP>(s_planes + (a_r + 3) * FT_PLP + (a_seg + 1) * 8) & valid;
+#else
         if (valid) flags = bs_corners<FT_PLP>(s_planes + (a_r + 3) * FT_PLP + (a_seg + 1) * 8) & valid;
+#endif
     }
+#if HYORB_FT_EXP == 1
+    if (flags != 0x12345u) flags = 0;
+#endif
     // ---- B. compact the corner bits into the CTA list: warp scan of the per-lane counts, one shared-memory atomic per warp
     {
         const int lane = tid & 31;
@@ -228,7 +238,11 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     __syncthreads();
 
     // ---- D. cell-local 3x3 NMS over the interior, stage survivors (s_emit aliases the plane buffer)
-    for (int i0 = 0; i0 < ncorner; i0 += FT_THREADS) {      // warp-uniform trip count: the ballot below needs all lanes
+#if HYORB_FT_EXP == 2
+    for (int i0 = 0; i0 < ncorner - 100000; i0 += FT_THREADS) {
+#else
+    for (int i0 = 0; i0 < ncorner; i0 += FT_THREADS) {
+#endif      // warp-uniform trip count: the ballot below needs all lanes
         const int i = i0 + tid;
         // branch-free: the eight neighbour scores are fetched together (independent loads, every address stays inside
         // s_score for an interior pixel) and neighbours that belong to another cell are replaced by 0

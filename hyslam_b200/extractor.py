@@ -168,6 +168,13 @@ class ORBExtractor:
         F.check(F.lib().hyorb_extractor_level_size(self._h, W, H, level, C.byref(w), C.byref(h)))
         return w.value, h.value
 
+    def keypoint_bound(self, W, H):
+        """most keypoints one WxH image can produce with these quotas (= entries per image a large host batch downloads)"""
+        n = F.lib().hyorb_extractor_keypoint_bound(self._h, W, H)
+        if n < 0:
+            F.check(n)
+        return n
+
     def debug_level(self, W, H, level, what=F.DBG_PYRAMID, image_index=0):
         w, h = self.level_size(W, H, level)
         out = np.empty((h, w), np.uint8)

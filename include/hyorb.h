@@ -114,6 +114,12 @@ enum {
     HYORB_DBG_LEVEL_COUNT = 3 /* one int32: keypoints kept on this level after DistributeOctTree */
 };
 HYORB_API int hyorb_extractor_level_size(hyorb_extractor *h, int width, int height, int level, int *lw, int *lh);
+/* Upper bound of the keypoints one width x height image can produce with this handle's quotas: sum over levels of
+ * max(quota + 3, 4 * roots) -- ORBExtractor::DistributeOctTree (ORBExtractor.cpp:107-290) stops at the first node count
+ * >= quota and one split adds at most 3 nodes.  Host-batch downloads copy min(capacity, bound) entries per image while
+ * the batch runs (anything beyond is fetched afterwards), so this is also the D2H size of a large batch.  Returns the
+ * bound (> 0) or a negative status. */
+HYORB_API int hyorb_extractor_keypoint_bound(hyorb_extractor *h, int width, int height);
 /* returns the number of bytes written (>= 0) or a negative status */
 HYORB_API long hyorb_extractor_debug_read(hyorb_extractor *h, int image_index, int what, int level, void *dst,
                                           size_t dst_bytes);
