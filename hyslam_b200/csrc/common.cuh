@@ -49,10 +49,10 @@ constexpr int FT_OW = FT_SW - 8, FT_OH = FT_SH - 2;     // emitted interior: 88 
 constexpr int FT_BOXW = FT_SW + 16;                     // TMA box width in bytes: region + up to 15 bytes of left alignment slack
 constexpr int FT_THREADS = 32 * FT_NSEG * (FT_PH / 32); // 192: one transposition unit (row, segment) and at most one test item per thread
 
-// fused pyramid + blur tiles (level.cu): 128 x 56 interior, halo of 16 columns (TMA boxes start at multiples of 16 bytes) and 3 rows
-constexpr int LV_TW = 128, LV_TH = 56, LV_HX = 16, LV_HY = 3;
-constexpr int LV_BW = LV_TW + 2 * LV_HX, LV_BH = LV_TH + 2 * LV_HY;   // 160 x 62 box
-constexpr int LV_THREADS = 192;                                      // warps 0-3 blur, warps 4-5 resize
+// fused pyramid + blur tiles (level.cu): 128 x 30 interior per WARP, halo of 16 columns (TMA boxes start at multiples of 16 bytes) and 3 rows
+constexpr int LV_TW = 128, LV_TH = 30, LV_HX = 16, LV_HY = 3;
+constexpr int LV_BW = LV_TW + 2 * LV_HX, LV_BH = LV_TH + 2 * LV_HY;   // 160 x 36 box
+constexpr int LV_WARPS = 4, LV_THREADS = 32 * LV_WARPS;              // warps are independent pipelines; 4 share a CTA's shared-memory allocation
 
 constexpr int QT_DMAX = 13;          // quadtree path bits per axis
 constexpr int QT_THREADS = 512;
@@ -80,6 +80,7 @@ struct LevelDev {
     unsigned mulW, mulH;      // ceil(2^20 / wCell), ceil(2^20 / hCell): exact division of a lattice coordinate (< 4096) by the cell size
     int lvTilesX, lvTilesY;   // fused pyramid + blur tiles of this level (level.cu)
     int lvDx, lvDy;           // offsets into the level-tile table: first destination column / row of level l+1 owned by each tile column / row
+    int rsInv, lvFused;       // this level as a DESTINATION of level.cu: resize-table offset of the source-row -> destination-row map; 0 = use k_resize
 };
 
 struct PlanDev {

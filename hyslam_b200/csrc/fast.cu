@@ -299,6 +299,7 @@ int launch_fast(const PlanDev &hp, const PlanDev *dp, const CUtensorMap &tm0, co
     if (!per) {
         HY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_fast, FT_THREADS, 0));
         if (per < 1) per = 1;
+        if (const char *v = getenv("HYORB_FT_CTAS")) { const int want = atoi(v); if (want >= 1 && want < per) per = want; }   // leave room for other lanes' kernels
         ctas_per_sm.store(per, std::memory_order_relaxed);
     }
     const int sms = sm_count > 0 ? sm_count : 148;
