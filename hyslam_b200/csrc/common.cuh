@@ -49,9 +49,13 @@ constexpr int FT_OW = FT_SW - 8, FT_OH = FT_SH - 2;     // emitted interior: 88 
 constexpr int FT_BOXW = FT_SW + 16;                     // TMA box width in bytes: region + up to 15 bytes of left alignment slack
 constexpr int FT_THREADS = 32 * FT_NSEG * (FT_PH / 32); // 192: one transposition unit (row, segment) and at most one test item per thread
 
-// fused pyramid + blur tiles (level.cu): 128 x 30 interior per WARP, halo of 16 columns (TMA boxes start at multiples of 16 bytes) and 3 rows
-constexpr int LV_TW = 128, LV_TH = 30, LV_HX = 16, LV_HY = 3;
-constexpr int LV_BW = LV_TW + 2 * LV_HX, LV_BH = LV_TH + 2 * LV_HY;   // 160 x 36 box
+// fused pyramid + blur tiles (level.cu): 128 x 20 interior per WARP, halo of 16 columns (TMA boxes start at multiples of 16 bytes) and 3 rows
+#ifndef HYORB_LV_TH
+#define HYORB_LV_TH 20
+#endif
+constexpr int LV_TW = 128, LV_TH = HYORB_LV_TH, LV_HX = 16, LV_HY = 3;
+static_assert(LV_TH % 5 == 0, "the blur walks the tile in groups of 5 rows");
+constexpr int LV_BW = LV_TW + 2 * LV_HX, LV_BH = LV_TH + 2 * LV_HY;   // 160 x 26 box
 constexpr int LV_WARPS = 4, LV_THREADS = 32 * LV_WARPS;              // warps are independent pipelines; 4 share a CTA's shared-memory allocation
 
 constexpr int QT_DMAX = 13;          // quadtree path bits per axis

@@ -3,7 +3,7 @@
 // Replaces, per level, `cv::resize(level l, level l+1, INTER_LINEAR)` of ORBExtractor::ComputePyramid (src/features/ORBExtractor.cpp:564-589)
 // and `GaussianBlur(level l clone, 7x7, 2, 2, BORDER_REFLECT_101)` of ORBExtractor::operator() (:536-537).  Arithmetic is the one of
 // pyramid.cu / blur.cu (OpenCV's 8-bit fixed-point kernels) -- only the data movement changes:
-//   * every WARP is its own pipeline: it walks 128 x 30 pixel tiles of the SOURCE level; a tile and its halo (16 columns either side -- TMA
+//   * every WARP is its own pipeline: it walks 128 x 20 pixel tiles of the SOURCE level; a tile and its halo (16 columns either side -- TMA
 //     boxes start at multiples of 16 bytes -- and 3 rows above / below) arrive in the warp's own shared-memory ring as ONE
 //     cp.async.bulk.tensor box per tile, the next boxes in flight while the current one is processed: no thread waits on a global load
 //     (the stand-alone kernels spent half of their stall samples on the long scoreboard) and there is no CTA-wide barrier at all;
@@ -22,10 +22,10 @@
 
 namespace hyorb {
 
-constexpr int LV_BUF = LV_BW * LV_BH;          // one box; a multiple of 128 bytes (TMA destination alignment)
-static_assert(LV_BUF % 128 == 0, "box size");
+constexpr int LV_BOX = LV_BW * LV_BH;                  // bytes of one box
+constexpr int LV_BUF = (LV_BOX + 127) & ~127;          // buffer stride: TMA destinations are 128-byte aligned
 #ifndef HYORB_LV_NBUF
-#define HYORB_LV_NBUF 3
+#define HYORB_LV_NBUF 2
 #endif
 constexpr int LV_NBUF = HYORB_LV_NBUF;         // boxes per warp: one being processed, the others in flight
 constexpr size_t LV_SMEM = (size_t)LV_WARPS * LV_NBUF * LV_BUF + sizeof(uint64_t) * LV_WARPS * LV_NBUF;
@@ -93,9 +93,9 @@ __device__ __forceinline__ void lv_reflect_box(uint8_t *box, int lane, int X0, i
 }
 
 #ifndef HYORB_LV_MINB
-#define HYORB_LV_MINB 3
+#define HYORB_LV_MINB 6
 #endif
-// Every WARP is its own pipeline: it walks 128 x 30 pixel tiles of the source level (tile = global warp index, + number of warps, ...),
+// Every WARP is its own pipeline: it walks 128 x 20 pixel tiles of the source level (tile = global warp index, + number of warps, ...),
 // owns LV_NBUF box buffers and mbarriers, and never meets a CTA-wide barrier.
 __global__ void __launch_bounds__(LV_THREADS, HYORB_LV_MINB)
 k_level(const PlanDev *__restrict__ plan, int l, const __grid_constant__ CUtensorMap tm0, const CUtensorMap *__restrict__ tmaps, int img0,
@@ -113,7 +113,7 @@ k_level(const PlanDev *__restrict__ plan, int l, const __grid_constant__ CUtenso
     auto issue = [&](int T, int buf) {
         const int b = T / perImage, r = T - b * perImage;
         const int ty = r / tilesX, tx = r - ty * tilesX;
-        mbar_arrive_expect_tx(&bars[buf], LV_BUF);
+        mbar_arrive_expect_tx(&bars[buf], LV_BOX);
         tma_load_3d(boxes + buf * LV_BUF, tm, &bars[buf], tx * LV_TW - LV_HX, ty * LV_TH - LV_HY, img0 + b);
     };
     if (lane == 0) {
@@ -184,7 +184,7 @@ k_level(const PlanDev *__restrict__ plan, int l, const __grid_constant__ CUtenso
         }
         if (do_resize) {
             // ---------------- level l+1: destination rows whose first tap row lies in this tile, destination columns likewise ----------------
-            // The warp walks the SOURCE rows Y0 .. Y0+30 once (horizontal pass of each: PRMT + DP2A on the lane's 4 destination columns) and
+            // The warp walks the SOURCE rows Y0 .. Y0+20 once (horizontal pass of each: PRMT + DP2A on the lane's 4 destination columns) and
             // emits a destination row whenever its second tap row has just been computed (tinv: source row -> destination row + weights).
             const LevelDev &D = plan->lv[l + 1];
             const ResizeTab *tabx = tabs + D.rsX;
