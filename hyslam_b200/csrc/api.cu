@@ -13,12 +13,13 @@
 // A batch call drives up to 2 x MAX_LANES streams and throughput users run several handles from several threads.  The
 // driver multiplexes streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue
 // serialise on each other (measured: two host threads x 8 lanes end to end 25-36k pairs/s with 8 queues, 39k with 32).
-// The variable is read when the CUDA context is created, so it is set when the library is loaded -- a value the user chose wins.
-__attribute__((constructor)) static void hyorb_default_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+// The variable is read when the CUDA context is created and belongs to the host process: the library does NOT touch the
+// environment; INTEGRATION.md recommends CUDA_DEVICE_MAX_CONNECTIONS=32 (bench.py and the Python package set it for themselves).
 
 namespace hyorb {
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
+    cudaStream_t home = nullptr; bool has_home = false;     // the owning handle's stream: fresh memory is zeroed on it
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return HYORB_OK;
@@ -28,8 +29,10 @@ struct DevBuf {
         if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) -> %s", bytes, cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? HYORB_ENOMEM : HYORB_ECUDA; }
         // fresh buffers are zeroed once: row padding of the image planes is read (and then multiplied by a zero coefficient or
         // masked) without ever being written, and this keeps those reads initialised
-        // (the handles' streams are non-blocking, i.e. not ordered after the legacy stream this memset runs on: wait for it)
-        if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { cudaGetLastError(); }
+        // -- on the handle's own stream (every use of the buffer is enqueued on it, or on a lane stream that first waits for it), so no
+        // other stream of the host application is stalled; buffers without a home stream fall back to a synchronous memset
+        if (has_home) { if (cudaMemsetAsync(p, 0, bytes, home) != cudaSuccess) cudaGetLastError(); }
+        else if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { cudaGetLastError(); }
         cap = bytes;
         return HYORB_OK;
     }
@@ -47,6 +50,11 @@ static int status_to_rc(int st)
     }
     if (st & (ST_QT_LIMIT | ST_QT_MISMATCH)) { set_error("quadtree kernel limit / consistency check failed (status 0x%x)", st); return HYORB_EUNSUPPORTED; }
     if (st & ST_BAD_INDEX) { set_error("candidate index or rotation bin out of range"); return HYORB_EINVAL; }
+    if (st & ST_ROWTAB_OVERFLOW) {
+        set_error("stereo: the right keypoints cover more image rows than the row table holds (20 rows per keypoint on average for device batches; "
+                  "the extractor and host entry points size it from the largest keypoint)");
+        return HYORB_ECAPACITY;
+    }
     if (st & ST_ROW_RANGE) { set_error("stereo: keypoint row band outside [0, n_rows) (the reference writes out of bounds here)"); return HYORB_EINVAL; }
     set_error("device status 0x%x", st);
     return HYORB_ECUDA;
@@ -203,7 +211,9 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
     HY_CUDA(cudaSetDevice(h->device));
     HY_TRY(ex_ensure_plan(h, w, hgt));
     HY_TRY(ex_ensure_workspace(h, B));
-    const size_t st_ints = sp ? stereo_scratch_ints_per_pair(capacity) : 0;
+    // the row table of the stereo stage is sized for this pyramid's largest keypoint (ORBExtractor.cpp:478: size = 31 * scale[level])
+    const int st_rows = sp ? stereo_rows_budget(h->plan.dev.lv[h->plan.dev.nlevels - 1].kpSize, sp->size_ref) : 0;
+    const size_t st_ints = sp ? stereo_scratch_ints_per_pair(capacity, st_rows) : 0;
     if (sp) {
         HY_TRY(h->d_rowtab.ensure(sizeof(int32_t) * st_ints * (B / 2)));
         HY_TRY(h->d_bestd.ensure(sizeof(int32_t) * (size_t)capacity * (B / 2)));
@@ -318,7 +328,7 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
                     const int p0 = i0 / 2;
                     HY_TRY(launch_stereo(*sp, Bk / 2, d_kps + (size_t)i0 * capacity, d_desc + (size_t)i0 * capacity * HYORB_DESC_BYTES, d_counts + i0, capacity,
                                          h->d_rowtab.as<int32_t>() + st_ints * p0, d_uR + (size_t)p0 * capacity, d_depth + (size_t)p0 * capacity, nullptr,
-                                         h->d_bestd.as<int32_t>() + (size_t)p0 * capacity, status, st, &h->launches));
+                                         h->d_bestd.as<int32_t>() + (size_t)p0 * capacity, status, st, &h->launches, st_rows));
                 }
                 if (h->profile) {
                     cudaEvent_t e;
@@ -447,6 +457,12 @@ HYORB_API int hyorb_extractor_create(const hyorb_extractor_params *params, int d
         else { e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking); h->own_stream = true; }
     }
     h->lane_stream[0] = h->stream;
+    {
+        DevBuf *bufs[] = {&h->d_plan, &h->d_resize, &h->d_lut, &h->d_pyr, &h->d_blur, &h->d_cand, &h->d_qcode, &h->d_qnode, &h->d_qleaf, &h->d_sel,
+                          &h->d_candCount, &h->d_selCount, &h->d_status, &h->d_in, &h->d_raw, &h->d_kps, &h->d_desc, &h->d_counts,
+                          &h->d_rowtab, &h->d_bestd, &h->d_uR, &h->d_depth, &h->d_tmaps, &h->d_tmaps_lv, &h->d_lvtab};
+        if (e == cudaSuccess) for (DevBuf *b : bufs) { b->home = h->stream; b->has_home = true; }
+    }
     for (int k = 0; k < hyorb_extractor::MAX_LANES && e == cudaSuccess; k++) {
         if (k > 0) e = cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking);
@@ -802,6 +818,7 @@ struct hyorb_matcher {
     long launches = 0;
     DevBuf d_status, d_a, d_b, d_c, d_d, d_e, d_f, d_g, d_h, d_i, d_j, d_k, d_l;   // generic staging slots
     DevBuf d_pkey, d_psecond, d_rowtab, d_bestd, d_cellof, d_cellcnt, d_kp1, d_kp2;
+    int stereo_rows = 0;      // row-table budget of the next stereo call (hyorb_stereo_match_host derives it from the keypoints it uploads)
 };
 
 static int m_prepare(hyorb_matcher *m)
@@ -853,6 +870,11 @@ HYORB_API int hyorb_matcher_create(int device, void *cuda_stream, hyorb_matcher 
         else { e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking); m->own_stream = true; }
     }
     if (e != cudaSuccess) { set_error("CUDA init: %s", cudaGetErrorString(e)); delete m; return HYORB_ECUDA; }
+    {
+        DevBuf *bufs[] = {&m->d_status, &m->d_a, &m->d_b, &m->d_c, &m->d_d, &m->d_e, &m->d_f, &m->d_g, &m->d_h, &m->d_i, &m->d_j, &m->d_k, &m->d_l,
+                          &m->d_pkey, &m->d_psecond, &m->d_rowtab, &m->d_bestd, &m->d_cellof, &m->d_cellcnt, &m->d_kp1, &m->d_kp2};
+        for (DevBuf *b : bufs) { b->home = m->stream; b->has_home = true; }
+    }
     *out = m;
     return HYORB_OK;
 }
@@ -1417,13 +1439,14 @@ HYORB_API int hyorb_stereo_match_batch_device(hyorb_matcher *m, const hyorb_ster
     HY_TRY(m_prepare(m));
     if (!sp || n_pairs < 0 || capacity < 1 || !d_kps || !d_desc || !d_counts || !d_uR || !d_depth) { set_error("bad argument"); return HYORB_EINVAL; }
     if (n_pairs == 0) return HYORB_OK;
-    HY_TRY(m->d_rowtab.ensure(sizeof(int32_t) * stereo_scratch_ints_per_pair(capacity) * n_pairs));
+    const int rows = m->stereo_rows > 0 ? m->stereo_rows : 0;      // hyorb_stereo_match_host sets it from the keypoints it uploads; else the default budget
+    HY_TRY(m->d_rowtab.ensure(sizeof(int32_t) * stereo_scratch_ints_per_pair(capacity, rows) * n_pairs));
     if (!d_best_dist) {
         HY_TRY(m->d_bestd.ensure(sizeof(int32_t) * (size_t)capacity * n_pairs));
         d_best_dist = m->d_bestd.as<int32_t>();
     }
     return launch_stereo(*sp, n_pairs, d_kps, d_desc, d_counts, capacity, m->d_rowtab.as<int32_t>(), d_uR, d_depth, d_best_r, d_best_dist,
-                         m->d_status.as<int>(), m->stream, &m->launches);
+                         m->d_status.as<int>(), m->stream, &m->launches, rows);
 }
 
 HYORB_API int hyorb_stereo_match_host(hyorb_matcher *m, const hyorb_stereo_params *sp, const hyorb_keypoint *kps_l, const uint8_t *desc_l, int n_l,
@@ -1452,8 +1475,13 @@ HYORB_API int hyorb_stereo_match_host(hyorb_matcher *m, const hyorb_stereo_param
     }
     HY_CUDA(cudaMemcpyAsync(m->d_c.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, m->stream));
     HY_CUDA(cudaStreamSynchronize(m->stream));     // cnt is a stack array
-    HY_TRY(hyorb_stereo_match_batch_device(m, sp, 1, m->d_a.as<hyorb_keypoint>(), m->d_b.as<uint8_t>(), m->d_c.as<int32_t>(), cap,
-                                           m->d_d.as<float>(), m->d_e.as<float>(), m->d_g.as<int32_t>(), m->d_h.as<int32_t>()));
+    float max_size = 0.f;
+    for (int i = 0; i < n_r; i++) max_size = std::max(max_size, kps_r[i].size);
+    m->stereo_rows = stereo_rows_budget(max_size, sp->size_ref);
+    const int rc = hyorb_stereo_match_batch_device(m, sp, 1, m->d_a.as<hyorb_keypoint>(), m->d_b.as<uint8_t>(), m->d_c.as<int32_t>(), cap,
+                                                   m->d_d.as<float>(), m->d_e.as<float>(), m->d_g.as<int32_t>(), m->d_h.as<int32_t>());
+    m->stereo_rows = 0;
+    HY_TRY(rc);
     HY_CUDA(cudaMemcpyAsync(uR, m->d_d.p, sizeof(float) * (size_t)n_l, cudaMemcpyDeviceToHost, m->stream));
     HY_CUDA(cudaMemcpyAsync(depth, m->d_e.p, sizeof(float) * (size_t)n_l, cudaMemcpyDeviceToHost, m->stream));
     if (best_r) HY_CUDA(cudaMemcpyAsync(best_r, m->d_g.p, sizeof(int32_t) * (size_t)n_l, cudaMemcpyDeviceToHost, m->stream));

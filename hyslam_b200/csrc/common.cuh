@@ -197,12 +197,14 @@ int launch_bow_match(const uint8_t *desc1, const uint8_t *mask1, const int32_t *
                      int32_t *cbegin, int32_t *cend, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
                      uint8_t *accepted, const EpipolarDev &epi, cudaStream_t st, long *launches);
 int launch_distinctive(const uint8_t *desc, const int32_t *off, int n_lm, int32_t *best_idx, int32_t *best_median, cudaStream_t st, long *launches);
-size_t stereo_scratch_ints_per_pair(int capacity);
+// rows_budget: row-table entries per right keypoint the scratch is sized for (stereo_rows_budget(largest keypoint size, size_ref); 0 = default 20)
+int stereo_rows_budget(float max_kp_size, float size_ref);
+size_t stereo_scratch_ints_per_pair(int capacity, int rows_budget);
 int launch_stereo(const hyorb_stereo_params &sp, int n_pairs, const hyorb_keypoint *kps, const uint8_t *desc, const int32_t *counts, int capacity,
-                  int32_t *scratch, float *uR, float *depth, int32_t *best_r, int32_t *best_d, int *status, cudaStream_t st, long *launches);
+                  int32_t *scratch, float *uR, float *depth, int32_t *best_r, int32_t *best_d, int *status, cudaStream_t st, long *launches, int rows_budget);
 
 // device-side status word bits (OR-ed by kernels, read back at sync)
-enum { ST_CAND_OVERFLOW = 1, ST_SEL_OVERFLOW = 2, ST_OUT_OVERFLOW = 4, ST_QT_LIMIT = 8, ST_BAD_INDEX = 16, ST_ROW_RANGE = 32, ST_QT_MISMATCH = 64 };
+enum { ST_CAND_OVERFLOW = 1, ST_SEL_OVERFLOW = 2, ST_OUT_OVERFLOW = 4, ST_QT_LIMIT = 8, ST_BAD_INDEX = 16, ST_ROW_RANGE = 32, ST_QT_MISMATCH = 64, ST_ROWTAB_OVERFLOW = 128 };
 
 // acceptance rules shared by the matching kernels (MatchCriteria.cpp:214-246, 601-635, 486-523);
 // best/second are Hamming distances as floats, FLT_MAX when absent.

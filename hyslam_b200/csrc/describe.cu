@@ -211,19 +211,24 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
 int launch_describe(const PlanDev &hp, const PlanDev *dp, const uint8_t *blur, const uint32_t *sel, const int *selCount,
                     hyorb_keypoint *kps, uint8_t *desc, int capacity, int *counts, int *status, int B, cudaStream_t st, long *launches)
 {
-    // the float copy of the pattern is filled once per device; call_once blocks concurrent first callers (the reference
+    // the float copy of the pattern is filled once per device; the mutex blocks concurrent first callers (the reference
     // runs the left and the right extractor on two threads) until the table is complete
-    static std::once_flag pattern_once[64];
+    static std::mutex pattern_mu;
+    static bool pattern_ready[64];      // set only after the table has been written successfully: a failed first call is retried by the next one
     int dev = 0;
     HY_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) { set_error("device ordinal %d not supported", dev); return HYORB_EUNSUPPORTED; }
-    cudaError_t perr = cudaSuccess;
-    std::call_once(pattern_once[dev], [&] {
-        k_pattern_to_float<<<1, 256, 0, st>>>();
-        perr = cudaStreamSynchronize(st);
-        ++*launches;
-    });
-    if (perr != cudaSuccess) { set_error("pattern table: %s", cudaGetErrorString(perr)); return HYORB_ECUDA; }
+    {
+        std::lock_guard<std::mutex> lock(pattern_mu);
+        if (!pattern_ready[dev]) {
+            k_pattern_to_float<<<1, 256, 0, st>>>();
+            cudaError_t perr = cudaGetLastError();
+            if (perr == cudaSuccess) perr = cudaStreamSynchronize(st);
+            ++*launches;
+            if (perr != cudaSuccess) { set_error("pattern table: %s", cudaGetErrorString(perr)); return HYORB_ECUDA; }
+            pattern_ready[dev] = true;
+        }
+    }
     int slots = hp.selTotalCap < capacity ? hp.selTotalCap : capacity;
     if (slots < 1) slots = 1;
     dim3 grd((slots + DS_WARPS - 1) / DS_WARPS, B);

@@ -84,7 +84,7 @@ k_preprocess(const uint8_t *__restrict__ src, int spitch, unsigned long long sst
             }
         }
         uint8_t *o = d + (size_t)y * dpitch + x;
-        if (dal && x + 4 <= dpitch) *(uint32_t *)o = (uint32_t)g[0] | ((uint32_t)g[1] << 8) | ((uint32_t)g[2] << 16) | ((uint32_t)g[3] << 24);
+        if (dal && x + 4 <= ow) *(uint32_t *)o = (uint32_t)g[0] | ((uint32_t)g[1] << 8) | ((uint32_t)g[2] << 16) | ((uint32_t)g[3] << 24);
         else
             for (int j = 0; j < 4 && x + j < ow; j++) o[j] = (uint8_t)g[j];
     }

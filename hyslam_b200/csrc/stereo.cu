@@ -18,7 +18,8 @@ namespace hyorb {
 
 constexpr int ST_THREADS = 256;
 constexpr int ST_MAX_ROWS = MAX_DIM + 1;
-constexpr int ST_ROWS_PER_KP = 20;     // rows one right keypoint may cover (ceil(2r)+2, r = 2*size/31); checked at run time
+constexpr int ST_ROWS_PER_KP = 20;     // default row-table budget: AVERAGE rows per right keypoint (a keypoint covers ceil(2r)+2 rows, r = 2*size/31);
+                                       // callers that know the largest keypoint size pass a larger budget (launch_stereo's rows_budget)
 constexpr int ST_HIST = 264;
 
 struct StereoArgs {
@@ -34,7 +35,7 @@ __device__ __forceinline__ bool right_band(const hyorb_keypoint &k, float size_r
 {
     const float r = __fdiv_rn(__fmul_rn(2.0f, k.size), size_ref);                 // :57
     maxr = (int)ceilf(__fadd_rn(k.y, r)); minr = (int)floorf(__fsub_rn(k.y, r));  // :58-59
-    return !(minr < 0 || maxr >= nRows || maxr - minr + 1 > ST_ROWS_PER_KP);
+    return !(minr < 0 || maxr >= nRows);
 }
 
 __global__ void __launch_bounds__(ST_THREADS)
@@ -78,7 +79,7 @@ k_stereo_table(StereoArgs A)
         __syncthreads();
     }
     const bool overflow = s_off[nRows] > A.tabCap;
-    if (overflow && tid == 0) atomicOr(A.status, ST_OUT_OVERFLOW);
+    if (overflow && tid == 0) atomicOr(A.status, ST_ROWTAB_OVERFLOW);
     for (int i = tid; i <= nRows; i += ST_THREADS) goff[i] = overflow ? 0 : s_off[i];
     if (overflow) return;
     for (int iR = tid; iR < nr; iR += ST_THREADS) {
@@ -181,11 +182,21 @@ k_stereo_cut(StereoArgs A)
     }
 }
 
-size_t stereo_scratch_ints_per_pair(int capacity) { return (size_t)capacity * ST_ROWS_PER_KP + (ST_MAX_ROWS + 1) + ST_HIST; }
+int stereo_rows_budget(float max_kp_size, float size_ref)
+{
+    int rows = ST_ROWS_PER_KP;
+    if (max_kp_size > 0 && size_ref > 0) {
+        const float r = 2.0f * max_kp_size / size_ref;
+        const int need = (int)ceilf(2.0f * r) + 3;
+        if (need > rows) rows = need;
+    }
+    return rows > ST_MAX_ROWS ? ST_MAX_ROWS : rows;
+}
+size_t stereo_scratch_ints_per_pair(int capacity, int rows_budget) { return (size_t)capacity * (rows_budget > 0 ? rows_budget : ST_ROWS_PER_KP) + (ST_MAX_ROWS + 1) + ST_HIST; }
 
-// scratch: stereo_scratch_ints_per_pair(capacity) * n_pairs int32
+// scratch: stereo_scratch_ints_per_pair(capacity, rows_budget) * n_pairs int32
 int launch_stereo(const hyorb_stereo_params &sp, int n_pairs, const hyorb_keypoint *kps, const uint8_t *desc, const int32_t *counts, int capacity,
-                  int32_t *scratch, float *uR, float *depth, int32_t *best_r, int32_t *best_d, int *status, cudaStream_t st, long *launches)
+                  int32_t *scratch, float *uR, float *depth, int32_t *best_r, int32_t *best_d, int *status, cudaStream_t st, long *launches, int rows_budget)
 {
     if (n_pairs <= 0) return HYORB_OK;
     if (sp.n_rows < 1 || sp.n_rows > ST_MAX_ROWS) { set_error("n_rows=%d outside 1..%d", sp.n_rows, ST_MAX_ROWS); return HYORB_EINVAL; }
@@ -196,7 +207,7 @@ int launch_stereo(const hyorb_stereo_params &sp, int n_pairs, const hyorb_keypoi
     const float mb = sp.mbf / sp.fx;            // Camera: mb = mbf / fx
     A.maxD = sp.mbf / mb;                       // Stereomatcher.cpp:68-70 (minZ = mb)
     A.kps = kps; A.desc = (const uint4 *)desc; A.counts = counts; A.capacity = capacity;
-    A.tabCap = capacity * ST_ROWS_PER_KP;
+    A.tabCap = capacity * (rows_budget > 0 ? rows_budget : ST_ROWS_PER_KP);
     A.rowtab = scratch;
     A.rowoff = scratch + (size_t)A.tabCap * n_pairs;
     A.hist = A.rowoff + (size_t)(ST_MAX_ROWS + 1) * n_pairs;

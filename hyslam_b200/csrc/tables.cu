@@ -142,7 +142,8 @@ int build_plan(const hyorb_extractor_params &p, int width, int height, HostPlan 
         L.nIni = (int)roundf((float)lw / (float)lh);
         if (L.nIni < 1 || L.nIni > QT_MAX_ROOTS) { set_error("level %d aspect %dx%d gives %d quadtree roots (supported 1..%d)", l, lw, lh, L.nIni, QT_MAX_ROOTS); return HYORB_EUNSUPPORTED; }
         L.hX = (float)lw / (float)L.nIni;
-        L.candCap = (L.w * L.h) / 8 + 1024;
+        // cell-local 3x3 NMS keeps at most ceil(wCell/2) * ceil(hCell/2) pixels of a cell: a quarter of the level plus one row / column per cell
+        L.candCap = (L.w / 2 + L.nCols + 2) * (L.h / 2 + L.nRows + 2);
         L.candOff = candOff; candOff += (unsigned)((L.candCap + 63) & ~63);
         int need = 4 * L.quota; if (need < 4 * L.nIni) need = 4 * L.nIni; if (need < 64) need = 64;
         L.qtMaxN = next_pow2(need);

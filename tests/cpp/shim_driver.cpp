@@ -30,6 +30,8 @@ template <typename T> static void put(FILE *f, const std::vector<T> &v) { if (!v
 
 int main(int argc, char **argv)
 {
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);      // hardware queues for the lanes' streams, before the CUDA context exists
+
     if (argc < 9) { fprintf(stderr, "usage: shim_driver left.raw right.raw W H nFeatures mbf fx out.bin\n"); return 2; }
     const int w = atoi(argv[3]), h = atoi(argv[4]), nf = atoi(argv[5]);
     const float mbf = (float)atof(argv[6]), fx = (float)atof(argv[7]);

@@ -163,3 +163,29 @@ def test_process_stereo_batch_matches_oracle():
         assert np.array_equal(depth[p, :nl].view(np.uint32), odepth.view(np.uint32))
     st, calls = ex.stage_times()
     assert calls == 0                      # profiling is off by default
+
+
+def test_stereo_with_large_keypoint_sizes_imaging_config():
+    """config/slam_feature_config.yaml's Imaging camera: 3000 features, scale 1.4 -- level-7 keypoints are 31 * 1.4^7 = 326 px wide, their
+    row band (r = 2 * size / 31 = 21 rows either side) is wider than the default row-table budget; both stereo entry points must size the
+    table from the keypoints instead of refusing the frame (round-1 ADVICE)."""
+    L, R = synth.stereo_pair(900, 1600, 11, "noise")
+    s = hb.FeatureExtractorSettings(nFeatures=3000, fScaleFactor=1.4, nLevels=8)
+    p = O.default_params(3000, 1.4, 8, 30)
+    okl, odl = O.extract(L, p); okr, odr = O.extract(R, p)
+    assert okr["size"].max() > 250
+    osp = O.StereoParams(386.1448, 718.856, 900, 100.0, 50.0, 31.0)
+    ouR, odepth, obr, obd = O.stereo_match(osp, okl, odl, okr, odr)
+    cam = hb.StereoCamera(386.1448, 718.856, 900.0)
+    # Stereomatcher mirror (hyorb_stereo_match_host)
+    sm = hb.Stereomatcher((okl, odl, okr, odr), cam)
+    sm.computeStereoMatches()
+    uR, depth = sm.getData()
+    assert np.array_equal(sm.best_r, obr) and np.array_equal(sm.best_dist, obd)
+    assert np.array_equal(uR.view(np.uint32), ouR.view(np.uint32)) and np.array_equal(depth.view(np.uint32), odepth.view(np.uint32))
+    # ProcessStereoImage in one call (hyorb_process_stereo_batch_host)
+    ex = hb.ORBExtractor(s)
+    kps, desc, counts, uR2, depth2 = ex.process_stereo_batch(np.stack([L, R]), cam, capacity=ex.default_capacity())
+    nl = counts[0]
+    assert nl == len(okl) and np.array_equal(kps[0, :nl], okl)
+    assert np.array_equal(uR2[0, :nl].view(np.uint32), ouR.view(np.uint32)) and np.array_equal(depth2[0, :nl].view(np.uint32), odepth.view(np.uint32))
