@@ -45,6 +45,7 @@ constexpr int FT_BUF_BYTES = (FT_BOXW * FT_PH + 127) & ~127;   // one pixel buff
 constexpr int FT_PLP = 8 * (FT_NSEG + 2) + 4;  // plane row pitch in words: an all-zero segment either side, +4 so that the 128-bit
                                                // loads of 8 consecutive rows hit disjoint banks
 static_assert(EMIT_CAP * 4 <= FT_PH * FT_PLP * 4, "the emit staging aliases the plane buffer");
+constexpr int FT_GP = 16 * FT_NSEG + 2;        // pair-word buffer: row pitch in words (+2: the 64-bit accesses of 16 consecutive rows hit disjoint banks)
 
 struct FastTile { int b, l, x0, sy0; };      // image, level, image column of region column 0, image row of score row 0
 
@@ -74,9 +75,6 @@ __device__ __forceinline__ uint32_t bit_range(int a, int b)
     return hi & ~lo;
 }
 
-#ifndef HYORB_FT_EXP
-#define HYORB_FT_EXP 0      // timing experiments only (tools/build_variant.sh): 1 = no corners after the test, 2 = no NMS, 3 = no test
-#endif
 #ifndef HYORB_FT_MINB
 #define HYORB_FT_MINB 5      // 64 registers: five 192-thread CTAs per SM (measured faster than 4 x 80 or 3 x 86 registers)
 #endif
@@ -85,13 +83,20 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
        uint32_t *__restrict__ cand, int *__restrict__ candCount, int *__restrict__ status)
 {
     __shared__ __align__(128) uint8_t s_pixbuf[2][FT_BUF_BYTES];
-    __shared__ __align__(16) uint32_t s_planes[FT_PH * FT_PLP];
+    __shared__ __align__(16) uint32_t s_planes_all[(FT_PH + 6) * FT_PLP];   // three rows of slack above and below: the pair words of the first / last
+                                                                           // three pixel rows look outside the box (their results are never used)
+    // score map + corner list; during the corner test the same bytes hold the pair words of every (pixel row, segment) item (fast_bitslice.cuh)
+    __shared__ __align__(8) uint8_t s_sl[FT_SH * FT_SW + 2 * FT_SH * FT_SW];
+    static_assert(sizeof(uint32_t) * (16 + FT_PH * FT_GP) <= FT_SH * FT_SW * 3, "the pair words alias score map + list");
+    static_assert((FT_SH * FT_SW) % 4 == 0, "list alignment");
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ __align__(4) uint8_t s_score[FT_SH * FT_SW];
-    __shared__ uint16_t s_list[FT_SH * FT_SW];
     __shared__ uint8_t s_cl[FT_SW], s_cr[FT_SW], s_ru[64], s_rd[64];   // 1 = the left / right / upper / lower neighbour is in the same cell
     __shared__ int s_n, s_ne, s_base;
+    uint32_t *const s_planes = s_planes_all + 3 * FT_PLP;
     uint32_t *s_emit = s_planes;            // the planes are dead once the corner test is done
+    uint8_t *const s_score = s_sl;
+    uint16_t *const s_list = (uint16_t *)(s_sl + FT_SH * FT_SW);
+    uint32_t *const s_g = (uint32_t *)s_sl + 16;
 
     grid_dependency_wait();      // launch_dependent (common.cuh): follows the last pyramid level
     const int tid = threadIdx.x;
@@ -126,7 +131,6 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     const uint8_t *pix8 = s_pixbuf[buf] + off;              // region, row pitch PITCHB
 
     if (tid == 0) { s_n = 0; s_ne = 0; }
-    for (int i = tid; i < FT_SH * FT_SW / 4; i += FT_THREADS) ((uint32_t *)s_score)[i] = 0;
     if (tid < FT_SW) {
         const int x = x0 + tid;                              // columns left of x = 19 are never emitted
         const int m = x >= DET_MIN ? (x - DET_MIN) % L.wCell : 1;
@@ -163,24 +167,30 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     __syncthreads();
 
     const int xEnd = L.maxBX - 3, yEnd = L.maxBY - 3;     // detect range [19, xEnd) x [19, yEnd)
-    // ---- A. corner test: warp -> (segment, block of 32 score rows), lane -> score row
+    // ---- A. corner test in the paired formulation (fast_bitslice.cuh): warp -> (segment, block of 32 PIXEL rows), lane -> pixel row.
+    // A1: every item compares the half ring with dx >= 0 against centre +- 20 (16 ripple compares) and publishes its 16 pair words;
+    // A2: the other half of the ring is read back from the items three rows above / below, shifted by the ring's x offsets.
     uint32_t flags = 0;
-    const int a_seg = (tid >> 5) % FT_NSEG, a_r = ((tid >> 5) / FT_NSEG) * 32 + (tid & 31);
-    if (a_r < FT_SH) {
+    const int a_seg = (tid >> 5) % FT_NSEG, a_pr = ((tid >> 5) / FT_NSEG) * 32 + (tid & 31);
+    const int a_r = a_pr - 3;                              // score row of this item (valid: 0 .. FT_SH-1)
+    uint32_t Gp[8], Gm[8];
+    bs_pairs<FT_PLP>(s_planes + a_pr * FT_PLP + (a_seg + 1) * 8, Gp, Gm);
+    {
+        uint2 *gdst = (uint2 *)(s_g + a_pr * FT_GP + a_seg * 16);
+#pragma unroll
+        for (int k = 0; k < 8; k++) gdst[k] = make_uint2(Gp[k], Gm[k]);
+    }
+    __syncthreads();
+    if (a_r >= 0 && a_r < FT_SH) {
         const int sy = sy0 + a_r;
         // region columns with a full ring [3, 93) that lie in the detect range, restricted to this segment
         const int cl = max(3, DET_MIN - x0), ch = min(FT_SW - 3, xEnd - x0);
         uint32_t valid = bit_range(cl - 32 * a_seg, ch - 32 * a_seg);
         if (sy < DET_MIN || sy >= yEnd) valid = 0;
-#if HYORB_FT_EXP == 3
-        if (valid == 0x12345u) flags = bs_corners<FT_PLP>(s_planes + (a_r + 3) * FT_PLP + (a_seg + 1) * 8) & valid;
-#else
-        if (valid) flags = bs_corners<FT_PLP>(s_planes + (a_r + 3) * FT_PLP + (a_seg + 1) * 8) & valid;
-#endif
+        if (valid) flags = bs_corners_paired<FT_GP>(Gp, Gm, s_g + a_pr * FT_GP + a_seg * 16) & valid;
     }
-#if HYORB_FT_EXP == 1
-    if (flags != 0x12345u) flags = 0;
-#endif
+    __syncthreads();      // the pair words are dead: their bytes become the score map (zeroed here) and the corner list
+    for (int i = tid; i < FT_SH * FT_SW / 4; i += FT_THREADS) ((uint32_t *)s_score)[i] = 0;
     // ---- B. compact the corner bits into the CTA list: warp scan of the per-lane counts, one shared-memory atomic per warp
     {
         const int lane = tid & 31;
@@ -238,11 +248,7 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     __syncthreads();
 
     // ---- D. cell-local 3x3 NMS over the interior, stage survivors (s_emit aliases the plane buffer)
-#if HYORB_FT_EXP == 2
-    for (int i0 = 0; i0 < ncorner - 100000; i0 += FT_THREADS) {
-#else
-    for (int i0 = 0; i0 < ncorner; i0 += FT_THREADS) {
-#endif      // warp-uniform trip count: the ballot below needs all lanes
+    for (int i0 = 0; i0 < ncorner; i0 += FT_THREADS) {      // warp-uniform trip count: the ballot below needs all lanes
         const int i = i0 + tid;
         // branch-free: the eight neighbour scores are fetched together (independent loads, every address stays inside
         // s_score for an interior pixel) and neighbours that belong to another cell are replaced by 0

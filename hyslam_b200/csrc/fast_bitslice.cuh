@@ -139,3 +139,48 @@ BS_HD uint32_t bs_corners(const uint32_t *rowp)
 #undef BS_RING
     return bs_arc9(B) | bs_arc9(D);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Paired formulation: every ordered comparison of the segment test is shared by TWO pixels.  With o_k the ring offset of
+// position k (k = 0..7: the half of the ring with dx >= 0) define at every pixel p
+//     Gp_k(p) = [I(p + o_k) > I(p) + 20]  = bright_k(p)          Gm_k(p) = [I(p + o_k) < I(p) - 20]  = dark_k(p)
+// then, because a > b + 20 <=> b < a - 20 on integers (the saturations at 255 / 0 leave both sides false together),
+//     bright_{k+8}(p) = [I(p - o_k) > I(p) + 20] = Gm_k(p - o_k)   dark_{k+8}(p) = [I(p - o_k) < I(p) - 20] = Gp_k(p - o_k)
+// so 16 ripple compares per 32 pixels instead of 32 and 7 plane shifts instead of 14; the other half of the ring is read back from
+// the pair words of the pixel rows r - dy_k, shifted by dx_k (exchange through a buffer every item writes its 16 words to).
+// bs_pairs: the 16 pair words of one item; bs_corners_paired: corner word from the item's own pair words and the buffer.
+// Buffer layout: word (2k + t) of item (row, seg) at g[row * GP + seg * 16 + 2k + t], t = 0: Gp_k, t = 1: Gm_k; the 16 words before an
+// item belong to the segment on its left (for segment 0: whatever precedes -- only bits of columns < 3 come from there, never valid).
+template <int PLP>
+BS_HD void bs_pairs(const uint32_t *rowp, uint32_t (&Gp)[8], uint32_t (&Gm)[8])
+{
+    uint32_t c[8], h[8], l[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) c[b] = rowp[b];
+    bs_thresholds(c, h, l);
+#define BS_PAIR(k, dx, dy) { \
+        const uint32_t *p = rowp + (dy) * PLP; \
+        uint32_t rv[8]; \
+        if ((dx) > 0) { _Pragma("unroll") for (int b = 0; b < 8; b++) rv[b] = BS_FSR(p[b], p[8 + b], (dx)); } \
+        else { _Pragma("unroll") for (int b = 0; b < 8; b++) rv[b] = p[b]; } \
+        bs_compare(rv, h, l, Gp[k], Gm[k]); }
+    BS_PAIR(0, 0, 3) BS_PAIR(1, 1, 3) BS_PAIR(2, 2, 2) BS_PAIR(3, 3, 1) BS_PAIR(4, 3, 0) BS_PAIR(5, 3, -1) BS_PAIR(6, 2, -2) BS_PAIR(7, 1, -3)
+#undef BS_PAIR
+}
+
+template <int GP>
+BS_HD uint32_t bs_corners_paired(const uint32_t (&Gp)[8], const uint32_t (&Gm)[8], const uint32_t *g)
+{
+    uint32_t B[16], D[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { B[k] = Gp[k]; D[k] = Gm[k]; }
+    // position k + 8 of pixel p = position k of pixel p - o_k: row - dy_k, column - dx_k (bit j of the result = bit j - dx of the row's words)
+#define BS_BACK(k, dx, dy) { \
+        const uint32_t *q = g - (dy) * GP + 2 * (k); \
+        if ((dx) > 0) { B[(k) + 8] = BS_FSL(q[-15], q[1], (dx)); D[(k) + 8] = BS_FSL(q[-16], q[0], (dx)); } \
+        else { B[(k) + 8] = q[1]; D[(k) + 8] = q[0]; } }
+    BS_BACK(0, 0, 3) BS_BACK(1, 1, 3) BS_BACK(2, 2, 2) BS_BACK(3, 3, 1) BS_BACK(4, 3, 0) BS_BACK(5, 3, -1) BS_BACK(6, 2, -2) BS_BACK(7, 1, -3)
+#undef BS_BACK
+    return bs_arc9(B) | bs_arc9(D);
+}
+

@@ -60,6 +60,34 @@ int main()
                 }
             }
     }
+    // ---- the paired formulation (bs_pairs + bs_corners_paired) must give the same corner words as bs_corners
+    {
+        const int GP = 16 * NSEG + 2;
+        static uint32_t gbuf[16 + H * GP];
+        uint32_t *g = gbuf + 16;
+        for (int trial = 0; trial < 100; trial++) {
+            const int amp = 1 + (int)(rnd() % 255);
+            for (int i = 0; i < H * W; i++) img[i] = (uint8_t)(128 + (int)(rnd() % (unsigned)amp) - amp / 2);
+            if (trial % 5 == 0) for (int i = 0; i < H * W; i++) img[i] = (rnd() & 1) ? 255 : 0;
+            to_planes(img, planes);
+            static uint32_t Gp[H][NSEG][8], Gm[H][NSEG][8];
+            memset(gbuf, 0xA5, sizeof(gbuf));          // pair words of rows without a full ring are never read for a valid pixel
+            for (int r = 3; r < H - 3; r++)            // (the kernel pads its plane buffer by three rows instead)
+                for (int s2 = 0; s2 < NSEG; s2++) {
+                    bs_pairs<PLP>(planes + r * PLP + (s2 + 1) * 8, Gp[r][s2], Gm[r][s2]);
+                    for (int k = 0; k < 8; k++) { g[r * GP + s2 * 16 + 2 * k] = Gp[r][s2][k]; g[r * GP + s2 * 16 + 2 * k + 1] = Gm[r][s2][k]; }
+                }
+            for (int r = 6; r < H - 6; r++)
+                for (int s2 = 0; s2 < NSEG; s2++) {
+                    const uint32_t want = bs_corners<PLP>(planes + r * PLP + (s2 + 1) * 8);
+                    const uint32_t got = bs_corners_paired<GP>(Gp[r][s2], Gm[r][s2], g + r * GP + s2 * 16);
+                    uint32_t valid = 0xFFFFFFFFu;
+                    if (s2 == 0) valid &= ~7u;                      // columns 0..2: no full ring
+                    if (s2 == NSEG - 1) valid &= 0x1FFFFFFFu;       // columns W-3..W-1
+                    if ((got ^ want) & valid) bad++;
+                }
+        }
+    }
     printf("corners %ld mismatches %ld\n", corners, bad);
     return bad ? 1 : 0;
 }
