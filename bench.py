@@ -685,14 +685,18 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     lv = level_bytes(ex)
     sumP = sum(lv)
+    fused = os.environ.get("HYORB_FUSED_LEVELS", "1") != "0"
     alg = {   # algorithmic bytes per image
-        "pyramid": sum(lv[:-1]) + sum(lv[1:]),
+        # level.cu (default): every level read ONCE, blurred copy and next level written; pyramid.cu + blur.cu: each level read twice
+        "pyramid": (2 * sumP + sum(lv[1:])) if fused else (sum(lv[:-1]) + sum(lv[1:])),
         "fast": sumP,
-        "blur": 2 * sumP,                                # materialised blur: read level + write blurred level
+        "blur": 0 if fused else 2 * sumP,                # materialised blur: read level + write blurred level
         "describe": sumP + 60 * (kp_per_step / B),       # read blurred windows (<= one pass) + 28 B keypoint + 32 B descriptor
         "quadtree": 0, "stereo": 0,
     }
     stages = {}
+    if fused:
+        stage_ms = {k: v for k, v in stage_ms.items() if k != "blur"}       # the blur is part of the "pyramid" stage (k_level)
     for k, v in stage_ms.items():
         per_launch_ms = v / max(stage_calls, 1)
         stages[k] = {"ms_per_step": per_launch_ms, "share": v / max(sum(stage_ms.values()), 1e-9),
@@ -700,7 +704,7 @@ def main():
     dom = max(stage_ms, key=lambda k: stage_ms[k])
     dom_ms = stage_ms[dom] / max(stage_calls, 1)
     achieved = alg[dom] * B / (dom_ms * 1e-3) / 1e9 if alg.get(dom) else 0.0
-    kname = {"fast": "k_fast", "pyramid": "k_resize", "blur": "k_blur", "describe": "k_describe", "quadtree": "k_quadtree", "stereo": "k_stereo"}[dom]
+    kname = {"fast": "k_fast", "pyramid": "k_level" if fused else "k_resize", "blur": "k_blur", "describe": "k_describe", "quadtree": "k_quadtree", "stereo": "k_stereo"}[dom]
     # DRAM traffic of that kernel from the committed `ncu --set full` capture of this same command (profiles/traffic.json:
     # bytes per image, dram__bytes_read.sum + dram__bytes_write.sum), scaled to the images of one launch
     traffic = None

@@ -45,6 +45,8 @@ constexpr int FT_BUF_BYTES = (FT_BOXW * FT_PH + 127) & ~127;   // one pixel buff
 constexpr int FT_PLP = 8 * (FT_NSEG + 2) + 4;  // plane row pitch in words: an all-zero segment either side, +4 so that the 128-bit
                                                // loads of 8 consecutive rows hit disjoint banks
 static_assert(EMIT_CAP * 4 <= FT_PH * FT_PLP * 4, "the emit staging aliases the plane buffer");
+constexpr int FT_SP = FT_BOXW;                 // score-map row pitch = pixel-box row pitch (28 words): a list entry indexes both, and the rows r, r+2, r+4, r+6 a
+                                               // warp's 32 list entries come from (see phase B) start 8 banks apart -- their byte gathers do not collide
 constexpr int FT_GP = 16 * FT_NSEG + 2;        // pair-word buffer: row pitch in words (+2: the 64-bit accesses of 16 consecutive rows hit disjoint banks)
 
 struct FastTile { int b, l, x0, sy0; };      // image, level, image column of region column 0, image row of score row 0
@@ -86,16 +88,17 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     __shared__ __align__(16) uint32_t s_planes_all[(FT_PH + 6) * FT_PLP];   // three rows of slack above and below: the pair words of the first / last
                                                                            // three pixel rows look outside the box (their results are never used)
     // score map + corner list; during the corner test the same bytes hold the pair words of every (pixel row, segment) item (fast_bitslice.cuh)
-    __shared__ __align__(8) uint8_t s_sl[FT_SH * FT_SW + 2 * FT_SH * FT_SW];
-    static_assert(sizeof(uint32_t) * (16 + FT_PH * FT_GP) <= FT_SH * FT_SW * 3, "the pair words alias score map + list");
-    static_assert((FT_SH * FT_SW) % 4 == 0, "list alignment");
+    __shared__ __align__(8) uint8_t s_sl[FT_SH * FT_SP + 2 * FT_SH * FT_SW];
+    static_assert(sizeof(uint32_t) * (16 + FT_PH * FT_GP) <= FT_SH * FT_SP + 2 * FT_SH * FT_SW, "the pair words alias score map + list");
+    static_assert((FT_SH * FT_SP) % 4 == 0 && FT_SH * FT_SP < 65536, "list alignment / 16-bit list entries");
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint8_t s_cl[FT_SW], s_cr[FT_SW], s_ru[64], s_rd[64];   // 1 = the left / right / upper / lower neighbour is in the same cell
+    __shared__ uint8_t s_msk[2 * FT_SW + 128];                          // 1 = the left / right / upper / lower neighbour is in the same cell
+    uint8_t *const s_cl = s_msk, *const s_cr = s_msk + FT_SW, *const s_ru = s_msk + 2 * FT_SW, *const s_rd = s_msk + 2 * FT_SW + 64;
     __shared__ int s_n, s_ne, s_base;
     uint32_t *const s_planes = s_planes_all + 3 * FT_PLP;
     uint32_t *s_emit = s_planes;            // the planes are dead once the corner test is done
     uint8_t *const s_score = s_sl;
-    uint16_t *const s_list = (uint16_t *)(s_sl + FT_SH * FT_SW);
+    uint16_t *const s_list = (uint16_t *)(s_sl + FT_SH * FT_SP);
     uint32_t *const s_g = (uint32_t *)s_sl + 16;
 
     grid_dependency_wait();      // launch_dependent (common.cuh): follows the last pyramid level
@@ -190,10 +193,14 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         if (valid) flags = bs_corners_paired<FT_GP>(Gp, Gm, s_g + a_pr * FT_GP + a_seg * 16) & valid;
     }
     __syncthreads();      // the pair words are dead: their bytes become the score map (zeroed here) and the corner list
-    for (int i = tid; i < FT_SH * FT_SW / 4; i += FT_THREADS) ((uint32_t *)s_score)[i] = 0;
+    for (int i = tid; i < FT_SH * FT_SP / 4; i += FT_THREADS) ((uint32_t *)s_score)[i] = 0;
     // ---- B. compact the corner bits into the CTA list: warp scan of the per-lane counts, one shared-memory atomic per warp
     {
-        const int lane = tid & 31;
+        // the lanes take the warp's 32 rows in the order 0, 2, 4, .., 30, 1, 3, .., 31: consecutive list entries (= the lanes of a warp in the
+        // phases below) then come from rows two apart, whose bytes lie 8 banks apart in the pixel box and the score map
+        const int lane = tid & 31, srcl = ((lane & 15) << 1) | (lane >> 4);
+        flags = __shfl_sync(0xffffffffu, flags, srcl);
+        const int l_r = a_r - lane + srcl;
         const int cnt = __popc(flags);
         int inc = cnt;
 #pragma unroll
@@ -206,7 +213,7 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         if (lane == 0 && total) base = atomicAdd(&s_n, total);
         base = __shfl_sync(0xffffffffu, base, 0);
         int pos = base + inc - cnt;
-        const int e0 = a_r * FT_SW + 32 * a_seg;
+        const int e0 = l_r * FT_SP + 32 * a_seg;
         // branch-free extraction: every lane walks all 32 bit positions with predicated stores (a data-dependent loop runs at the
         // pace of the warp's busiest lane and costs several times more instructions)
         uint16_t *dstp = s_list + pos;
@@ -220,17 +227,20 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     const int ncorner = s_n;
     for (int i = tid; i < ncorner; i += FT_THREADS) {
         const int e = s_list[i];
-        const int r = e / FT_SW, cidx = e - r * FT_SW;
-        const uint8_t *p = pix8 + (r + 3) * PITCHB + cidx;
+        static_assert(FT_SP == PITCHB, "a list entry indexes the pixel box and the score map alike");
+        const uint8_t *p = pix8 + 3 * PITCHB + e;
         const int v = p[0];
         // 16-bit lanes: low = centre - ring + 0x4000 (dark arcs, biased), high = ring - centre (bright arcs), as ONE multiply-add
         // per ring pixel (FMA pipe; the ALU pipe is this kernel's bottleneck): (ring - centre) * 65535 + 0x4000 =
         // (ring - centre) << 16 | (0x4000 + centre - ring) -- the bias keeps the low lane positive, so nothing carries or borrows
         // across the lanes; min / max are order-preserving under it and it comes off at the end.
-        const uint32_t A = 0x4000u - (uint32_t)v * 65535u;
+        uint32_t K65535;                          // kept opaque: the compiler otherwise splits x * 65535 + A into a shift-add and a subtract
+        asm("mov.u32 %0, 65535;" : "=r"(K65535));
+        uint32_t A = 0x4000u - (uint32_t)v * K65535;
+        asm("" : "+r"(A));                        // ... or refactors it into (ring - centre) * 65535 + 0x4000, again two instructions per ring pixel
         uint32_t wv[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) wv[k] = (uint32_t)p[ring_off(k)] * 65535u + A;
+        for (int k = 0; k < 16; k++) wv[k] = (uint32_t)p[ring_off(k)] * K65535 + A;
         uint32_t m3[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) m3[k] = __vimin3_s16x2(wv[k], wv[(k + 1) & 15], wv[(k + 2) & 15]);
@@ -252,12 +262,12 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         const int i = i0 + tid;
         // branch-free: the eight neighbour scores are fetched together (independent loads, every address stays inside
         // s_score for an interior pixel) and neighbours that belong to another cell are replaced by 0
-        const int e = i < ncorner ? (int)s_list[i] : (FT_SW + FT_C0);
-        const int r = e / FT_SW, cidx = e - r * FT_SW;
+        const int e = i < ncorner ? (int)s_list[i] : (FT_SP + FT_C0);
+        const int r = e / FT_SP, cidx = e - r * FT_SP;
         const bool inner = i < ncorner && r >= 1 && r <= FT_OH && cidx >= FT_C0 && cidx < FT_C0 + FT_OW;      // else: halo, belongs to the neighbouring tile
-        const uint8_t *q = s_score + (inner ? e : FT_SW + FT_C0);
+        const uint8_t *q = s_score + (inner ? e : FT_SP + FT_C0);
         const int s = q[0];
-        const int nl = q[-1], nr = q[1], nu = q[-FT_SW], nul = q[-FT_SW - 1], nur = q[-FT_SW + 1], nd = q[FT_SW], ndl = q[FT_SW - 1], ndr = q[FT_SW + 1];
+        const int nl = q[-1], nr = q[1], nu = q[-FT_SP], nul = q[-FT_SP - 1], nur = q[-FT_SP + 1], nd = q[FT_SP], ndl = q[FT_SP - 1], ndr = q[FT_SP + 1];
         // masks applied as multiplies by 0 / 1 (FMA pipe) instead of selects (ALU pipe, the bottleneck)
         const int Lk = s_cl[cidx], Rk = s_cr[cidx], Uk = s_ru[r], Dk = s_rd[r];
         const int m0 = __vimax3_s32(nl * Lk, nr * Rk, nu * Uk);
