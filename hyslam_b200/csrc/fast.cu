@@ -17,9 +17,11 @@
 // buffer: the box of the CTA's next tile is in flight while the current one is processed, so no thread spends
 // instructions or scoreboard stalls on staging.  Per tile:
 //   T. every thread transposes 32 pixels into 8 bit-plane words (fast_bitslice.cuh);
-//   A. every thread runs the bit-sliced segment test on 32 pixels (one 3-input logic op per bit and ring position,
-//      funnel shifts for the ring's x offsets, 9-of-16 arc logic on 32 pixels per op);
-//   B. corner bits are compacted into the CTA's list (warp scan + one shared-memory atomic per warp);
+//   A. every thread runs the bit-sliced segment test on 32 pixels in the PAIRED formulation: one 3-input logic op per bit for the
+//      half ring with dx >= 0 (funnel shifts for the x offsets), the 16 pair words published to shared memory, the other half ring
+//      read back from the items three rows above / below; 9-of-16 arc logic on 32 pixels per op;
+//   B. corner bits are compacted into the CTA's list (warp scan + one shared-memory atomic per warp; rows interleaved two apart
+//      so that the byte gathers of C and D spread over the banks);
 //   C. scores are computed only for the listed corners with 3-input integer min/max (VIMNMX3);
 //   D. cell-local 3x3 NMS (branch-free) and a CTA-aggregated emit.
 #include <algorithm>
