@@ -132,6 +132,7 @@ static int ex_ensure_plan(hyorb_extractor *h, int w, int hgt)
         const int roots = np.dev.lv[l].h > 0 ? np.dev.lv[l].w / np.dev.lv[l].h + 2 : 2;
         h->kp_bound += std::max(h->quota[l] + 3, 4 * roots);
     }
+    if (const char *v = getenv("HYORB_KP_BOUND")) { const int b = atoi(v); if (b > 0) h->kp_bound = b; }   // tests: force the overflow fetch of large host batches
     h->Bcap = 0;
     return HYORB_OK;
 }

@@ -19,6 +19,9 @@
 
 namespace hyorb {
 
+#ifndef HYORB_QT_MINB
+#define HYORB_QT_MINB 3      // 40 registers, 3 CTAs per SM; 4 x 32 registers measured the same (0.486 vs 0.482 ms): the kernel is not occupancy-bound
+#endif
 constexpr int QT_LAT = 1024;      // threads per CTA when only a few images are in flight: per-frame latency over occupancy
 constexpr unsigned NODE_FINAL = 0xFFFFu;   // candidate already sits in an emitted leaf
 constexpr unsigned NODE_STAY = 0x4000u;    // candidate stays in an unexpanded node of the previous depth (last pass only)
@@ -112,7 +115,7 @@ __device__ __forceinline__ void agg_inc(uint32_t *arr, int slot)
 }
 
 template <int QT>
-__global__ void __launch_bounds__(QT)
+__global__ void __launch_bounds__(QT, QT == 512 ? HYORB_QT_MINB : 1)
 k_quadtree(const PlanDev *__restrict__ plan, const uint32_t *__restrict__ cand_all, const int *__restrict__ candCount,
            const uint32_t *__restrict__ lut, uint32_t *__restrict__ qcode_all, uint16_t *__restrict__ qnode_all,
            uint2 *__restrict__ qleaf_all, uint32_t *__restrict__ sel_all, int *__restrict__ selCount, int *__restrict__ status)

@@ -85,7 +85,10 @@ k_stereo_table(StereoArgs A)
     for (int iR = tid; iR < nr; iR += ST_THREADS) {
         int minr, maxr;
         if (!right_band(kr[iR], A.sp.size_ref, nRows, minr, maxr)) continue;
-        for (int yi = minr; yi <= maxr; yi++) tab[s_off[yi] + atomicAdd(&s_fill[yi], 1)] = iR;
+        // entry = right index | octave << 16: the search filters on the octave without touching the keypoint (capacity <= 65535)
+        // (octaves are 0 .. nlevels-1; stored + 4 and clamped to [0, 32767] so that any value a caller could pass in [-4, 32763] stays exact)
+        const int entry = iR | (min(max(kr[iR].octave + 4, 0), 0x7FFF) << 16);
+        for (int yi = minr; yi <= maxr; yi++) tab[s_off[yi] + atomicAdd(&s_fill[yi], 1)] = entry;
     }
 }
 
@@ -118,8 +121,8 @@ k_stereo_search(StereoArgs A)
         if (lo != hi && !(maxU < 0)) {
             const uint4 a0 = dl[2 * iL], a1 = dl[2 * iL + 1];
             for (int c = lo + lane; c < hi; c += 32) {
-                const int iR = tab[c];
-                const int oR = kr[iR].octave;
+                const int entry = tab[c];
+                const int iR = entry & 0xFFFF, oR = (entry >> 16) - 4;
                 if (oR < kp.octave - 1 || oR > kp.octave + 1) continue;        // :100-101
                 const float u = kr[iR].x;
                 if (u >= minU && u <= maxU) {                                  // :105

@@ -180,3 +180,23 @@ def test_device_pointer_entry_matches_host_entry(pitched):
         n = counts[i]
         assert k2[i, :n].tobytes() == kps[i, :n].tobytes()
         assert np.array_equal(d_desc[i, :n].cpu().numpy(), desc[i, :n])
+
+
+def test_large_host_batch_fetches_what_exceeds_the_download_bound(monkeypatch):
+    """Host batches of more than 8 images download min(capacity, keypoint bound) entries per image while the batch runs and fetch the
+    rest after the counts have arrived (api.cu ex_fetch_overflow).  With the bound forced far below what the images produce, the
+    results must still be complete and identical to the single-image calls."""
+    imgs = np.stack([synth.noise_image(240, 320, 100 + i) for i in range(12)])
+    s = _settings(600)
+    ref = hb.ORBExtractor(s)
+    want = [ref(im, None) for im in imgs]
+    ref.close()
+    monkeypatch.setenv("HYORB_KP_BOUND", "100")
+    ex = hb.ORBExtractor(s)
+    assert ex.keypoint_bound(320, 240) == 100
+    kps, desc, counts = ex.extract_batch(imgs, capacity=1024)
+    for i, (k, d) in enumerate(want):
+        assert counts[i] == len(k) and len(k) > 300
+        assert_kps_equal(kps[i, :counts[i]], k, f"image {i}")
+        assert np.array_equal(desc[i, :counts[i]], d)
+    ex.close()
