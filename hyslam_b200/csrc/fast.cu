@@ -94,6 +94,7 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     static_assert(sizeof(uint32_t) * (16 + FT_PH * FT_GP) <= FT_SH * FT_SP + 2 * FT_SH * FT_SW, "the pair words alias score map + list");
     static_assert((FT_SH * FT_SP) % 4 == 0 && FT_SH * FT_SP < 65536, "list alignment / 16-bit list entries");
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(16) FastTile s_tile[2];
     __shared__ uint8_t s_msk[2 * FT_SW + 128];                          // 1 = the left / right / upper / lower neighbour is in the same cell
     uint8_t *const s_cl = s_msk, *const s_cr = s_msk + FT_SW, *const s_ru = s_msk + 2 * FT_SW, *const s_rd = s_msk + 2 * FT_SW + 64;
     __shared__ int s_n, s_ne, s_base;
@@ -108,6 +109,7 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     // pixel box of tile T -> buffer `buf`; issued by one thread, completion lands on s_bar[buf]
     auto issue = [&](int T, int buf) {
         const FastTile t = fast_tile(plan, T);
+        s_tile[buf] = t;         // decoded once by the issuing thread; everybody reads it after the barrier that ends the previous tile
         mbar_arrive_expect_tx(&s_bar[buf], FT_BOXW * FT_PH);
         tma_load_3d(s_pixbuf[buf], t.l == 0 ? &tm0 : &tmaps[t.l], &s_bar[buf], t.x0 & ~15, t.sy0 - 3, img0 + t.b);
     };
@@ -128,7 +130,7 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     const int buf = it & 1;
     // the other buffer was last read before the barrier that ended the previous iteration: refill it now
     if (tid == 0 && T + (int)gridDim.x < nTiles) { fence_proxy_async(); issue(T + gridDim.x, buf ^ 1); }
-    const FastTile tile = fast_tile(plan, T);
+    const FastTile tile = s_tile[buf];
     const int l = tile.l, b = tile.b;
     const LevelDev &L = plan->lv[l];
     const int x0 = tile.x0, sy0 = tile.sy0;
@@ -150,9 +152,15 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     }
     mbar_wait(&s_bar[buf], (it >> 1) & 1);      // the pixel box has landed
 
+    const int xEnd = L.maxBX - 3, yEnd = L.maxBY - 3;     // detect range [19, xEnd) x [19, yEnd)
+    // Partial tiles (bottom / right edge of a level): score rows [rLo, rHi) and region columns [cl, ch) hold detectable pixels.  Pair
+    // words are needed for pixel rows rLo .. rHi+5 (score row r = pixel row r+3 reads the items of pixel rows r .. r+6) and columns
+    // cl-3 .. ch+2, bit planes three rows further: everything else is skipped (whole warps on the short tiles of a level's last row).
+    const int rLo = max(0, DET_MIN - sy0), rHi = min(FT_SH, yEnd - sy0);
+    const int cl = max(3, DET_MIN - x0), ch = min(FT_SW - 3, xEnd - x0);
     // ---- T. bit-plane transposition: thread -> (region row, segment)
-    {
-        const int row = tid / FT_NSEG, seg = tid - row * FT_NSEG;
+    if (const int row = tid / FT_NSEG; row >= rLo - 3 && row <= rHi + 8) {
+        const int seg = tid - row * FT_NSEG;
         const int o = off + 32 * seg;
         const uint32_t *src = (const uint32_t *)(s_pixbuf[buf] + row * PITCHB) + (o >> 2);
         const unsigned sh = (unsigned)(o & 3) * 8;
@@ -171,7 +179,6 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     }
     __syncthreads();
 
-    const int xEnd = L.maxBX - 3, yEnd = L.maxBY - 3;     // detect range [19, xEnd) x [19, yEnd)
     // ---- A. corner test in the paired formulation (fast_bitslice.cuh): warp -> (segment, block of 32 PIXEL rows), lane -> pixel row.
     // A1: every item compares the half ring with dx >= 0 against centre +- 20 (16 ripple compares) and publishes its 16 pair words;
     // A2: the other half of the ring is read back from the items three rows above / below, shifted by the ring's x offsets.
@@ -179,8 +186,8 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     const int a_seg = (tid >> 5) % FT_NSEG, a_pr = ((tid >> 5) / FT_NSEG) * 32 + (tid & 31);
     const int a_r = a_pr - 3;                              // score row of this item (valid: 0 .. FT_SH-1)
     uint32_t Gp[8], Gm[8];
-    bs_pairs<FT_PLP>(s_planes + a_pr * FT_PLP + (a_seg + 1) * 8, Gp, Gm);
-    {
+    if (a_pr >= rLo && a_pr <= rHi + 5 && 32 * a_seg + 31 >= cl - 3 && 32 * a_seg < ch + 3) {
+        bs_pairs<FT_PLP>(s_planes + a_pr * FT_PLP + (a_seg + 1) * 8, Gp, Gm);
         uint2 *gdst = (uint2 *)(s_g + a_pr * FT_GP + a_seg * 16);
 #pragma unroll
         for (int k = 0; k < 8; k++) gdst[k] = make_uint2(Gp[k], Gm[k]);
@@ -189,7 +196,6 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     if (a_r >= 0 && a_r < FT_SH) {
         const int sy = sy0 + a_r;
         // region columns with a full ring [3, 93) that lie in the detect range, restricted to this segment
-        const int cl = max(3, DET_MIN - x0), ch = min(FT_SW - 3, xEnd - x0);
         uint32_t valid = bit_range(cl - 32 * a_seg, ch - 32 * a_seg);
         if (sy < DET_MIN || sy >= yEnd) valid = 0;
         if (valid) flags = bs_corners_paired<FT_GP>(Gp, Gm, s_g + a_pr * FT_GP + a_seg * 16) & valid;
