@@ -91,6 +91,7 @@ struct hyorb_extractor {
     DevBuf d_tmaps, d_tmaps_lv, d_lvtab;
     CUtensorMap h_tmaps[HYORB_MAX_LEVELS], h_tmaps_lv[HYORB_MAX_LEVELS];
     CUtensorMap tm0, tmL0;    // level 0 with the FAST box / with the fused-level box (level.cu)
+    int dl_bound = 0;         // entries per image a large host batch downloads while it runs (= kp_bound; HYORB_KP_BOUND overrides it for tests)
     int kp_bound = 0;         // sum over levels of (quota + 3): the most keypoints DistributeOctTree returns per image (ORBExtractor.cpp:107-290 stops
                               // splitting at the first node count >= quota, one split adds at most 3); host downloads are sized by it
     int fused_levels = 1;     // 1: level.cu (pyramid + blur in one pass per level); 0: pyramid.cu + blur.cu (HYORB_FUSED_LEVELS)
@@ -132,7 +133,8 @@ static int ex_ensure_plan(hyorb_extractor *h, int w, int hgt)
         const int roots = np.dev.lv[l].h > 0 ? np.dev.lv[l].w / np.dev.lv[l].h + 2 : 2;
         h->kp_bound += std::max(h->quota[l] + 3, 4 * roots);
     }
-    if (const char *v = getenv("HYORB_KP_BOUND")) { const int b = atoi(v); if (b > 0) h->kp_bound = b; }   // tests: force the overflow fetch of large host batches
+    h->dl_bound = h->kp_bound;
+    if (const char *v = getenv("HYORB_KP_BOUND")) { const int b = atoi(v); if (b > 0) h->dl_bound = b; }   // tests: force the overflow fetch of large host batches
     h->Bcap = 0;
     return HYORB_OK;
 }
@@ -316,7 +318,7 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
             }
             case 4:
                 HY_TRY(launch_describe(P, dp, blur, sel, selCount, d_kps + (size_t)i0 * capacity, d_desc + (size_t)i0 * capacity * HYORB_DESC_BYTES, capacity,
-                                       d_counts + i0, status, Bk, st, &h->launches));
+                                       d_counts + i0, status, Bk, st, &h->launches, h->kp_bound));
                 if (h->profile) {
                     cudaEvent_t e;
                     if (!h->ev_free.empty()) { e = h->ev_free.back(); h->ev_free.pop_back(); } else HY_CUDA(cudaEventCreate(&e));
@@ -340,7 +342,7 @@ static int ex_run(hyorb_extractor *h, Level0 l0, int B, int w, int hgt, hyorb_ke
                 if (io && !io->defer_results) {
                     // download this lane's results: per image only the first `rows` entries of its capacity-sized block (2-D copies), where
                     // rows = what the quadtree can produce at most for these quotas; ex_fetch_overflow() covers an image that still exceeded it
-                    const size_t rows = (size_t)std::min(capacity, h->kp_bound);
+                    const size_t rows = (size_t)std::min(capacity, h->dl_bound);
                     HY_CUDA(cudaMemcpyAsync(io->counts + i0, d_counts + i0, sizeof(int32_t) * Bk, cudaMemcpyDeviceToHost, st));
                     HY_CUDA(cudaMemcpy2DAsync(io->kps + (size_t)i0 * capacity, sizeof(hyorb_keypoint) * (size_t)capacity, d_kps + (size_t)i0 * capacity,
                                               sizeof(hyorb_keypoint) * (size_t)capacity, sizeof(hyorb_keypoint) * rows, Bk, cudaMemcpyDeviceToHost, st));
@@ -396,7 +398,7 @@ static int ex_download_small(hyorb_extractor *h, const HostIO &io, int B, int ca
 static int ex_fetch_overflow(hyorb_extractor *h, const HostIO &io, int B, int capacity, const hyorb_keypoint *d_kps, const uint8_t *d_desc,
                              const float *d_uR, const float *d_depth)
 {
-    const int rows = std::min(capacity, h->kp_bound);
+    const int rows = std::min(capacity, h->dl_bound);
     bool any = false;
     for (int i = 0; i < B; i++) {
         const int n = std::min(io.counts[i], capacity);
@@ -724,7 +726,7 @@ HYORB_API int hyorb_extractor_keypoint_bound(hyorb_extractor *h, int width, int 
     if (!h) { set_error("null handle"); return HYORB_EINVAL; }
     HY_CUDA(cudaSetDevice(h->device));
     HY_TRY(ex_ensure_plan(h, width, height));
-    return h->kp_bound;
+    return h->dl_bound;
 }
 
 HYORB_API int hyorb_extractor_stage_times(hyorb_extractor *h, double *ms, long *calls, int reset)

@@ -155,7 +155,7 @@ int launch_quadtree(const PlanDev &hp, const PlanDev *dp, const uint32_t *cand, 
                     uint32_t *qcode, uint16_t *qnode, uint2 *qleaf, uint32_t *sel, int *selCount, int *status, int B, cudaStream_t st, long *launches);
 int launch_blur(const PlanDev &hp, const PlanDev *dp, Level0 l0, const uint8_t *pyr, uint8_t *blur, int B, cudaStream_t st, long *launches);
 int launch_describe(const PlanDev &hp, const PlanDev *dp, const uint8_t *blur, const uint32_t *sel, const int *selCount,
-                    hyorb_keypoint *kps, uint8_t *desc, int capacity, int *counts, int *status, int B, cudaStream_t st, long *launches);
+                    hyorb_keypoint *kps, uint8_t *desc, int capacity, int *counts, int *status, int B, cudaStream_t st, long *launches, int max_kps);
 
 // matching / stereo (match.cu, stereo.cu)
 int launch_match_bruteforce(const uint8_t *q, int nq, const uint8_t *t, int nt, int rule, float thr, float ratio,

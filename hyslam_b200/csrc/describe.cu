@@ -95,28 +95,38 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
     // 31 disc rows and the 512 rotated-pattern taps then hit shared memory instead of issuing byte gathers to L1
     __shared__ uint32_t s_patch[DS_WARPS][PT_ROWS * PT_WORDS];
     __shared__ uint32_t s_mask[16][8];
+    __shared__ int s_end[HYORB_MAX_LEVELS + 1];       // s_end[l] = output slots of levels < l (exclusive ends), s_end[nl] = total
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 128) s_mask[threadIdx.x >> 3][threadIdx.x & 7] = disc_mask_word(threadIdx.x >> 3, threadIdx.x & 7);
-    __syncthreads();
     const int b = blockIdx.y;
-    const int k = blockIdx.x * DS_WARPS + warp;
     const int nl = plan->nlevels;
-    // locate output slot k: levels are concatenated in order (ORBExtractor.cpp:523-555).  Lane i holds level i's count;
-    // an inclusive warp scan gives the level boundaries.
-    int cnt = 0;
-    if (lane < nl) { cnt = selCount[b * HYORB_MAX_LEVELS + lane]; cnt = min(cnt, plan->lv[lane].selCap); }
-    int inc = cnt;
+    // locate the output slots: levels are concatenated in order (ORBExtractor.cpp:523-555).  ONE warp of the CTA scans the level counts
+    // (lane i holds level i's count) and publishes the level boundaries; the other warps used to repeat the scan behind its global loads.
+    if (warp == DS_WARPS - 1) {
+        int cnt = 0;
+        if (lane < nl) { cnt = selCount[b * HYORB_MAX_LEVELS + lane]; cnt = min(cnt, plan->lv[lane].selCap); }
+        int inc = cnt;
 #pragma unroll
-    for (int o = 1; o < HYORB_MAX_LEVELS; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
+        for (int o = 1; o < HYORB_MAX_LEVELS; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane < HYORB_MAX_LEVELS) s_end[lane + 1] = inc;      // lanes >= nl add 0: s_end[nl..] = total
+        if (lane == 0) s_end[0] = 0;
     }
-    const int total = __shfl_sync(0xffffffffu, inc, HYORB_MAX_LEVELS - 1);      // lanes >= nl add 0
-    const unsigned below = __ballot_sync(0xffffffffu, lane < nl && inc <= k);    // levels that end at or before slot k
-    const int l = k < total ? __popc(below) : -1;
-    const int j = k - __shfl_sync(0xffffffffu, inc - cnt, l < 0 ? 0 : l);
+    __syncthreads();
+    const int k = blockIdx.x * DS_WARPS + warp;
+    const int total = s_end[nl];
+    int l = -1, j = 0;
+    if (k < total) {
+        l = 0;
+#pragma unroll
+        for (int t = 1; t < HYORB_MAX_LEVELS; t++) l += (t < nl && s_end[t] <= k);       // number of levels that end at or before slot k
+        j = k - s_end[l];
+    }
     if (k == 0 && lane == 0) {
-        if (total > capacity) { atomicOr(status, ST_OUT_OVERFLOW); counts[b] = capacity; }
+        // every slot needs a warp: the grid covers min(capacity, the extractor's keypoint bound) slots (launch_describe)
+        if (total > capacity || total > (int)gridDim.x * DS_WARPS) { atomicOr(status, ST_OUT_OVERFLOW); counts[b] = min(total, capacity); }
         else counts[b] = total;
     }
     if (l < 0 || k >= capacity) return;
@@ -209,7 +219,7 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
 }
 
 int launch_describe(const PlanDev &hp, const PlanDev *dp, const uint8_t *blur, const uint32_t *sel, const int *selCount,
-                    hyorb_keypoint *kps, uint8_t *desc, int capacity, int *counts, int *status, int B, cudaStream_t st, long *launches)
+                    hyorb_keypoint *kps, uint8_t *desc, int capacity, int *counts, int *status, int B, cudaStream_t st, long *launches, int max_kps)
 {
     // the float copy of the pattern is filled once per device; the mutex blocks concurrent first callers (the reference
     // runs the left and the right extractor on two threads) until the table is complete
@@ -229,7 +239,10 @@ int launch_describe(const PlanDev &hp, const PlanDev *dp, const uint8_t *blur, c
             pattern_ready[dev] = true;
         }
     }
+    // one warp per output slot: at most min(capacity, what the quadtree can produce for these quotas (max_kps; 0 = unknown), the leaf
+    // capacity); the kernel reports ST_OUT_OVERFLOW if an image ever produced more than the grid covers
     int slots = hp.selTotalCap < capacity ? hp.selTotalCap : capacity;
+    if (max_kps > 0 && max_kps < slots) slots = max_kps;
     if (slots < 1) slots = 1;
     dim3 grd((slots + DS_WARPS - 1) / DS_WARPS, B);
     k_describe<<<grd, DS_WARPS * 32, 0, st>>>(dp, blur, sel, selCount, kps, desc, capacity, counts, status);
