@@ -142,18 +142,22 @@ k_describe(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ blur, c
     {
         // lanes 0..29 cover 3 rows x 10 words per step; all 13 loads are issued before the first store
         const int lr = lane / PT_WORDS, wd = lane - lr * PT_WORDS;
-        const uint32_t *src = (const uint32_t *)(level + (size_t)(py - PT_R + lr) * pitch + gx0) + wd;
-        const size_t step = (size_t)3 * pitch / 4;
+        // 32-bit word offsets from ONE 64-bit base (a level is far below 2^31 words): one IMAD.WIDE per load instead of 64-bit pointer chains
+        const uint32_t *base = (const uint32_t *)(level + gx0);
+        const int pw = pitch >> 2;                               // pitch is a multiple of 16
+        const int o0 = (py - PT_R + lr) * pw + wd;
+        const bool act = lane < 30;
         uint32_t v[13];
 #pragma unroll
         for (int t = 0; t < 13; t++) {
             const int r = 3 * t + lr;
-            v[t] = (lane < 30 && r < PT_ROWS) ? __ldg(src + t * step) : 0u;
+            v[t] = (act && r < PT_ROWS) ? __ldg(base + (o0 + 3 * t * pw)) : 0u;
         }
+        uint32_t *dstw = patch + lr * PT_WORDS + wd;
 #pragma unroll
         for (int t = 0; t < 13; t++) {
             const int r = 3 * t + lr;
-            if (lane < 30 && r < PT_ROWS) patch[r * PT_WORDS + wd] = v[t];
+            if (act && r < PT_ROWS) dstw[3 * t * PT_WORDS] = v[t];
         }
     }
     __syncwarp();
