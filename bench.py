@@ -552,7 +552,7 @@ def main():
         step_device(args.warmup + i)
     stage_ms, stage_calls = ex.stage_times(reset=True)
     ex.set_profiling(False)
-    ex.set_pipelining(device_lanes=int(os.environ.get("HYORB_LANES", "2")), side_blur=int(os.environ.get("HYORB_SIDE_BLUR", "2")),
+    ex.set_pipelining(device_lanes=int(os.environ.get("HYORB_LANES", "3")), side_blur=int(os.environ.get("HYORB_SIDE_BLUR", "2")),
                       host_lanes=int(os.environ.get("HYORB_HOST_LANES", "-1")))
 
     # ---- end to end through the host-buffer ABI call (pinned host in, host out).  Each call is synchronous (uploads, kernels
