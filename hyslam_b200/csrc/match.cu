@@ -72,12 +72,14 @@ k_bf_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, i
     const int q0 = (blockIdx.x * BF_THREADS + threadIdx.x) * BF_QPT;
     const int t0 = blockIdx.y * chunk, t1 = min(t0 + chunk, nt);
     uint4 a0[BF_QPT], a1[BF_QPT];
-    uint32_t bkey[BF_QPT]; int second[BF_QPT];
+    // running smallest and second-smallest KEY (distance << 22 | target): three min / max per distance, no branch; the second-best
+    // distance of the rules (counted with multiplicity, like the reference's best / second-best update) is the second key's distance
+    uint32_t bkey[BF_QPT], skey[BF_QPT];
 #pragma unroll
     for (int k = 0; k < BF_QPT; k++) {
         a0[k] = a1[k] = make_uint4(0, 0, 0, 0);
         if (q0 + k < nq) { a0[k] = q[2 * (size_t)(q0 + k)]; a1[k] = q[2 * (size_t)(q0 + k) + 1]; }
-        bkey[k] = KEY_NONE; second[k] = DIST_NONE;
+        bkey[k] = KEY_NONE; skey[k] = KEY_NONE;
     }
     for (int base = t0; base < t1; base += BF_TILE) {
         const int cnt = min(BF_TILE, t1 - base);
@@ -88,14 +90,18 @@ k_bf_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, i
         for (int j = 0; j < cnt; j++) {
             const uint4 b0 = s_t[2 * j], b1 = s_t[2 * j + 1];
 #pragma unroll
-            for (int k = 0; k < BF_QPT; k++) scan_update(bkey[k], second[k], hamming256(a0[k], a1[k], b0, b1), (uint32_t)(base + j));
+            for (int k = 0; k < BF_QPT; k++) {
+                const uint32_t key = ((uint32_t)hamming256(a0[k], a1[k], b0, b1) << POS_BITS) + (uint32_t)(base + j);
+                skey[k] = min(skey[k], max(bkey[k], key));
+                bkey[k] = min(bkey[k], key);
+            }
         }
     }
 #pragma unroll
     for (int k = 0; k < BF_QPT; k++)
         if (q0 + k < nq) {
             pkey[(size_t)blockIdx.y * nq + q0 + k] = bkey[k];
-            psecond[(size_t)blockIdx.y * nq + q0 + k] = (uint16_t)second[k];
+            psecond[(size_t)blockIdx.y * nq + q0 + k] = (uint16_t)min(skey[k] >> POS_BITS, (uint32_t)DIST_NONE);
         }
 }
 
