@@ -851,7 +851,7 @@ static int m_upload(hyorb_matcher *m, DevBuf &buf, const void *src, size_t bytes
 static int bf_splits(int nq, int nt)
 {
     // enough CTAs to fill 148 SMs a few times over, without slicing the target list below one smem tile
-    const int qblocks = (nq + 255) / 256;      // k_bf_partial: 128 threads x 2 queries
+    const int qblocks = (nq + bf_queries_per_cta() - 1) / bf_queries_per_cta();      // k_bf_partial: 128 threads x BF_QPT queries
     int s = (148 * 8 + qblocks - 1) / qblocks;
     const int maxs = std::max(1, nt / 128);
     return std::max(1, std::min(s, std::min(maxs, 64)));

@@ -196,6 +196,7 @@ int launch_bow_match(const uint8_t *desc1, const uint8_t *mask1, const int32_t *
                      const int32_t *node2, int n2, int32_t *iota, int32_t *sorted_node2, int32_t *sorted_idx2, void *temp, size_t temp_bytes,
                      int32_t *cbegin, int32_t *cend, int rule, float thr, float ratio, int32_t *best_idx, uint16_t *best, uint16_t *second,
                      uint8_t *accepted, const EpipolarDev &epi, cudaStream_t st, long *launches);
+int bf_queries_per_cta();
 int launch_distinctive(const uint8_t *desc, const int32_t *off, int n_lm, int32_t *best_idx, int32_t *best_median, cudaStream_t st, long *launches);
 // rows_budget: row-table entries per right keypoint the scratch is sized for (stereo_rows_budget(largest keypoint size, size_ref); 0 = default 20)
 int stereo_rows_budget(float max_kp_size, float size_ref);

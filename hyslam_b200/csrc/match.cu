@@ -63,7 +63,11 @@ __device__ __forceinline__ void write_result(int q, uint32_t bkey, int second, i
 constexpr int BF_THREADS = 128, BF_TILE = 128;
 
 // Two queries per thread: a target's two 128-bit shared-memory loads and its position bookkeeping are shared by two distances.
-constexpr int BF_QPT = 2;
+#ifndef HYORB_BF_QPT
+#define HYORB_BF_QPT 2
+#endif
+constexpr int BF_QPT = HYORB_BF_QPT;
+int bf_queries_per_cta() { return BF_THREADS * BF_QPT; }
 __global__ void __launch_bounds__(BF_THREADS)
 k_bf_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, int chunk,
              uint32_t *__restrict__ pkey, uint16_t *__restrict__ psecond)
