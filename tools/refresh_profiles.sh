@@ -6,7 +6,8 @@ tag=${1:-r2f}
 cp gpurun_out/${tag}_bench.json profiles/${tag}_bench.json
 cp gpurun_out/${tag}_bench_reference.json profiles/
 cp gpurun_out/${tag}_launches.csv profiles/
-python tools/ncu_summary.py launches profiles/${tag}_launches.csv > profiles/${tag}_launches.txt
+( python tools/ncu_summary.py launches profiles/${tag}_launches.csv; echo
+  python tools/ncu_summary.py launches profiles/${tag}_launches.csv 0 84 "[launches 0-83 of the library = warm-up + timed device-resident steps of bench.py: 6 steps x 14 kernels over 256 images, 1 lane -- the launches the bench's stage times describe]" ) > profiles/${tag}_launches.txt
 for k in k_fast k_level k_describe k_quadtree k_stereo_search; do
   python tools/ncu_summary.py full gpurun_out/${tag}_$k.ncu-rep > profiles/${tag}_${k}_full.txt
   ncu -i gpurun_out/${tag}_$k.ncu-rep --page raw --csv 2>/dev/null | python -c "
