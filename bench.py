@@ -722,7 +722,7 @@ def main():
 
     # ---- CPU baseline: the reference's own code on all host threads, bounded sample (kind "reference"; "port" without _ref)
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:        # the CPU arm is timed at N = 1 only (rank 0); multi-GPU lines carry cpu_baseline = null
         os.sched_setaffinity(0, full_affinity)        # the GPU legs ran on the GPU's NUMA node; the CPU arm gets every host thread
         cores = len(os.sched_getaffinity(0))
         sample_pairs = max(1, min(P, cores))
