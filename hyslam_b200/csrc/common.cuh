@@ -98,7 +98,7 @@ struct PlanDev {
     LevelDev lv[HYORB_MAX_LEVELS];
 };
 
-struct ResizeTab { int ofs; short c0, c1; };   // source index + Q11 coefficients of one destination row/column
+struct __align__(8) ResizeTab { int ofs; short c0, c1; };   // source index + Q11 coefficients of one destination row/column
 
 // where level 0 lives for the current batch
 struct Level0 {

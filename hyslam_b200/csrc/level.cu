@@ -110,30 +110,41 @@ k_level(const PlanDev *__restrict__ plan, int l, const __grid_constant__ CUtenso
     const int tilesX = L.lvTilesX, perImage = L.lvTilesX * L.lvTilesY;
     const CUtensorMap *tm = l == 0 ? &tm0 : &tmaps[l];
     const long long gw = (long long)blockIdx.x * LV_WARPS + warp, nw = (long long)gridDim.x * LV_WARPS;
-    auto issue = [&](int T, int buf) {
-        const int b = T / perImage, r = T - b * perImage;
-        const int ty = r / tilesX, tx = r - ty * tilesX;
-        mbar_arrive_expect_tx(&bars[buf], LV_BOX);
-        tma_load_3d(boxes + buf * LV_BUF, tm, &bars[buf], tx * LV_TW - LV_HX, ty * LV_TH - LV_HY, img0 + b);
+    // Tile coordinates advance incrementally (a tile index -> (image, tile row, tile column) decode costs two integer divisions, ~80
+    // instructions, and a warp visits a tile every ~3000): `cur` is the tile being processed, `pre` the one being prefetched.
+    struct TileId { int b, ty, tx; };
+    const int tilesY = L.lvTilesY;
+    auto decode = [&](long long T) { TileId t; t.b = (int)(T / perImage); const int r = (int)(T - (long long)t.b * perImage); t.ty = r / tilesX; t.tx = r - t.ty * tilesX; return t; };
+    const TileId step = decode(nw);
+    auto advance = [&](TileId &t) {
+        t.tx += step.tx; if (t.tx >= tilesX) { t.tx -= tilesX; t.ty++; }
+        t.ty += step.ty; if (t.ty >= tilesY) { t.ty -= tilesY; t.b++; }
+        t.b += step.b;
     };
+    auto issue = [&](const TileId &t, int buf) {
+        mbar_arrive_expect_tx(&bars[buf], LV_BOX);
+        tma_load_3d(boxes + buf * LV_BUF, tm, &bars[buf], t.tx * LV_TW - LV_HX, t.ty * LV_TH - LV_HY, img0 + t.b);
+    };
+    TileId cur = decode(gw), pre = cur;
     if (lane == 0) {
         for (int k = 0; k < LV_NBUF; k++) mbar_init(&bars[k], 1);
         mbar_fence_init();
         fence_proxy_async();
         if (l > 0) tensormap_acquire(tm);
-        for (int k = 0; k < LV_NBUF - 1; k++)
-            if (gw + k * nw < nTiles) issue((int)(gw + k * nw), k);
+    }
+    for (int k = 0; k < LV_NBUF - 1; k++) {            // `pre` ends LV_NBUF - 1 tiles ahead of `cur` on every lane
+        if (lane == 0 && gw + k * nw < nTiles) issue(pre, k);
+        advance(pre);
     }
     __syncwarp();
 
     const int w = L.w, h = L.h;
     int it = 0;
-    for (long long TT = gw; TT < nTiles; TT += nw, it++) {
-        const int T = (int)TT, buf = it % LV_NBUF;
+    for (long long TT = gw; TT < nTiles; TT += nw, it++, advance(cur), advance(pre)) {
+        const int buf = it % LV_NBUF;
         // buffer (it - 1) % LV_NBUF was released by the __syncwarp that ended the previous iteration: refill it with the tile LV_NBUF - 1 ahead
-        if (lane == 0 && TT + (LV_NBUF - 1) * nw < nTiles) { fence_proxy_async(); issue((int)(TT + (LV_NBUF - 1) * nw), (it + LV_NBUF - 1) % LV_NBUF); }
-        const int b = T / perImage, rem = T - b * perImage;
-        const int ty = rem / tilesX, tx = rem - ty * tilesX;
+        if (lane == 0 && TT + (LV_NBUF - 1) * nw < nTiles) { fence_proxy_async(); issue(pre, (it + LV_NBUF - 1) % LV_NBUF); }
+        const int b = cur.b, ty = cur.ty, tx = cur.tx;
         const int X0 = tx * LV_TW, Y0 = ty * LV_TH;
         uint8_t *box = boxes + buf * LV_BUF;            // box(0,0) = image (X0 - 16, Y0 - 3)
         mbar_wait(&bars[buf], (it / LV_NBUF) & 1);
@@ -190,6 +201,7 @@ k_level(const PlanDev *__restrict__ plan, int l, const __grid_constant__ CUtenso
             const ResizeTab *tabx = tabs + D.rsX;
             const int dw = D.w;
             const int dxa = lvtab[L.lvDx + tx], dxb = lvtab[L.lvDx + tx + 1];
+            const int dya = lvtab[L.lvDy + ty];             // first destination row of this tile; the rows it emits are dya, dya + 1, ...
             const int sEnd = min(Y0 + LV_TH, h - 1);
             uint8_t *dimg = pyr + (size_t)b * plan->pyrStride + D.off;
             const int dpitch = D.pitch;
@@ -210,7 +222,7 @@ k_level(const PlanDev *__restrict__ plan, int l, const __grid_constant__ CUtenso
                 const bool full = x4 + 3 < dw;
                 const uint8_t *brow = box + LV_HY * LV_BW;                       // box row of source row Y0
                 const ResizeTab *ti = tabs + D.rsInv + Y0 + 1;                  // entry of source row s: the destination row whose taps are (s-1, s)
-                uint8_t *dcol = dimg + x4;
+                uint8_t *d = dimg + (size_t)dya * dpitch + x4;
                 auto emit = [&](const ResizeTab e, const LvH &h0, const LvH &h1) {
                     if (e.ofs < 0) return;                                      // warp-uniform: no destination row ends on this source row
                     const uint32_t b0 = (uint32_t)(uint16_t)e.c0 << 16, b1 = (uint32_t)(uint16_t)e.c1 << 16;
@@ -219,9 +231,9 @@ k_level(const PlanDev *__restrict__ plan, int l, const __grid_constant__ CUtenso
                     for (int j = 0; j < 4; j++) v[j] = __umulhi(b0, h0.h[j]) + __umulhi(b1, h1.h[j]) + 2u;      // <= 1023; the result is v >> 2
                     const uint32_t p01 = (v[0] | (v[1] << 16)) >> 2, p23 = (v[2] | (v[3] << 16)) >> 2;
                     const uint32_t o = __byte_perm(p01, p23, 0x6420);
-                    uint8_t *d = dcol + (size_t)e.ofs * dpitch;
                     if (full) *(uint32_t *)d = o;
                     else for (int j = 0; x4 + j < dw; j++) d[j] = (uint8_t)(o >> (8 * j));
+                    d += dpitch;
                 };
                 LvH hA = lv_hrow(brow, so, shf, sel, c01), hB;
                 ResizeTab e = ti[0];
