@@ -23,7 +23,7 @@
 //   B. corner bits are compacted into the CTA's list (warp scan + one shared-memory atomic per warp; rows interleaved two apart
 //      so that the byte gathers of C and D spread over the banks);
 //   C. scores are computed only for the listed corners with 3-input integer min/max (VIMNMX3);
-//   D. cell-local 3x3 NMS (branch-free) and a CTA-aggregated emit.
+//   D. cell-local 3x3 NMS (branch-free); every warp stages its survivors and appends them to the level's list with one atomic.
 #include <algorithm>
 #include <atomic>
 
@@ -41,12 +41,13 @@ __device__ __forceinline__ constexpr int ring_off(int k)
     return dy[k] * FT_BOXW + dx[k];
 }
 
-constexpr int EMIT_CAP = 2048;                 // NMS survivors of one tile: (FT_OW/2+1)*(FT_OH/2+1) = 1305 plus adjacent pairs across cell edges
+constexpr int EMIT_W = 512;                    // staging entries per warp: a tile has at most (FT_OW/2+1)*(FT_OH/2+1) = 1305 NMS survivors plus adjacent pairs across
+                                               // cell edges, spread over the six warps by list position; a warp that still exceeded its segment is reported
 constexpr int PITCHB = FT_BOXW;                // box row stride in bytes
 constexpr int FT_BUF_BYTES = (FT_BOXW * FT_PH + 127) & ~127;   // one pixel buffer, 128-byte aligned for TMA
 constexpr int FT_PLP = 8 * (FT_NSEG + 2) + 4;  // plane row pitch in words: an all-zero segment either side, +4 so that the 128-bit
                                                // loads of 8 consecutive rows hit disjoint banks
-static_assert(EMIT_CAP * 4 <= FT_PH * FT_PLP * 4, "the emit staging aliases the plane buffer");
+static_assert(EMIT_W * (FT_THREADS / 32) <= (FT_PH + 6) * FT_PLP, "the emit staging aliases the plane buffer (slack rows included)");
 constexpr int FT_SP = FT_BOXW;                 // score-map row pitch = pixel-box row pitch (28 words): a list entry indexes both, and the rows r, r+2, r+4, r+6 a
                                                // warp's 32 list entries come from (see phase B) start 8 banks apart -- their byte gathers do not collide
 constexpr int FT_GP = 16 * FT_NSEG + 2;        // pair-word buffer: row pitch in words (+2: the 64-bit accesses of 16 consecutive rows hit disjoint banks)
@@ -97,9 +98,9 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     __shared__ __align__(16) FastTile s_tile[2];
     __shared__ uint8_t s_msk[2 * FT_SW + 128];                          // 1 = the left / right / upper / lower neighbour is in the same cell
     uint8_t *const s_cl = s_msk, *const s_cr = s_msk + FT_SW, *const s_ru = s_msk + 2 * FT_SW, *const s_rd = s_msk + 2 * FT_SW + 64;
-    __shared__ int s_n, s_ne, s_base;
+    __shared__ int s_n;
     uint32_t *const s_planes = s_planes_all + 3 * FT_PLP;
-    uint32_t *s_emit = s_planes;            // the planes are dead once the corner test is done
+    uint32_t *s_emit = s_planes_all;        // the planes are dead once the corner test is done
     uint8_t *const s_score = s_sl;
     uint16_t *const s_list = (uint16_t *)(s_sl + FT_SH * FT_SP);
     uint32_t *const s_g = (uint32_t *)s_sl + 16;
@@ -137,7 +138,7 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     const int off = x0 & 15;                                // byte position of region column 0 inside the box
     const uint8_t *pix8 = s_pixbuf[buf] + off;              // region, row pitch PITCHB
 
-    if (tid == 0) { s_n = 0; s_ne = 0; }
+    if (tid == 0) s_n = 0;
     if (tid < FT_SW) {
         const int x = x0 + tid;                              // columns left of x = 19 are never emitted
         const int m = x >= DET_MIN ? (x - DET_MIN) % L.wCell : 1;
@@ -266,6 +267,8 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
     __syncthreads();
 
     // ---- D. cell-local 3x3 NMS over the interior, stage survivors (s_emit aliases the plane buffer)
+    const int wbase = (tid >> 5) * EMIT_W;
+    int wn = 0;
     for (int i0 = 0; i0 < ncorner; i0 += FT_THREADS) {      // warp-uniform trip count: the ballot below needs all lanes
         const int i = i0 + tid;
         // branch-free: the eight neighbour scores are fetched together (independent loads, every address stays inside
@@ -283,30 +286,23 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         const int m2 = __vimax3_s32(ndl * (Dk * Lk), ndr * (Dk * Rk), m0);
         const bool kept = inner && s > max(m1, m2);
         const uint32_t packed = pack_cand(x0 + cidx - LATTICE_MIN, sy0 + r - LATTICE_MIN, s);
+        // survivors go to the WARP's own staging segment (count in a warp-uniform register: no shared-memory atomic, no CTA barrier)
         const unsigned bal = __ballot_sync(0xffffffffu, kept);
         if (bal) {
-            const int lane = tid & 31;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_ne, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const int pos = base + __popc(bal & ((1u << lane) - 1));
-            if (kept && pos < EMIT_CAP) s_emit[pos] = packed;
+            const int pos = wn + __popc(bal & ((1u << (tid & 31)) - 1));
+            if (kept && pos < EMIT_W) s_emit[wbase + pos] = packed;
+            wn += __popc(bal);
         }
     }
-    __syncthreads();
-    int ne = s_ne;
-    if (ne > 0) {       // CTA-uniform
-        int *cnt = candCount + b * HYORB_MAX_LEVELS + l;
-        if (tid == 0) {
-            if (ne > EMIT_CAP) { atomicOr(status, ST_CAND_OVERFLOW); }
-            s_base = atomicAdd(cnt, min(ne, EMIT_CAP));
-        }
-        __syncthreads();
-        ne = min(ne, EMIT_CAP);
-        const int base = s_base;
+    if (wn > 0) {       // warp-uniform: the warp reserves its range of the level's candidate list and copies its segment out
+        const int lane = tid & 31;
+        if (wn > EMIT_W) { if (lane == 0) atomicOr(status, ST_CAND_OVERFLOW); wn = EMIT_W; }
+        int base = 0;
+        if (lane == 0) base = atomicAdd(candCount + b * HYORB_MAX_LEVELS + l, wn);
+        base = __shfl_sync(0xffffffffu, base, 0);
         uint32_t *out = cand + (size_t)b * plan->candStride + L.candOff;
-        for (int i = tid; i < ne; i += FT_THREADS) {
-            if (base + i < L.candCap) out[base + i] = s_emit[i];
+        for (int i = lane; i < wn; i += 32) {
+            if (base + i < L.candCap) out[base + i] = s_emit[wbase + i];
             else atomicOr(status, ST_CAND_OVERFLOW);
         }
     }
