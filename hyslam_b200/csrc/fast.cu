@@ -300,6 +300,7 @@ k_fast(const PlanDev *__restrict__ plan, const __grid_constant__ CUtensorMap tm0
         int base = 0;
         if (lane == 0) base = atomicAdd(candCount + b * HYORB_MAX_LEVELS + l, wn);
         base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();            // the staged entries of the other lanes
         uint32_t *out = cand + (size_t)b * plan->candStride + L.candOff;
         for (int i = lane; i < wn; i += 32) {
             if (base + i < L.candCap) out[base + i] = s_emit[wbase + i];
