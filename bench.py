@@ -718,7 +718,7 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom] * B, "launch_ms": dom_ms,
                 "timing": f"CUDA events on the launching stream, {ksteps} steps with the kernels serialised (1 lane, no side stream)",
-                "note": "integer-logic kernel: ncu shows its shared-memory pipe 73 % and ALU pipe 56 % busy at 58 % issue, DRAM 2 % (profiles/r2h_k_fast_full.txt); reported against the HBM roofline as the contract asks; DESIGN.md section 4"}
+                "note": "integer-logic kernel: ncu shows its shared-memory pipe 73 % and ALU pipe 57 % busy at 59 % issue, DRAM 2 % (profiles/r2i_k_fast_full.txt); reported against the HBM roofline as the contract asks; DESIGN.md section 4"}
 
     # ---- CPU baseline: the reference's own code on all host threads, bounded sample (kind "reference"; "port" without _ref)
     cpu = None
