@@ -578,13 +578,17 @@ def main():
     dt1 = time.perf_counter() - t0
 
     n_workers = max(1, args.e2e_workers)
+    # several handles overlap each other's copies and kernels already: each then runs best with fewer, larger lanes (measured 2 handles
+    # x 4 / 6 / 8 / 12 lanes: 46.7k / 46.3k / 45.8k / 45.3k pairs/s; one handle alone: 33.2k / 34.7k / 35.8k / 35.8k)
+    mt_lanes = int(os.environ.get("HYORB_HOST_LANES", "4" if n_workers > 1 else "-1"))
+    ex.set_pipelining(host_lanes=mt_lanes)
     workers = [(ex, outs)]
     keep = []
     for _ in range(n_workers - 1):
         o2, k2 = make_outs()
         keep.append(k2)
         workers.append((hb.ORBExtractor(hb.FeatureExtractorSettings(nFeatures=NFEAT), device=local), o2))
-        workers[-1][0].set_pipelining(host_lanes=int(os.environ.get("HYORB_HOST_LANES", "-1")))
+        workers[-1][0].set_pipelining(host_lanes=mt_lanes)
     for exw, ow in workers[1:]:
         exw.process_stereo_batch(h_in, cam, capacity=cap, out=ow)          # allocate its workspace outside the timed region
     start = threading.Barrier(n_workers + 1)
@@ -737,7 +741,8 @@ def main():
                          f"per-step intermediates ({B} pyramids + blurred copies) also exceed L2"},
         "kpts_per_sec": value * kp_per_step / P, "keypoints_per_frame": kp_per_step / P, "stereo_matches_per_frame": matched / P,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h, "steps": n_workers * e2e_steps,
-                "api": f"hyorb_process_stereo_batch_host (pinned host buffers in and out), {n_workers} host threads with one extractor handle each",
+                "api": f"hyorb_process_stereo_batch_host (pinned host buffers in and out), {n_workers} host threads with one extractor handle each"
+                       + (f", {mt_lanes} lanes per call (hyorb_extractor_set_pipelining)" if mt_lanes > 0 else ""),
                 "single_handle_value": e2e_single, "per_rank_link_GBps": per_rank_gbs, "host_affinity": affinity},
         "sustained": sustained, "digest": digest,
         "gpu_launches": int(launches), "roofline": roofline, "stages": stages, "c4_match": c4, "other_configs": others, "cpu_baseline": cpu, "clocks": clocks,
