@@ -83,6 +83,7 @@ struct LevelDev {
     int qtMaxN;               // power of two >= 4*quota: node arrays of the quadtree kernel
     unsigned mulW, mulH;      // ceil(2^20 / wCell), ceil(2^20 / hCell): exact division of a lattice coordinate (< 4096) by the cell size
     int lvTilesX, lvTilesY;   // fused pyramid + blur tiles of this level (level.cu)
+    int lvCol;                // offset (in ints, a multiple of 4) of the per-destination-group column constants of level l+1 in the level-tile table
     int lvDx, lvDy;           // offsets into the level-tile table: first destination column / row of level l+1 owned by each tile column / row
     int rsInv, lvFused;       // this level as a DESTINATION of level.cu: resize-table offset of the source-row -> destination-row map; 0 = use k_resize
 };

@@ -198,7 +198,6 @@ k_level(const PlanDev *__restrict__ plan, int l, const __grid_constant__ CUtenso
             // The warp walks the SOURCE rows Y0 .. Y0+20 once (horizontal pass of each: PRMT + DP2A on the lane's 4 destination columns) and
             // emits a destination row whenever its second tap row has just been computed (tinv: source row -> destination row + weights).
             const LevelDev &D = plan->lv[l + 1];
-            const ResizeTab *tabx = tabs + D.rsX;
             const int dw = D.w;
             const int dxa = lvtab[L.lvDx + tx], dxb = lvtab[L.lvDx + tx + 1];
             const int dya = lvtab[L.lvDy + ty];             // first destination row of this tile; the rows it emits are dya, dya + 1, ...
@@ -207,16 +206,12 @@ k_level(const PlanDev *__restrict__ plan, int l, const __grid_constant__ CUtenso
             const int dpitch = D.pitch;
             for (int g = (dxa >> 2) + lane; 4 * g < dxb; g += 32) {
                 const int x4 = 4 * g;
-                int s0 = 0;
-                uint32_t sel[4], c01[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const ResizeTab t = tabx[min(x4 + j, dw - 1)];
-                    if (j == 0) s0 = t.ofs;
-                    const uint32_t dlt = (uint32_t)(t.ofs - s0);
-                    sel[j] = dlt | ((dlt + 1) << 4);
-                    c01[j] = (uint32_t)(uint16_t)t.c0 | ((uint32_t)(uint16_t)t.c1 << 16);
-                }
+                // column constants of this 4-pixel destination group, precomputed on the host (level_tiles): first source column, the
+                // byte selectors of the four tap pairs relative to it, the four Q11 coefficient pairs
+                const uint4 *ce = (const uint4 *)(lvtab + L.lvCol) + 3 * (size_t)g;
+                const uint4 e0 = ce[0], e1 = ce[1], e2 = ce[2];
+                const int s0 = (int)e0.x;
+                const uint32_t sel[4] = {e0.y, e0.z, e0.w, e1.x}, c01[4] = {e1.y, e1.z, e1.w, e2.x};
                 const int so = s0 - (X0 - LV_HX);                               // box column of the first tap
                 const unsigned shf = (unsigned)(so & 3) * 8;
                 const bool full = x4 + 3 < dw;
@@ -317,6 +312,21 @@ void level_tiles(HostPlan *plan)
         for (int t = 0, d = 0; t <= L.lvTilesX; t++) {
             while (d < D.w && tx[d].ofs < t * LV_TW) d++;
             plan->lvtab.push_back(t == L.lvTilesX ? D.w : d);
+        }
+        // per destination 4-pixel group: {s0, sel[4], c01[4]} padded to 12 words, 16-byte aligned
+        while (plan->lvtab.size() % 4) plan->lvtab.push_back(0);
+        L.lvCol = (int)plan->lvtab.size();
+        for (int x4 = 0; x4 < D.w; x4 += 4) {
+            int ent[12] = {0};
+            const int s0 = tx[x4].ofs;
+            ent[0] = s0;
+            for (int j = 0; j < 4; j++) {
+                const ResizeTab t = tx[std::min(x4 + j, D.w - 1)];
+                const unsigned dlt = (unsigned)(t.ofs - s0);
+                ent[1 + j] = (int)(dlt | ((dlt + 1) << 4));
+                ent[5 + j] = (int)((uint32_t)(uint16_t)t.c0 | ((uint32_t)(uint16_t)t.c1 << 16));
+            }
+            for (int k = 0; k < 12; k++) plan->lvtab.push_back(ent[k]);
         }
         L.lvDy = (int)plan->lvtab.size();
         for (int t = 0, d = 0; t <= L.lvTilesY; t++) {
