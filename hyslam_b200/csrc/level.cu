@@ -246,6 +246,7 @@ k_level(const PlanDev *__restrict__ plan, int l, const __grid_constant__ CUtenso
                 }
             }
         }
+        fence_proxy_async();  // edge tiles wrote into the box (lv_reflect_box): order those generic-proxy stores before the TMA write that reuses it
         __syncwarp();         // the box is free for the load after next
     }
 }
