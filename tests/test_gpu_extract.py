@@ -200,3 +200,20 @@ def test_large_host_batch_fetches_what_exceeds_the_download_bound(monkeypatch):
         assert_kps_equal(kps[i, :counts[i]], k, f"image {i}")
         assert np.array_equal(desc[i, :counts[i]], d)
     ex.close()
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("nl,sf,h,w,nf", [(1, 1.2, 240, 320, 300),      # a single level: nothing to resize
+                                          (3, 2.0, 480, 640, 500),      # exact 2x: cv::resize's INTER_AREA shortcut (k_resize) between fused levels
+                                          (4, 1.05, 300, 400, 400),     # more than 32 destination groups per 128-pixel tile column
+                                          (2, 1.999, 400, 600, 300)])   # the widest tap spread the resize supports
+def test_level_kernel_edge_pyramids(nl, sf, h, w, nf, fused, monkeypatch):
+    monkeypatch.setenv("HYORB_FUSED_LEVELS", str(fused))
+    img = synth.noise_image(h, w, 5)
+    s = hb.FeatureExtractorSettings(nFeatures=nf, fScaleFactor=sf, nLevels=nl)
+    ok, od = O.extract(img, O.default_params(nf, sf, nl, 30))
+    ex = hb.ORBExtractor(s)
+    k, d = ex(img, None)
+    assert_kps_equal(k, ok, "keypoints")
+    assert np.array_equal(d, od)
+    ex.close()
