@@ -217,3 +217,22 @@ def test_level_kernel_edge_pyramids(nl, sf, h, w, nf, fused, monkeypatch):
     assert_kps_equal(k, ok, "keypoints")
     assert np.array_equal(d, od)
     ex.close()
+
+
+@pytest.mark.parametrize("name", ["binary_noise", "checker2", "dots4", "sparse_dots"])
+def test_adversarial_textures_match_oracle(name):
+    """High-frequency synthetic textures at C2 size: up to 26k NMS survivors on one level (5.5 % of its pixels), levels with no corner
+    at all, dense isolated peaks -- the candidate capacity, the per-warp survivor staging of k_fast and the quadtree's early exits."""
+    h, w = 376, 1241
+    rng = np.random.default_rng(3)
+    yy, xx = np.arange(h)[:, None], np.arange(w)[None, :]
+    img = {"binary_noise": lambda: (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8),
+           "checker2": lambda: (((yy // 2 + xx // 2) % 2) * 255).astype(np.uint8),
+           "dots4": lambda: np.where((yy % 4 == 0) & (xx % 4 == 0), 255, 0).astype(np.uint8),
+           "sparse_dots": lambda: np.where(rng.random((h, w)) < 0.03, 255, 30).astype(np.uint8)}[name]()
+    ok, od = O.extract(img, _oparams(_settings(2000)))
+    ex = hb.ORBExtractor(_settings(2000))
+    k, d = ex(img, None)
+    assert_kps_equal(k, ok, name)
+    assert np.array_equal(d, od)
+    ex.close()
