@@ -13,8 +13,12 @@
  * tree).  The reference has no tests or golden vectors of its own on this path.  The
  * third-party arithmetic underneath (OpenCV: resize / GaussianBlur / FAST / fastAtan2 / gemm) is pinned
  * bit-for-bit against cv2 4.13 in tests/test_oracle_vs_cv2.py and tests/test_cvshim_vs_cv2.py.
- * Still unpinned (no reference code executed): the matcher rows (criteria, window query, projection) --
- * see DESIGN.md section 2 -- and the BoW rows (DBoW2 is absent).
+ * The matcher rows (criteria, grid / window query, projection x4, triangulation gate, Fuse, SearchBySim3,
+ * SearchForInitialization) are pinned the same way: oracle/_ref also compiles FeatureMatcher.cc, MatchCriteria.cpp,
+ * Frame.cc, KeyFrame.cc, MapPoint.cc, Camera.cpp and LandMarkMatches.cpp unmodified, and
+ * tests/test_oracle_match_vs_ref.py compares what a hySLAM caller observes after each call.
+ * Still unpinned (no reference code can be executed): BoW quantisation -- DBoW2 and the ORB vocabulary are not in the
+ * reference tree.
  *
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  * Compile with -ffp-contract=off: the reference is an x86-64 baseline build (no FMA).
