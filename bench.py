@@ -339,6 +339,37 @@ def cv2_primitives_ms(image):
     return res
 
 
+def c4_cpu_arms(c4_data, cores):
+    """C4 on the host cores, bounded samples of the same 8000 x 8000 problem, all threads (ctypes releases the GIL): the reference's own
+    distance path (FeatureDescriptor::distance -> ORBDistance::distance, one cv::Mat clone per call: FeatureDescriptor.h:31) and a lean
+    scan (contiguous descriptors, hardware popcount); both with the best / second-best bookkeeping, checked against the GPU's answer."""
+    from oracle import ref as R
+    da, db, gpu_idx, gpu_best = c4_data
+    out = {}
+    for name, lean, per_thread, reps in (("reference_distance_path", False, 400, 1), ("lean_popcount", True, 500, 20)):
+        nqs = min(len(da), cores * per_thread)
+        bounds = [nqs * i // cores for i in range(cores + 1)]
+        res = [None] * cores
+
+        def work(i):
+            a, b = bounds[i], bounds[i + 1]
+            for _ in range(reps):
+                if b > a:
+                    res[i] = R.bf_scan(da[a:b], db, lean)
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        dt = time.perf_counter() - t0
+        idx = np.concatenate([r[0] for r in res if r is not None]); best = np.concatenate([r[1] for r in res if r is not None])
+        out[name] = {"distance_evals_per_s": reps * nqs * len(db) / dt, "cores": cores,
+                     "sample": f"{nqs} of the 8000 queries x 8000 targets" + (f", {reps} repetitions" if reps > 1 else "") + f" ({dt:.2f} s)",
+                     "agrees_with_gpu": bool(np.array_equal(idx, gpu_idx[:nqs]) and np.array_equal(best, gpu_best[:nqs].astype(np.int32)))}
+    return out
+
+
 def cpu_baseline_block(images, cores, seconds):
     """cpu_baseline object: all-cores throughput of the reference's code (or the port when _ref is absent) on `images`,
     repeated for about `seconds`; plus the labelled side figures."""
@@ -642,6 +673,7 @@ def main():
     # ---- auxiliary line item (config C4, not the headline metric): keyframe-pair brute-force Hamming matching, 8000 x 8000
     # descriptors, BoW acceptance rule (SearchForTriangulation's scan), device-resident
     c4 = None
+    c4_data = None
     try:
         from hyslam_b200 import synth
         nq = nt = 8000
@@ -666,6 +698,7 @@ def main():
         mms = m0.elapsed_time(m1) / reps
         c4 = {"workload": "C4: 8000 x 8000 descriptors, brute force, best/second-best + ratio test", "ms_per_pair_of_keyframes": mms,
               "distance_evals_per_s": nq * nt / (mms * 1e-3), "popc32_per_s": 8 * nq * nt / (mms * 1e-3), "accepted": int(oacc.sum().item())}
+        c4_data = (da, db, obi.cpu().numpy(), ob.cpu().numpy())
         try:      # the POPC32 issue rate measured on a B200 of this pool by tools/popc_bench.cu (profiles/r2_popc_peak.json)
             pk = json.load(open(os.path.join(ROOT, "profiles", "r2_popc_peak.json")))
             c4["popc32_peak_measured_per_s"] = pk["popc_plus_iadd"]["popc_per_s"]
@@ -731,6 +764,8 @@ def main():
         cores = len(os.sched_getaffinity(0))
         sample_pairs = max(1, min(P, cores))
         cpu = cpu_baseline_block(host_batches[0][: 2 * sample_pairs], cores, args.cpu_seconds)
+        if c4_data is not None and isinstance(c4, dict) and "error" not in c4 and ref_available():
+            c4["cpu_baseline"] = c4_cpu_arms(c4_data, cores)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -93,6 +93,17 @@ def hamming(a, b):
     return float(lib().ref_hamming(_p(a), _p(b)))
 
 
+def bf_scan(q, t, lean=False):
+    """brute-force best / second-best scan on the CPU: the reference's own FeatureDescriptor::distance per pair (lean=False) or contiguous
+    descriptors + hardware popcount (lean=True).  Returns (best_idx, best, second)."""
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    bi = np.empty(len(q), np.int32); b = np.empty(len(q), np.int32); s2 = np.empty(len(q), np.int32)
+    L = lib()
+    L.ref_bf_scan.restype = C.c_long
+    L.ref_bf_scan(_p(q), len(q), _p(t), len(t), int(bool(lean)), _p(bi), _p(b), _p(s2))
+    return bi, b, s2
+
+
 def stereo_match(sp, kl, dl, kr, dr):
     kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
     dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)

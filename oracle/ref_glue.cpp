@@ -146,6 +146,44 @@ REF_API float ref_hamming(const uint8_t *a, const uint8_t *b)
     return da.distance(db);
 }
 
+// C4 CPU arms (bench.py c4_match): a brute-force scan of `nq` query descriptors over `nt` targets with the best / second-best
+// bookkeeping of BestMatchBoWCriterion (MatchCriteria.cpp:601-635).  lean = 0: every distance through the reference's own
+// FeatureDescriptor::distance -> ORBDistance::distance (FeatureDescriptor.cpp:14-18, DescriptorDistance.cpp:9-25: a cv::Mat header copy
+// per call, the bit-trick popcount); lean = 1: contiguous descriptors and the hardware popcount.  Returns the number of distances.
+#if defined(__x86_64__)
+__attribute__((target("popcnt")))
+#endif
+REF_API long ref_bf_scan(const uint8_t *q, int nq, const uint8_t *t, int nt, int lean, int32_t *best_idx, int32_t *best, int32_t *second)
+{
+    if (lean) {
+        for (int i = 0; i < nq; i++) {
+            const uint64_t *a = (const uint64_t *)(q + 32 * (size_t)i);
+            int b1 = 256 + 1, b2 = 256 + 1, bi = -1;
+            for (int j = 0; j < nt; j++) {
+                const uint64_t *b = (const uint64_t *)(t + 32 * (size_t)j);
+                const int d = __builtin_popcountll(a[0] ^ b[0]) + __builtin_popcountll(a[1] ^ b[1]) + __builtin_popcountll(a[2] ^ b[2]) + __builtin_popcountll(a[3] ^ b[3]);
+                if (d < b1) { b2 = b1; b1 = d; bi = j; } else if (d < b2) b2 = d;
+            }
+            best_idx[i] = bi; best[i] = b1; second[i] = b2;
+        }
+        return (long)nq * nt;
+    }
+    std::shared_ptr<HYSLAM::DescriptorDistance> dist_func = std::make_shared<HYSLAM::ORBDistance>();
+    std::vector<HYSLAM::FeatureDescriptor> dq, dt;
+    dq.reserve(nq); dt.reserve(nt);
+    for (int i = 0; i < nq; i++) dq.push_back(HYSLAM::FeatureDescriptor(cv::Mat(1, 32, CV_8UC1, (void *)(q + 32 * (size_t)i)), dist_func));
+    for (int j = 0; j < nt; j++) dt.push_back(HYSLAM::FeatureDescriptor(cv::Mat(1, 32, CV_8UC1, (void *)(t + 32 * (size_t)j)), dist_func));
+    for (int i = 0; i < nq; i++) {
+        float b1 = 1e30f, b2 = 1e30f; int bi = -1;
+        for (int j = 0; j < nt; j++) {
+            const float d = dq[i].distance(dt[j]);
+            if (d < b1) { b2 = b1; b1 = d; bi = j; } else if (d < b2) b2 = d;
+        }
+        best_idx[i] = bi; best[i] = (int32_t)b1; second[i] = b2 < 1e29f ? (int32_t)b2 : 257;
+    }
+    return (long)nq * nt;
+}
+
 static std::vector<HYSLAM::FeatureDescriptor> wrap_descriptors(const uint8_t *d, int n, std::shared_ptr<HYSLAM::DescriptorDistance> dist_func)
 {
     std::vector<HYSLAM::FeatureDescriptor> out;
