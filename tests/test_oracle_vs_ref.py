@@ -124,3 +124,15 @@ def test_tie_policy_report():
         assert abs(len(ka) - len(km)) <= 0.01 * len(ka)
     print(f"glibc-malloc vs monotonic arena: identical frames {same_frames}/6, shared keypoints min {min(frac):.4f} mean {np.mean(frac):.4f}")
     assert min(frac) > 0.90
+
+
+def test_bruteforce_scan_arms_agree_with_the_oracle():
+    """bench.py's C4 CPU arms (oracle/ref_glue.cpp ref_bf_scan): the reference's own FeatureDescriptor::distance path and the lean
+    popcount scan must both give the oracle's best index / best / second-best distances."""
+    q = synth.random_descriptors(64, 11)
+    t = np.concatenate([synth.random_descriptors(500, 12), q[:16] ^ 1])      # a few near-duplicates: ties and tiny distances
+    bi, b, s, _ = O.match_csr(q, t, mode=1, thr=50.0, ratio=0.6)
+    for lean in (False, True):
+        ri, rb, rs = R.bf_scan(q, t, lean)
+        assert np.array_equal(ri, bi) and np.array_equal(rb, np.asarray(b, np.int32))
+        assert np.array_equal(rs, np.asarray(s, np.int32))
