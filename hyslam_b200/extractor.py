@@ -103,13 +103,15 @@ class ORBExtractor:
 
     def extract_batch(self, images, capacity=None):
         """Throughput form over a [B,H,W] uint8 host array.  Returns (kps[B,cap], desc[B,cap,32], counts[B])."""
-        images = np.ascontiguousarray(images, np.uint8)
+        if images.dtype != np.uint8 or images.ndim != 3 or images.strides[2] != 1 or images.strides[1] < images.shape[2]:
+            images = np.ascontiguousarray(images, np.uint8)      # pitched views (rows contiguous, any row / image stride) go through as they are
         B, H, W = images.shape
         cap = capacity or self.default_capacity()
         kps = np.empty((B, cap), F.KP_DTYPE)
         desc = np.empty((B, cap, 32), np.uint8)
         counts = np.zeros(B, np.int32)
-        F.check(F.lib().hyorb_extract_batch_host(self._h, F.ptr(images), B, W, H, W, W * H, F.ptr(kps), F.ptr(desc), cap, F.ptr(counts)))
+        F.check(F.lib().hyorb_extract_batch_host(self._h, F.ptr(images), B, W, H, images.strides[1], images.strides[0], F.ptr(kps), F.ptr(desc), cap,
+                                                 F.ptr(counts)))
         return kps, desc, counts
 
     def extract_batch_device(self, d_images, B, W, H, stride, image_stride, d_kps, d_desc, capacity, d_counts):

@@ -236,3 +236,20 @@ def test_adversarial_textures_match_oracle(name):
     assert_kps_equal(k, ok, name)
     assert np.array_equal(d, od)
     ex.close()
+
+
+def test_pitched_host_batch_equals_dense_host_batch():
+    """Host frames with a 16-byte-aligned row pitch are read in place through TMA (no device-side repack); dense odd-width rows are
+    repacked on the device.  Both layouts of the same frames must give the same bytes (large-batch path, > 8 images)."""
+    imgs = np.stack([synth.noise_image(200, 333, 60 + i) for i in range(10)])
+    pitch = (333 + 15) & ~15
+    store = np.zeros((10, 200, pitch), np.uint8)
+    store[:, :, :333] = imgs
+    ex = hb.ORBExtractor(_settings(500, nlevels=5))
+    kd, dd, cd = ex.extract_batch(imgs, capacity=1024)
+    kp, dp, cp = ex.extract_batch(store[:, :, :333], capacity=1024)
+    assert np.array_equal(cd, cp) and cd.min() > 100
+    for i in range(10):
+        assert_kps_equal(kp[i, :cp[i]], kd[i, :cd[i]], f"image {i}")
+        assert np.array_equal(dp[i, :cp[i]], dd[i, :cd[i]])
+    ex.close()
